@@ -1,0 +1,243 @@
+"""ctypes binding to oracle/_ref/libswiftref.so -- TEST INFRASTRUCTURE ONLY.
+
+The library is the UNMODIFIED reference (ajm/swiftlink) compiled by oracle/Makefile plus the
+dump driver oracle/ref_driver.cc.  Only tests/, tests/golden/make_golden.py, bench.py's
+reference/cpu_baseline legs and __graft_entry__.smoke() may import this module; the product
+package (swiftlink_b200/) never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+LIB_PATH = os.path.join(REF_DIR, "libswiftref.so")
+EXAMPLES = os.path.join(REF_DIR, "examples")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_peel_cost.restype = C.c_uint
+        for name in ("ref_dg_likelihood", "ref_dg_recombination_prob", "ref_dg_marker_transmission",
+                     "ref_chain_run", "ref_ls_forward", "ref_calc_trait_prob", "ref_bench_lsweeps",
+                     "ref_bench_lodpasses"):
+            getattr(L, name).restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _ip(a):
+    return _p(a, C.c_int)
+
+
+def _dp(a):
+    return _p(a, C.c_double)
+
+
+def set_threads(n):
+    lib().ref_set_threads(C.c_int(n))
+
+
+def seed(s):
+    lib().ref_seed(C.c_uint(s))
+
+
+def example(name):
+    return tuple(os.path.join(EXAMPLES, "%s.%s" % (name, ext)) for ext in ("ped", "map", "dat"))
+
+
+class Ref(object):
+    """One pedigree loaded through the reference's own parsers."""
+
+    def __init__(self, ped, mapf, dat, sex_linked=False, lodscores=5):
+        self.L = lib()
+        self.h = self.L.ref_open(ped.encode(), mapf.encode(), dat.encode(), int(sex_linked), int(lodscores))
+        if not self.h:
+            raise RuntimeError("reference failed to parse %s" % ped)
+        self.h = C.c_void_p(self.h)
+        d = np.zeros(6, dtype=np.int32)
+        self.L.ref_dims(self.h, _ip(d))
+        self.N, self.F, self.M, self.nlod, self.sex_linked, self.leaves = [int(x) for x in d]
+
+    def close(self):
+        if self.h:
+            self.L.ref_close(self.h)
+            self.h = None
+
+    # ---- inputs -------------------------------------------------------------------
+    def person_table(self):
+        N = self.N
+        mother = np.zeros(N, np.int32); father = np.zeros(N, np.int32); sex = np.zeros(N, np.int32)
+        aff = np.zeros(N, np.int32); typed = np.zeros(N, np.int32); dprob = np.zeros((N, 4))
+        self.L.ref_person_table(self.h, _ip(mother), _ip(father), _ip(sex), _ip(aff), _ip(typed), _dp(dprob))
+        return dict(mother=mother, father=father, sex=sex, affection=aff, typed=typed, disease_prob=dprob)
+
+    def person_names(self):
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(self.N):
+            self.L.ref_person_name(self.h, i, buf, 256)
+            out.append(buf.value.decode())
+        return out
+
+    def marker_names(self):
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(self.M):
+            self.L.ref_marker_name(self.h, i, buf, 256)
+            out.append(buf.value.decode())
+        return out
+
+    def genotypes(self):
+        g = np.zeros((self.N, self.M), np.int32)
+        self.L.ref_genotypes(self.h, _ip(g))
+        return g
+
+    def marker_trait_prob(self):
+        t = np.zeros((self.N, self.M, 4))
+        self.L.ref_marker_trait_prob(self.h, _dp(t))
+        return t
+
+    def map_table(self):
+        M = self.M
+        gdist = np.zeros(M); minor = np.zeros(M); prob = np.zeros((M, 4)); xprob = np.zeros((M, 4))
+        theta = np.zeros(M - 1); partial = np.zeros(M - 1)
+        self.L.ref_map_table(self.h, _dp(gdist), _dp(minor), _dp(prob), _dp(xprob), _dp(theta), _dp(partial))
+        return dict(gdist=gdist, minor=minor, prob=prob, xprob=xprob, theta=theta, partial=partial)
+
+    def disease_model(self):
+        d = np.zeros(4)
+        self.L.ref_disease_model(self.h, _dp(d))
+        return dict(freq=float(d[0]), penetrance=d[1:].copy())
+
+    # ---- plan ---------------------------------------------------------------------
+    def build_peel(self, iterations=1000000):
+        self.L.ref_build_peel(self.h, int(iterations))
+
+    def set_peel(self, seq):
+        s = np.ascontiguousarray(seq, dtype=np.uint32)
+        assert s.shape == (self.N,)
+        return bool(self.L.ref_set_peel(self.h, _p(s, C.c_uint)))
+
+    def elim_masks(self):
+        m = np.zeros((self.M, self.N), np.int32)
+        self.L.ref_elim_masks(self.h, _ip(m))
+        return m
+
+    def num_ops(self):
+        return int(self.L.ref_num_ops(self.h))
+
+    def peel_cost(self):
+        return int(self.L.ref_peel_cost(self.h))
+
+    def ops(self):
+        out = []
+        N = self.N
+        for i in range(self.num_ops()):
+            info = np.zeros(5, np.int32); cut = np.zeros(N, np.int32); prev = np.zeros(N, np.int32)
+            kids = np.zeros(N, np.int32)
+            self.L.ref_op_info(self.h, i, _ip(info), _ip(cut), _ip(prev), _ip(kids))
+            out.append(dict(type=int(info[0]), peelnode=int(info[1]), cutset=cut[:info[2]].tolist(),
+                            previous=prev[:info[3]].tolist(), children=kids[:info[4]].tolist()))
+        return out
+
+    def op_indices(self, i, which, locus=0):
+        n = int(self.L.ref_op_indices(self.h, i, which, locus, None, 0))
+        buf = np.zeros(max(n, 1), np.int32)
+        self.L.ref_op_indices(self.h, i, which, locus, _ip(buf), n)
+        return buf[:n].copy()
+
+    # ---- descent graph --------------------------------------------------------------
+    def dg_random(self):
+        return bool(self.L.ref_dg_random(self.h))
+
+    def dg_get(self):
+        g = np.zeros((self.M, self.N, 2), np.int32)
+        self.L.ref_dg_get(self.h, _ip(g))
+        return g
+
+    def dg_set(self, g):
+        g = np.ascontiguousarray(g, dtype=np.int32)
+        assert g.shape == (self.M, self.N, 2)
+        self.L.ref_dg_set(self.h, _ip(g))
+
+    def dg_likelihood(self):
+        return float(self.L.ref_dg_likelihood(self.h))
+
+    def dg_recombination_prob(self, locus):
+        return float(self.L.ref_dg_recombination_prob(self.h, int(locus)))
+
+    def dg_marker_transmission(self):
+        return float(self.L.ref_dg_marker_transmission(self.h))
+
+    def sequential_imputation(self, iterations):
+        self.L.ref_sequential_imputation(self.h, int(iterations))
+
+    def chain_run(self, burnin, iterations, scoring_period=10, lsampler_prob=0.5):
+        n = (self.M - 1) * self.nlod
+        raw = np.zeros(n); lod = np.zeros(n); cnt = C.c_int(0)
+        tp = self.L.ref_chain_run(self.h, int(burnin), int(iterations), int(scoring_period),
+                                  C.c_double(lsampler_prob), _dp(raw), _dp(lod), C.byref(cnt))
+        return dict(trait_prob=float(tp), raw=raw.reshape(self.M - 1, self.nlod),
+                    lod=lod.reshape(self.M - 1, self.nlod), count=cnt.value)
+
+    # ---- L-sampler ------------------------------------------------------------------
+    def matrix_sizes(self):
+        cs = [len(o["cutset"]) for o in self.ops()]
+        return [4 ** c for c in cs], [4 ** (c + 1) for c in cs]
+
+    def ls_forward(self, locus, mode=0, ignore_left=False, ignore_right=False):
+        ms, ps = self.matrix_sizes()
+        mat = np.zeros(sum(ms)); pre = np.zeros(sum(ps))
+        res = self.L.ref_ls_forward(self.h, int(locus), int(mode), int(ignore_left), int(ignore_right),
+                                    _dp(mat), _dp(pre))
+        return float(res), mat, pre
+
+    def ls_step(self, locus):
+        self.L.ref_ls_step(self.h, int(locus))
+
+    def ls_backward_trace(self):
+        pmk = np.zeros(self.N, np.int32); dist = np.zeros((self.num_ops(), 4))
+        self.L.ref_ls_backward_trace(self.h, _ip(pmk), _dp(dist))
+        return pmk, dist
+
+    def ls_sample_indicators(self, pmk):
+        p = np.ascontiguousarray(pmk, dtype=np.int32)
+        self.L.ref_ls_sample_indicators(self.h, _ip(p))
+
+    # ---- LOD ------------------------------------------------------------------------
+    def calc_trait_prob(self):
+        return float(self.L.ref_calc_trait_prob(self.h))
+
+    def lod_interval(self, interval, dump_k=-1):
+        res = np.zeros(self.nlod); prob = np.zeros(self.nlod)
+        mat = None
+        if dump_k >= 0:
+            ms, _ = self.matrix_sizes()
+            mat = np.zeros(sum(ms))
+        self.L.ref_lod_interval(self.h, int(interval), _dp(res), _dp(prob), int(dump_k),
+                                _dp(mat) if mat is not None else None)
+        return res, prob, mat
+
+    # ---- timing ---------------------------------------------------------------------
+    def bench_lsweeps(self, reps, lgroups=-1):
+        return float(self.L.ref_bench_lsweeps(self.h, int(reps), int(lgroups)))
+
+    def bench_lodpasses(self, reps):
+        return float(self.L.ref_bench_lodpasses(self.h, int(reps)))
