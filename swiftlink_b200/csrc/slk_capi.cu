@@ -1,0 +1,642 @@
+// slk_capi.cu -- implementation of the C ABI in include/swiftlink_b200.h: plan upload, chain
+// state, kernel launches.  There is deliberately no CPU fallback anywhere in this file: if no
+// sm_100 device is usable every compute entry point fails with SLK_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swiftlink_b200.h"
+#include "slk_plan.h"
+#include "slk_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+    return fail(SLK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+
+template<typename T>
+cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& owned) {
+    void* p = 0;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if(e != cudaSuccess) return e;
+    owned.push_back(p);
+    if(!v.empty()) {
+        e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if(e != cudaSuccess) return e;
+    }
+    *out = (const T*) p;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+struct slk_plan {
+    int device;
+    int sm_count;
+    slk::HostPlan host;
+    SlkDevPlan dev;
+    std::vector<void*> owned;
+    int ls_blocks_per_sm, lod_blocks_per_sm;
+    int ls_cta_smem, lod_cta_smem;
+};
+
+struct slk_chain {
+    slk_plan* plan;
+    uint64_t seed;
+    uint32_t chain_id;
+    cudaStream_t own_stream, stream;
+    uint8_t* dgp;
+    int32_t* dg_staging;          // device int32[M][N][2] for upload/download conversion
+    double* lod;
+    double* lod_out;
+    double* gscratch;
+    size_t gscratch_doubles;
+    int* err;                     // device [4]
+    int32_t count;                // scoring passes (LODscores::count)
+    // debug buffers (allocated on first use)
+    double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
+};
+
+namespace {
+
+template<int T> void launch_ls(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
+    slk_lsampler_kernel<T><<<grid, cta, smem, s>>>(L);
+}
+template<int T> void launch_lod(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
+    slk_lodscore_kernel<T><<<grid, cta, smem, s>>>(L);
+}
+
+template<int T> cudaError_t prep_kernels(int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
+    cudaError_t e;
+    if(ls) {
+        e = cudaFuncSetAttribute(slk_lsampler_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ls_smem);
+        if(e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ls_occ, slk_lsampler_kernel<T>, ls_cta, ls_smem);
+        if(e != cudaSuccess) return e;
+    }
+    if(lod) {
+        e = cudaFuncSetAttribute(slk_lodscore_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, lod_smem);
+        if(e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(lod_occ, slk_lodscore_kernel<T>, lod_cta, lod_smem);
+        if(e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t prep_by_team(int team, int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
+    switch(team) {
+        case 32:  return prep_kernels<32>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
+        case 64:  return prep_kernels<64>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
+        case 128: return prep_kernels<128>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
+        case 256: return prep_kernels<256>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
+        default:  return prep_kernels<512>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
+    }
+}
+
+void launch_ls_by_team(int team, const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
+    switch(team) {
+        case 32:  launch_ls<32>(L, grid, cta, smem, s); break;
+        case 64:  launch_ls<64>(L, grid, cta, smem, s); break;
+        case 128: launch_ls<128>(L, grid, cta, smem, s); break;
+        case 256: launch_ls<256>(L, grid, cta, smem, s); break;
+        default:  launch_ls<512>(L, grid, cta, smem, s); break;
+    }
+}
+
+void launch_lod_by_team(int team, const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
+    switch(team) {
+        case 32:  launch_lod<32>(L, grid, cta, smem, s); break;
+        case 64:  launch_lod<64>(L, grid, cta, smem, s); break;
+        case 128: launch_lod<128>(L, grid, cta, smem, s); break;
+        case 256: launch_lod<256>(L, grid, cta, smem, s); break;
+        default:  launch_lod<512>(L, grid, cta, smem, s); break;
+    }
+}
+
+int grid_for(int nunits, int teams_per_cta, int blocks_per_sm, int sm_count) {
+    int need = (nunits + teams_per_cta - 1) / teams_per_cta;
+    int cap = blocks_per_sm * sm_count;
+    int g = need < cap ? need : cap;
+    return g < 1 ? 1 : g;
+}
+
+SlkLaunch base_launch(slk_chain* c) {
+    SlkLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.plan = c->plan->dev;
+    L.dgp = c->dgp;
+    L.lod = c->lod;
+    L.gscratch = c->gscratch;
+    L.err = c->err;
+    L.seed = c->seed;
+    L.chain = c->chain_id;
+    L.window = 2;
+    L.dump_k = -1;
+    return L;
+}
+
+int check_device_error(slk_chain* c) {
+    int h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, c->err, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if(e != cudaSuccess) return fail(SLK_ERR_CUDA, "device error: %s", cudaGetErrorString(e));
+    if(h[0] != 0) {
+        cudaMemsetAsync(c->err, 0, 4 * sizeof(int), c->stream);
+        if(h[0] == SLK_ERR_ZERO_LIKELIHOOD)
+            return fail(h[0], "likelihood is zero at locus %d (check penetrance function?)", h[1]);
+        return fail(h[0], "intermediate state had a likelihood of 0.0 or less (lod score unit %d)", h[1]);
+    }
+    return SLK_OK;
+}
+
+int ensure_debug(slk_chain* c) {
+    if(c->dbg_mat) return SLK_OK;
+    const slk::HostPlan& hp = c->plan->host;
+    CU(cudaMalloc((void**) &c->dbg_mat, sizeof(double) * hp.sum_cells));
+    CU(cudaMalloc((void**) &c->dbg_pre, sizeof(double) * hp.sum_presum));
+    CU(cudaMalloc((void**) &c->dbg_dist4, sizeof(double) * 4 * hp.nops));
+    CU(cudaMalloc((void**) &c->dbg_pmk, sizeof(int) * hp.N));
+    CU(cudaMalloc((void**) &c->dbg_res, sizeof(double) * (hp.nlod + 1)));
+    CU(cudaMalloc((void**) &c->dbg_prob, sizeof(double) * (hp.nlod + 1)));
+    return SLK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int slk_abi_version(void) { return SLK_ABI_VERSION; }
+
+const char* slk_last_error(void) { return g_error.c_str(); }
+
+int slk_device_count(void) {
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
+    if(!problem || !out) return fail(SLK_ERR_INVALID, "null argument");
+    *out = 0;
+    slk_plan* p = new slk_plan();
+    std::string err;
+    if(!slk::build_plan(*problem, p->host, err)) {
+        delete p;
+        return fail(SLK_ERR_INVALID, "%s", err.c_str());
+    }
+    int ndev = slk_device_count();
+    if(ndev == 0 || device < 0 || device >= ndev) {
+        delete p;
+        return fail(SLK_ERR_NO_DEVICE, "no usable CUDA device %d (found %d): this library has no CPU path", device, ndev);
+    }
+    p->device = device;
+    cudaDeviceProp prop;
+    if(cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete p;
+        return fail(SLK_ERR_CUDA, "cannot select device %d", device);
+    }
+    if(prop.major < 10) {
+        delete p;
+        return fail(SLK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    p->sm_count = prop.multiProcessorCount;
+
+    const slk::HostPlan& h = p->host;
+    SlkDevPlan& d = p->dev;
+    memset(&d, 0, sizeof(d));
+    d.N = h.N; d.F = h.F; d.M = h.M; d.nlod = h.nlod; d.sex_linked = h.sex_linked; d.nops = h.nops; d.last_op = h.last_op;
+    d.marker_transmission = h.marker_transmission;
+    cudaError_t e = cudaSuccess;
+#define UP(field, vec) if(e == cudaSuccess) e = upload(vec, &d.field, p->owned)
+    UP(mother, h.mother); UP(father, h.father); UP(male, h.male); UP(disease_prob, h.disease_prob);
+    UP(gcode, h.gcode); UP(fprior, h.fprior); UP(theta, h.theta); UP(partial, h.partial);
+    UP(log_theta, h.log_theta); UP(log_1mtheta, h.log_1mtheta);
+    for(int k = 0; k < 2; ++k) {
+        const slk::HostProgram& hp = k ? h.lod : h.ls;
+        SlkProgram& dp = k ? d.lod : d.ls;
+#define UPP(field) if(e == cudaSuccess) e = upload(hp.field, &dp.field, p->owned)
+        UPP(stream); UPP(op_start); UPP(items); UPP(flevel_start); UPP(bops); UPP(blevel_start);
+#undef UPP
+        dp.stream_words = (int) hp.stream.size();
+        dp.n_items = (int) hp.items.size();
+        dp.n_flevels = (int) hp.flevel_start.size() - 1;
+        dp.n_blevels = (int) hp.blevel_start.size() - 1;
+        dp.arena_doubles = hp.arena_doubles;
+        dp.smem_doubles = hp.smem_doubles;
+        dp.team_threads = hp.team_threads;
+        dp.cta_threads = hp.cta_threads;
+        dp.prog_smem_bytes = hp.prog_smem_bytes;
+        dp.team_smem_bytes = hp.team_smem_bytes;
+    }
+#undef UP
+    if(e != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e);
+        slk_plan_destroy(p);
+        return fail(SLK_ERR_CUDA, "plan upload failed: %s", msg.c_str());
+    }
+
+    p->ls_cta_smem = d.ls.prog_smem_bytes + (d.ls.cta_threads / d.ls.team_threads) * d.ls.team_smem_bytes;
+    p->lod_cta_smem = d.lod.prog_smem_bytes + (d.lod.cta_threads / d.lod.team_threads) * d.lod.team_smem_bytes;
+    if(p->ls_cta_smem > slk::kSmemPerBlockMax || p->lod_cta_smem > slk::kSmemPerBlockMax) {
+        slk_plan_destroy(p);
+        return fail(SLK_ERR_UNSUPPORTED, "peel program needs %d / %d bytes of shared memory per CTA", p->ls_cta_smem, p->lod_cta_smem);
+    }
+    p->ls_blocks_per_sm = p->lod_blocks_per_sm = 1;
+    e = prep_by_team(d.ls.team_threads, p->ls_cta_smem, 0, d.ls.cta_threads, 0, &p->ls_blocks_per_sm, 0, true, false);
+    if(e == cudaSuccess)
+        e = prep_by_team(d.lod.team_threads, 0, p->lod_cta_smem, 0, d.lod.cta_threads, 0, &p->lod_blocks_per_sm, false, true);
+    if(e != cudaSuccess || p->ls_blocks_per_sm < 1 || p->lod_blocks_per_sm < 1) {
+        std::string msg = cudaGetErrorString(e);
+        slk_plan_destroy(p);
+        return fail(SLK_ERR_CUDA, "kernel configuration failed: %s", msg.c_str());
+    }
+    *out = p;
+    return SLK_OK;
+}
+
+void slk_plan_destroy(slk_plan* p) {
+    if(!p) return;
+    for(size_t i = 0; i < p->owned.size(); ++i) cudaFree(p->owned[i]);
+    delete p;
+}
+
+static int fill_stats(const slk::HostPlan& h, const slk_plan* p, double* out, int cap) {
+    double v[20] = {
+        (double) h.nops, (double) h.sum_cells, (double) h.sum_presum, h.flops_ls, h.flops_lod,
+        (double)(h.ls.flevel_start.size() - 1), (double)(h.ls.blevel_start.size() - 1),
+        (double)(h.lod.flevel_start.size() - 1), (double) h.ls.arena_doubles, (double) h.lod.arena_doubles,
+        (double) h.lod.valid_cells, (double) h.max_cutset, (double) h.ls.team_threads, (double) h.lod.team_threads,
+        (double) h.ls.smem_doubles, (double) h.lod.smem_doubles,
+        p ? (double) p->ls_blocks_per_sm : 0.0, p ? (double) p->lod_blocks_per_sm : 0.0,
+        p ? (double) p->ls_cta_smem : 0.0, p ? (double) p->lod_cta_smem : 0.0
+    };
+    int n = cap < 20 ? cap : 20;
+    for(int i = 0; i < n; ++i) out[i] = v[i];
+    return n;
+}
+
+int slk_plan_stats(const slk_plan* p, double* out, int cap) {
+    if(!p || !out) return 0;
+    return fill_stats(p->host, p, out, cap);
+}
+
+int slk_plan_validate(const slk_problem* problem, double* stats, int cap) {
+    if(!problem) return fail(SLK_ERR_INVALID, "null argument");
+    slk::HostPlan hp;
+    std::string err;
+    if(!slk::build_plan(*problem, hp, err)) return fail(SLK_ERR_INVALID, "%s", err.c_str());
+    if(stats) fill_stats(hp, 0, stats, cap);
+    return SLK_OK;
+}
+
+int slk_chain_create(slk_plan* plan, uint64_t seed, uint32_t chain_id, slk_chain** out) {
+    if(!plan || !out) return fail(SLK_ERR_INVALID, "null argument");
+    *out = 0;
+    CU(cudaSetDevice(plan->device));
+    slk_chain* c = new slk_chain();
+    memset(c, 0, sizeof(*c));
+    c->plan = plan; c->seed = seed; c->chain_id = chain_id;
+    const SlkDevPlan& d = plan->dev;
+    const size_t cells = (size_t) d.M * d.N;
+    const int nlod_total = (d.M - 1) * d.nlod;
+    // global arena slab: one slice per resident team of either kernel
+    size_t ls_teams = (size_t) plan->ls_blocks_per_sm * plan->sm_count * (d.ls.cta_threads / d.ls.team_threads);
+    size_t lod_teams = (size_t) plan->lod_blocks_per_sm * plan->sm_count * (d.lod.cta_threads / d.lod.team_threads);
+    size_t sc = std::max(ls_teams * (size_t)(d.ls.arena_doubles - d.ls.smem_doubles),
+                         lod_teams * (size_t)(d.lod.arena_doubles - d.lod.smem_doubles));
+    c->gscratch_doubles = sc;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    c->stream = c->own_stream;
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->dgp, cells);
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->dg_staging, cells * 2 * sizeof(int32_t));
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->lod, sizeof(double) * nlod_total);
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->lod_out, sizeof(double) * nlod_total);
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->gscratch, sizeof(double) * std::max<size_t>(sc, 2));
+    if(e == cudaSuccess) e = cudaMalloc((void**) &c->err, 4 * sizeof(int));
+    if(e == cudaSuccess) e = cudaMemset(c->err, 0, 4 * sizeof(int));
+    if(e == cudaSuccess) e = cudaMemset(c->dgp, 0, cells);
+    if(e != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e);
+        slk_chain_destroy(c);
+        return fail(SLK_ERR_CUDA, "chain allocation failed: %s", msg.c_str());
+    }
+    *out = c;
+    return slk_lodscore_init(c);
+}
+
+void slk_chain_destroy(slk_chain* c) {
+    if(!c) return;
+    cudaSetDevice(c->plan->device);
+    if(c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    cudaFree(c->dgp); cudaFree(c->dg_staging); cudaFree(c->lod); cudaFree(c->lod_out);
+    cudaFree(c->gscratch); cudaFree(c->err);
+    cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
+    cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
+    delete c;
+}
+
+int slk_chain_set_stream(slk_chain* c, void* cuda_stream) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t) cuda_stream : c->own_stream;
+    return SLK_OK;
+}
+
+int slk_chain_sync(slk_chain* c) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    CU(cudaSetDevice(c->plan->device));
+    return check_device_error(c);
+}
+
+int slk_dg_upload(slk_chain* c, const int32_t* dg) {
+    if(!c || !dg) return fail(SLK_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->plan->device));
+    const size_t cells = (size_t) c->plan->dev.M * c->plan->dev.N;
+    CU(cudaMemcpyAsync(c->dg_staging, dg, cells * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    slk_dg_pack_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(c->dg_staging, c->dgp, cells);
+    CU(cudaGetLastError());
+    // the caller may reuse its buffer as soon as we return (GPULodscores::calculate uses a
+    // synchronous copy for the same reason, gpu_lodscores.cc:598-607)
+    CU(cudaStreamSynchronize(c->stream));
+    return SLK_OK;
+}
+
+int slk_dg_download(slk_chain* c, int32_t* dg) {
+    if(!c || !dg) return fail(SLK_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->plan->device));
+    const size_t cells = (size_t) c->plan->dev.M * c->plan->dev.N;
+    slk_dg_unpack_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(c->dgp, c->dg_staging, cells);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dg, c->dg_staging, cells * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    return check_device_error(c);
+}
+
+int slk_lsampler_window(slk_chain* c, uint64_t iteration, int window_length, int offset) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    if(window_length < 2 || offset < 0 || offset >= window_length)
+        return fail(SLK_ERR_INVALID, "window_length must be >= 2 and 0 <= offset < window_length");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    CU(cudaSetDevice(p->device));
+    SlkLaunch L = base_launch(c);
+    L.iteration = iteration;
+    L.window = window_length;
+    L.offset = offset;
+    L.nunits = (d.M - offset + window_length - 1) / window_length;
+    if(L.nunits <= 0) return SLK_OK;
+    const int tpc = d.ls.cta_threads / d.ls.team_threads;
+    const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
+    launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    return SLK_OK;
+}
+
+int slk_lsampler_sweep(slk_chain* c, uint64_t iteration) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    // same draw as the oracle: first parity class of the sweep
+    const int first = slk_uniform(c->seed, c->chain_id, iteration, 0u, SLK_SLOT_PHASE) < 0.5 ? 0 : 1;
+    int rc = slk_lsampler_window(c, iteration, 2, first);
+    if(rc != SLK_OK) return rc;
+    return slk_lsampler_window(c, iteration, 2, 1 - first);
+}
+
+int slk_lodscore_init(slk_chain* c) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    CU(cudaSetDevice(c->plan->device));
+    const int n = (c->plan->dev.M - 1) * c->plan->dev.nlod;
+    slk_lod_init_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->lod, n);
+    CU(cudaGetLastError());
+    c->count = 0;
+    return SLK_OK;
+}
+
+int slk_lodscore_accumulate(slk_chain* c) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    CU(cudaSetDevice(p->device));
+    SlkLaunch L = base_launch(c);
+    L.accumulate = 1;
+    L.nunits = (d.M - 1) * d.nlod;
+    const int tpc = d.lod.cta_threads / d.lod.team_threads;
+    const int grid = grid_for(L.nunits, tpc, p->lod_blocks_per_sm, p->sm_count);
+    launch_lod_by_team(d.lod.team_threads, L, grid, d.lod.cta_threads, p->lod_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    c->count += 1;
+    return SLK_OK;
+}
+
+int slk_lodscore_read(slk_chain* c, double* raw, int32_t* count) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    CU(cudaSetDevice(c->plan->device));
+    const int n = (c->plan->dev.M - 1) * c->plan->dev.nlod;
+    if(raw) CU(cudaMemcpyAsync(raw, c->lod, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if(count) *count = c->count;
+    return check_device_error(c);
+}
+
+int slk_lodscore_normalise(slk_chain* c, double trait_prob, double* out) {
+    if(!c || !out) return fail(SLK_ERR_INVALID, "null argument");
+    if(c->count < 1) return fail(SLK_ERR_INVALID, "no scoring pass has been accumulated");
+    CU(cudaSetDevice(c->plan->device));
+    const int n = (c->plan->dev.M - 1) * c->plan->dev.nlod;
+    slk_lod_normalise_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->lod, c->lod_out, n, log((double) c->count), trait_prob);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->lod_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    return check_device_error(c);
+}
+
+int slk_trait_likelihood(slk_plan* plan, double* log_prob) {
+    if(!plan || !log_prob) return fail(SLK_ERR_INVALID, "null argument");
+    slk_chain* c = 0;
+    int rc = slk_chain_create(plan, 0, 0, &c);
+    if(rc != SLK_OK) return rc;
+    rc = ensure_debug(c);
+    if(rc == SLK_OK) {
+        const SlkDevPlan& d = plan->dev;
+        SlkLaunch L = base_launch(c);
+        L.no_dg = 1;
+        L.accumulate = 0;
+        L.nunits = 1;
+        L.dump_result = c->dbg_res;
+        L.dump_prob = c->dbg_prob;
+        launch_lod_by_team(d.lod.team_threads, L, 1, d.lod.cta_threads, plan->lod_cta_smem, c->stream);
+        cudaError_t e = cudaGetLastError();
+        if(e == cudaSuccess) e = cudaMemcpyAsync(log_prob, c->dbg_prob, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if(e != cudaSuccess) rc = fail(SLK_ERR_CUDA, "trait likelihood launch failed: %s", cudaGetErrorString(e));
+        else rc = check_device_error(c);
+    }
+    slk_chain_destroy(c);
+    return rc;
+}
+
+// ---- parity hooks ----------------------------------------------------------------------
+
+static int debug_ls(slk_chain* c, uint64_t iteration, int locus, int il, int ir, bool forward_only,
+                    double* matrices, double* presums, int32_t* pmk, double* dist4, double* result) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    const slk::HostPlan& hp = p->host;
+    if(locus < 0 || locus >= d.M) return fail(SLK_ERR_INVALID, "locus out of range");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_debug(c);
+    if(rc != SLK_OK) return rc;
+    uint8_t* saved = 0;
+    if(forward_only) {
+        // the kernel always completes the update; keep the row so the call has no side effect
+        CU(cudaMalloc((void**) &saved, d.N));
+        CU(cudaMemcpyAsync(saved, c->dgp + (size_t) locus * d.N, d.N, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(c->dbg_mat, 0, sizeof(double) * hp.sum_cells, c->stream));
+    CU(cudaMemsetAsync(c->dbg_pre, 0, sizeof(double) * hp.sum_presum, c->stream));
+    CU(cudaMemsetAsync(c->dbg_dist4, 0, sizeof(double) * 4 * hp.nops, c->stream));
+    CU(cudaMemsetAsync(c->dbg_pmk, 0xff, sizeof(int) * hp.N, c->stream));
+    SlkLaunch L = base_launch(c);
+    L.iteration = iteration;
+    L.window = d.M + 1;
+    L.offset = locus;
+    L.nunits = 1;
+    L.ignore_left = il; L.ignore_right = ir;
+    L.dump_mat = c->dbg_mat; L.dump_pre = c->dbg_pre; L.dump_dist4 = c->dbg_dist4; L.dump_pmk = c->dbg_pmk;
+    L.dump_result = c->dbg_res;
+    launch_ls_by_team(d.ls.team_threads, L, 1, d.ls.cta_threads, p->ls_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    if(forward_only) {
+        CU(cudaMemcpyAsync(c->dgp + (size_t) locus * d.N, saved, d.N, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if(matrices) CU(cudaMemcpyAsync(matrices, c->dbg_mat, sizeof(double) * hp.sum_cells, cudaMemcpyDeviceToHost, c->stream));
+    if(presums)  CU(cudaMemcpyAsync(presums, c->dbg_pre, sizeof(double) * hp.sum_presum, cudaMemcpyDeviceToHost, c->stream));
+    if(pmk)      CU(cudaMemcpyAsync(pmk, c->dbg_pmk, sizeof(int) * hp.N, cudaMemcpyDeviceToHost, c->stream));
+    if(dist4)    CU(cudaMemcpyAsync(dist4, c->dbg_dist4, sizeof(double) * 4 * hp.nops, cudaMemcpyDeviceToHost, c->stream));
+    if(result)   CU(cudaMemcpyAsync(result, c->dbg_res, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if(saved) cudaFree(saved);
+    if(forward_only) {
+        // a zero likelihood is a legitimate answer for the forward hook
+        cudaMemsetAsync(c->err, 0, 4 * sizeof(int), c->stream);
+        return SLK_OK;
+    }
+    return check_device_error(c);
+}
+
+int slk_debug_lsampler_forward(slk_chain* c, int locus, int ignore_left, int ignore_right,
+                               double* matrices, double* presums, double* result) {
+    return debug_ls(c, 0, locus, ignore_left, ignore_right, true, matrices, presums, 0, 0, result);
+}
+
+int slk_debug_lsampler_step(slk_chain* c, uint64_t iteration, int locus, int ignore_left, int ignore_right,
+                            int32_t* pmk, double* dist4, double* result) {
+    return debug_ls(c, iteration, locus, ignore_left, ignore_right, false, 0, 0, pmk, dist4, result);
+}
+
+int slk_debug_lod_interval(slk_chain* c, int interval, double* result, double* prob, int dump_k, double* matrices) {
+    if(!c || !result || !prob) return fail(SLK_ERR_INVALID, "null argument");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    const slk::HostPlan& hp = p->host;
+    if(interval < 0 || interval >= d.M - 1) return fail(SLK_ERR_INVALID, "interval out of range");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_debug(c);
+    if(rc != SLK_OK) return rc;
+    const int tpc = d.lod.cta_threads / d.lod.team_threads;
+    SlkLaunch L = base_launch(c);
+    L.accumulate = 0;
+    L.unit_base = interval * d.nlod;
+    L.nunits = d.nlod;
+    L.dump_result = c->dbg_res;
+    L.dump_prob = c->dbg_prob;
+    launch_lod_by_team(d.lod.team_threads, L, grid_for(L.nunits, tpc, p->lod_blocks_per_sm, p->sm_count),
+                       d.lod.cta_threads, p->lod_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(result, c->dbg_res, sizeof(double) * d.nlod, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(prob, c->dbg_prob, sizeof(double) * d.nlod, cudaMemcpyDeviceToHost, c->stream));
+    if(matrices && dump_k >= 0 && dump_k < d.nlod) {
+        CU(cudaMemsetAsync(c->dbg_mat, 0, sizeof(double) * hp.sum_cells, c->stream));
+        SlkLaunch L2 = L;
+        L2.unit_base = interval * d.nlod + dump_k;
+        L2.nunits = 1;
+        L2.dump_mat = c->dbg_mat;
+        L2.dump_result = c->dbg_res + d.nlod;
+        L2.dump_prob = c->dbg_prob + d.nlod;
+        launch_lod_by_team(d.lod.team_threads, L2, 1, d.lod.cta_threads, p->lod_cta_smem, c->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(matrices, c->dbg_mat, sizeof(double) * hp.sum_cells, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_device_error(c);
+}
+
+int slk_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if(slk_device_count() <= device) return fail(SLK_ERR_NO_DEVICE, "no usable CUDA device %d", device);
+    CU(cudaSetDevice(device));
+    uint32_t* d = 0;
+    CU(cudaMalloc((void**) &d, 16));
+    slk_philox_kernel<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return SLK_OK;
+}
+
+int slk_debug_uniform(int device, uint64_t seed, uint32_t chain, uint64_t iteration, uint32_t locus,
+                      uint32_t slot, double* out) {
+    if(slk_device_count() <= device) return fail(SLK_ERR_NO_DEVICE, "no usable CUDA device %d", device);
+    CU(cudaSetDevice(device));
+    double* d = 0;
+    CU(cudaMalloc((void**) &d, 8));
+    slk_uniform_kernel<<<1, 1>>>(seed, chain, iteration, locus, slot, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return SLK_OK;
+}
+
+int slk_measure_fp64_peak(int device, double* tflops) {
+    if(!tflops) return fail(SLK_ERR_INVALID, "null argument");
+    if(slk_device_count() <= device) return fail(SLK_ERR_NO_DEVICE, "no usable CUDA device %d", device);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 14;
+    double* d = 0;
+    CU(cudaMalloc((void**) &d, sizeof(double) * blocks * threads));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for(int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(a));
+        slk_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double fl = 2.0 * 8.0 * (double) iters * blocks * threads;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if(rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return SLK_OK;
+}
+
+}  // extern "C"

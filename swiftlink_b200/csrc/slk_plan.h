@@ -1,0 +1,55 @@
+// slk_plan.h -- host-side flattening of a peel sequence into the device plan (slk_types.h).
+#ifndef SLK_PLAN_H
+#define SLK_PLAN_H
+
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "swiftlink_b200.h"
+#include "slk_types.h"
+
+namespace slk {
+
+struct HostProgram {
+    std::vector<uint32_t> stream;
+    std::vector<uint16_t> op_start;
+    std::vector<uint32_t> items;
+    std::vector<uint16_t> flevel_start;
+    std::vector<uint16_t> bops;
+    std::vector<uint16_t> blevel_start;
+    std::vector<int> mat_off;        // arena offset per op
+    int arena_doubles;
+    int smem_doubles;
+    int team_threads;
+    int cta_threads;
+    int prog_smem_bytes;
+    int team_smem_bytes;
+    long valid_cells;                // static valid cells (trait) or dense cells (sampler)
+};
+
+struct HostPlan {
+    int N, F, M, nlod, sex_linked, nops, last_op;
+    std::vector<int16_t> mother, father;
+    std::vector<uint8_t> male;
+    std::vector<double> disease_prob;    // [N][4]
+    std::vector<uint8_t> gcode;          // [M][N]
+    std::vector<double> fprior;          // [M][2][4]
+    std::vector<double> theta, partial, log_theta, log_1mtheta;
+    double marker_transmission;
+    std::vector<int> dense_off;          // per op
+    long sum_cells, sum_presum;          // sum 4^c, sum 4^(c+1)
+    double flops_ls, flops_lod;          // SURVEY.md section 8(d) F_L and F_T
+    int max_cutset;
+    HostProgram ls, lod;
+};
+
+// shared-memory budget per SM the layout may assume (bytes); 227 KB on sm_100
+static const int kSmemPerBlockMax = 232448;
+
+// Builds the flattened plan.  Returns false and fills err on a malformed problem.
+bool build_plan(const slk_problem& pb, HostPlan& out, std::string& err);
+
+}  // namespace slk
+
+#endif

@@ -1,0 +1,125 @@
+// slk_types.h -- internal layout of the flattened, device-resident peel plan.
+//
+// The reference keeps one heap object per (op, locus) with pointer-chased members
+// (gpu_lodscores.cc:396-507: ~7M cudaMallocs at 200 ops x 10k loci).  Here the whole plan is a
+// few flat arrays, independent of the number of loci:
+//
+//   program stream   one variable-length record of 32-bit words per peel op (layout below),
+//                    staged once per CTA into shared memory;
+//   items            the forward schedule: ops grouped into dependency levels, each op split
+//                    into chunks of SLK_CHUNK valid cells; one warp executes one item;
+//   bops             the backward (sampling) schedule: ops grouped into levels by "who peels
+//                    my cutset", four lanes per op;
+//   arena            one slab of doubles per team holding every live peel matrix; offsets
+//                    below `smem_doubles` live in shared memory, the rest in an L2-resident
+//                    global scratch slab (only needed when sum 4^c outgrows 227 KB).
+//
+// Two programs are built from the same peel sequence: the sampler program (all matrices live
+// until the backward pass) and the trait program (matrices freed after their single consumer,
+// peeling.h:136-143 / peel_sequence_generator.cc:70-82 guarantee exactly one).
+#ifndef SLK_TYPES_H
+#define SLK_TYPES_H
+
+#include <stdint.h>
+
+#define SLK_CHUNK      128          // valid cells per forward item (4 per lane)
+#define SLK_SLOTS      (SLK_CHUNK / 32)
+#define SLK_POS_PEEL   15           // digit position meaning "the peel node itself"
+#define SLK_NO_SHIFT   0xFF
+
+// ---- program stream record -------------------------------------------------------------
+//  w0  type[0:3) | c[4:8) | nprev[8:12) | nkids[12:16) | peelnode[16:32)
+//  w1  arena offset of this op's matrix (doubles)
+//  w2  dense offset (sum of 4^c of earlier ops, peel order) -- parity dumps only
+//  w3  flags: bit0 = some previous function is keyed on the peel node
+//  w4,w5  static legal masks, 4 bits per cutset digit (trait program: disease_prob != 0;
+//         sampler program: unused, the per-locus masks come from the elimination table)
+//  w6  static legal mask of the peel node (low 4 bits)
+//  then ceil(c/2) words: cutset person ids, two 16-bit ids per word
+//  then per previous function:
+//        word A  arena offset of the consumed matrix
+//        word B  peel_shift[0:8) (SLK_NO_SHIFT if the peel node is not one of its keys) | nruns[8:16)
+//        ceil(nruns/2) words of 16-bit runs: src_shift[0:5) | dst_shift[5:10) | nbits[10:15)
+//  then per child (CHILD_PEEL: the peel node itself; PARENT_PEEL: cutset members that are its
+//  offspring, cutset order):
+//        person[0:16) | kid_pos[16:20) | mat_pos[20:24) | pat_pos[24:28) | male[28]
+#define SLK_REC_HEADER 7
+
+struct SlkProgram {
+    const uint32_t* stream;         // [stream_words]
+    const uint16_t* op_start;       // [nops] word offset of each record
+    const uint32_t* items;          // op[0:16) | chunk[16:32)
+    const uint16_t* flevel_start;   // [n_flevels + 1] into items
+    const uint16_t* bops;           // ops in backward-level order
+    const uint16_t* blevel_start;   // [n_blevels + 1] into bops
+    int stream_words;
+    int n_items;
+    int n_flevels;
+    int n_blevels;
+    int arena_doubles;              // whole arena
+    int smem_doubles;               // arena prefix kept in shared memory
+    int team_threads;               // 32, 64, 128, 256 or 512
+    int cta_threads;
+    int prog_smem_bytes;            // CTA-shared staging of stream/op_start/items/levels
+    int team_smem_bytes;            // per team: arena prefix + tables
+};
+
+struct SlkDevPlan {
+    int N, F, M, nlod, sex_linked, nops;
+    int last_op;                    // op whose 1-cell matrix is the likelihood
+    const int16_t* mother;          // [N] (-1 founders)
+    const int16_t* father;          // [N]
+    const uint8_t* male;            // [N]
+    const double* disease_prob;     // [N][4]
+    const uint8_t* gcode;           // [M][N]: legal mask (trait encoding) | prior class << 4
+    const double* fprior;           // [M][2][4] founder priors (autosomal/female, X male)
+    const double* theta;            // [M-1]
+    const double* partial;          // [M-1]
+    const double* log_theta;        // [M-1] ln theta
+    const double* log_1mtheta;      // [M-1] ln (1 - theta)
+    double marker_transmission;     // descent_graph.cc:22,35
+    SlkProgram ls;                  // sampler program
+    SlkProgram lod;                 // trait program
+};
+
+// Per-team shared-memory layout (byte offsets from the team's base), used by the host to size
+// launches and by the kernels to carve the slab.
+struct SlkTeamLayout {
+    int arena;      // smem_doubles doubles
+    int tables;     // (N-F)*4 doubles: sampler transmission u-values / trait recombination weights
+    int scal;       // 16 doubles of per-unit scalars (thetas, founder priors)
+    int lmw;        // nops x uint64 per-locus legal masks of each op's cutset (sampler)
+    int bytes;      // 4 byte arrays of round16(N): gcode row, dg left, dg right, sampled genotypes
+    int nbytes;     // round16(N)
+    int red;        // 32 ints of reduction scratch
+    int total;
+};
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline SlkTeamLayout slk_team_layout(int N, int F, int nops, int smem_doubles) {
+    SlkTeamLayout L;
+    L.arena = 0;
+    L.tables = (smem_doubles * 8 + 15) & ~15;
+    L.scal = L.tables + (N - F) * 4 * 8;
+    L.lmw = L.scal + 16 * 8;
+    L.bytes = L.lmw + nops * 8;
+    L.nbytes = (N + 15) & ~15;
+    L.red = L.bytes + 4 * L.nbytes;
+    L.total = (L.red + 32 * 4 + 15) & ~15;
+    return L;
+}
+
+// prior classes (person.cc:224-299 collapses to these; see slk_plan.cc)
+enum {
+    SLK_PRIOR_UU = 0,        // (1,0,0,0)
+    SLK_PRIOR_AA = 1,        // (0,1,0,0)
+    SLK_PRIOR_HET = 2,       // (0,0,.5,.5)
+    SLK_PRIOR_FLAT = 3,      // (.25,.25,.25,.25)
+    SLK_PRIOR_XMALE = 4,     // (.5,.5,0,0)
+    SLK_PRIOR_FOUNDER = 5,   // fprior[locus][0]
+    SLK_PRIOR_FOUNDER_X = 6  // fprior[locus][1]
+};
+
+#endif

@@ -1,0 +1,199 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the C oracle on the
+same seeded inputs (bit-exact for peel matrices, sampled genotypes and descent graphs; 1e-12
+relative for log-likelihoods, where the device log() may differ from glibc in the last ulp),
+and against the golden vectors frozen from the compiled reference."""
+import numpy as np
+import pytest
+
+from common import CASES, golden, problem, oracle_problem
+
+pytestmark = pytest.mark.gpu
+
+LOG_TOL = 1e-12          # relative tolerance on ln-likelihood values (north_star allows 1e-9)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from swiftlink_b200 import capi
+    assert capi.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    made = {}
+
+    def get(name, seed=77, chain_id=3):
+        key = (name, seed, chain_id)
+        if key not in made:
+            plan = made.get(("plan", name))
+            if plan is None:
+                plan = capi.Plan(problem(name))
+                made[("plan", name)] = plan
+            made[key] = capi.Chain(plan, seed=seed, chain_id=chain_id)
+        return made[key]
+    yield get
+    for k, v in made.items():
+        if k[0] != "plan":
+            v.close()
+    for k, v in made.items():
+        if k[0] == "plan":
+            v.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dg_roundtrip(gpu, name):
+    ch = gpu(name)
+    for g in golden(name)["dgs"]:
+        ch.dg_upload(g)
+        assert (ch.dg_download() == g).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matrices_bit_exact(gpu, name):
+    """every peel matrix and presum matrix of every locus == oracle (== reference)"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    for gi in range(fx["dgs"].shape[0]):
+        dg = np.ascontiguousarray(fx["dgs"][gi])
+        ch.dg_upload(dg)
+        for l in range(orc.M):
+            r0, m0, p0 = orc.ls_forward(dg, l)
+            r1, m1, p1 = ch.debug_forward(l)
+            assert r0 == r1
+            assert (m0 == m1).all() and (p0 == p1).all(), (name, gi, l)
+        assert (ch.dg_download() == dg).all()          # the forward hook has no side effect
+        # golden vectors straight from the reference
+        for l in fx["sample_loci"]:
+            _, m1, p1 = ch.debug_forward(int(l))
+            assert (m1 == fx["ls_mat_%d_%d" % (gi, l)]).all()
+            assert (p1 == fx["ls_pre_%d_%d" % (gi, l)]).all()
+        # sequential-imputation thetas (sampler_rfunction.h:84-112)
+        _, m1, _ = ch.debug_forward(int(fx["sample_loci"][1]), ignore_left=True, ignore_right=False)
+        assert (m1 == fx["ls_si_mat_%d" % gi]).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_single_locus_steps_match_oracle(gpu, name):
+    """sampling 4-vectors, sampled genotypes and the written indicators, locus by locus"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    dg = np.ascontiguousarray(fx["dgs"][1]).copy()
+    ch.dg_upload(dg)
+    for it in range(3):
+        for l in range(orc.M):
+            ro, pmko, disto = orc.ls_step(dg, l, 77, 3, it)
+            rg, pmkg, distg = ch.debug_step(it, l)
+            assert ro == rg and (pmko == pmkg).all() and (disto == distg).all(), (name, it, l)
+    assert (ch.dg_download() == dg).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sweeps_match_oracle(gpu, name):
+    """whole even/odd sweeps (all loci of a parity class in one launch) == sequential oracle"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    for gi in (0, 2):
+        dg = np.ascontiguousarray(fx["dgs"][gi]).copy()
+        ch.dg_upload(dg)
+        for it in range(100, 108):
+            assert orc.ls_sweep(dg, 77, 3, it) == 0
+            ch.lsampler_sweep(it)
+        assert (ch.dg_download() == dg).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sweep_independent_of_chain_partitioning(gpu, name):
+    """Philox keyed by (chain, iteration, locus): windows of 4 in any order == windows of 2"""
+    fx, ch = golden(name), gpu(name)
+    dg = np.ascontiguousarray(fx["dgs"][2])
+    ch.dg_upload(dg)
+    ch.lsampler_window(5, 2, 0)
+    a = ch.dg_download()
+    ch.dg_upload(dg)
+    ch.lsampler_window(5, 4, 2)
+    ch.lsampler_window(5, 4, 0)
+    assert (ch.dg_download() == a).all()
+    other = gpu(name, seed=77, chain_id=4)
+    other.dg_upload(dg)
+    other.lsampler_window(5, 2, 0)
+    if fx["dgs"].shape[1] > 3:
+        assert not (other.dg_download() == a).all()    # a different chain id draws differently
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lod_positions_match_oracle(gpu, name):
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    for gi in range(fx["dgs"].shape[0]):
+        dg = np.ascontiguousarray(fx["dgs"][gi])
+        ch.dg_upload(dg)
+        for itv in range(orc.M - 1):
+            r0, p0, m0 = orc.lod_interval(dg, itv, 1)
+            r1, p1, m1 = ch.debug_lod_interval(itv, 1)
+            assert (r0 == r1).all(), (name, gi, itv)              # trait likelihoods: bit-exact
+            assert (m0 == m1).all()
+            assert np.abs(p0 - p1).max() <= LOG_TOL * np.abs(p0).max()
+        for itv in fx["sample_intervals"]:
+            r1, p1, m1 = ch.debug_lod_interval(int(itv), 2)
+            assert (r1 == fx["lod_result_%d_%d" % (gi, itv)]).all()
+            assert (m1 == fx["lod_mat_%d_%d" % (gi, itv)]).all()
+            ref = fx["lod_prob_%d_%d" % (gi, itv)]
+            assert np.abs(p1 - ref).max() <= LOG_TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lod_accumulate_and_normalise(gpu, name):
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    ch.lodscore_init()
+    sc = np.zeros((orc.M - 1) * orc.nlod)
+    for k, gi in enumerate((1, 2, 3)):
+        dg = np.ascontiguousarray(fx["dgs"][gi])
+        ch.dg_upload(dg)
+        ch.lodscore_accumulate()
+        orc.lod_pass(dg, sc, k == 0)
+    raw, cnt = ch.lodscore_read()
+    assert cnt == 3
+    assert np.abs(raw.ravel() - sc).max() <= LOG_TOL * np.abs(sc).max()
+    tp = float(fx["trait_prob"])
+    lod = ch.lodscore_normalise(tp)
+    want = (sc - np.log(3.0) - tp) / np.log(10.0)
+    assert np.abs(lod.ravel() - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    ch.lodscore_init()
+    raw, cnt = ch.lodscore_read()
+    assert cnt == 0 and (raw == -np.finfo(np.float64).max).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trait_likelihood(gpu, name):
+    fx, ch = golden(name), gpu(name)
+    got = ch.plan.trait_likelihood()
+    assert abs(got - float(fx["trait_prob"])) <= LOG_TOL * abs(float(fx["trait_prob"]))
+
+
+def test_zero_likelihood_is_reported(gpu):
+    """an impossible marker configuration must surface as SLK_ERR_ZERO_LIKELIHOOD
+    (locus_sampler2.cc:137-142), not as garbage"""
+    from swiftlink_b200 import capi
+    d = dict(problem("loop"))
+    elim = d["elim"].copy()
+    ops = d["ops"]
+    # contradict the data: allow only genotype AA for everyone at locus 1 while the typed
+    # people are heterozygous there
+    elim[1, :] = 1
+    d["elim"] = elim
+    plan = capi.Plan(d)
+    ch = capi.Chain(plan, seed=1)
+    ch.dg_upload(np.ascontiguousarray(golden("loop")["dgs"][1]))
+    ch.lsampler_window(0, 2, 1)
+    with pytest.raises(capi.SlkError) as e:
+        ch.sync()
+    assert e.value.code == capi.ERR_ZERO_LIKELIHOOD
+    ch.sync()                                       # the error is reported once, then cleared
+    ch.close()
+    plan.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_descent_graph_stays_legal_under_sweeps(gpu, name):
+    """size-independent property: after any number of sweeps every locus still has non-zero
+    likelihood under the oracle (the reference's own self-check, locus_sampler2.cc:137-142)"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    ch.dg_upload(np.ascontiguousarray(fx["dgs"][0]))
+    for it in range(200, 260):
+        ch.lsampler_sweep(it)
+    dg = ch.dg_download()
+    assert set(np.unique(dg)) <= {0, 1} and (dg[:, :orc.F, :] == 0).all()
+    for l in range(orc.M):
+        assert orc.ls_forward(dg, l)[0] > 0.0
