@@ -79,6 +79,12 @@ typedef struct {
     const int32_t* father;                     /* [N] */
     const int32_t* sex;                        /* [N] SLK_MALE / SLK_FEMALE / SLK_UNSEXED */
     const int32_t* typed;                      /* [N] Person::istyped() */
+    const int32_t* prior_as_founder;           /* [N] Person::isfounder() AS SEEN BY populate_trait_prob_cache.
+                                                  In the reference this is 1 for every person: the cache is
+                                                  filled while the ped file is parsed (pedigree_parser.cc:153),
+                                                  before parent ids are resolved (pedigree.cc:164-193), so
+                                                  untyped non-founders get the population genotype prior too.
+                                                  NULL means "all 1" (reference behaviour). */
     const uint8_t* genotypes;                  /* [N][M] SLK_UNTYPED.. (Person::get_marker) */
     const double* disease_prob;                /* [N][4] Person::get_disease_prob (person.cc:85-119) */
     const double* marker_prob;                 /* [M][4] Snp::prob   (genetic_map.h:68-74) */

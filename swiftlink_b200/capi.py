@@ -43,6 +43,7 @@ class Problem(C.Structure):
                 ("n_lod", C.c_int32), ("sex_linked", C.c_int32),
                 ("mother", C.POINTER(C.c_int32)), ("father", C.POINTER(C.c_int32)),
                 ("sex", C.POINTER(C.c_int32)), ("typed", C.POINTER(C.c_int32)),
+                ("prior_as_founder", C.POINTER(C.c_int32)),
                 ("genotypes", C.POINTER(C.c_uint8)), ("disease_prob", C.POINTER(C.c_double)),
                 ("marker_prob", C.POINTER(C.c_double)), ("marker_xprob", C.POINTER(C.c_double)),
                 ("theta", C.POINTER(C.c_double)), ("partial_theta", C.POINTER(C.c_double)),
@@ -93,6 +94,8 @@ def make_problem(d):
     keep["father"] = np.ascontiguousarray(d["father"], np.int32)
     keep["sex"] = np.ascontiguousarray(d["sex"], np.int32)
     keep["typed"] = np.ascontiguousarray(d["typed"], np.int32)
+    paf = d.get("prior_as_founder")
+    keep["paf"] = None if paf is None else np.ascontiguousarray(paf, np.int32)
     keep["genotypes"] = np.ascontiguousarray(d["genotypes"], np.uint8).reshape(N, M)
     keep["disease_prob"] = np.ascontiguousarray(d["disease_prob"], np.float64)
     keep["mapprob"] = np.ascontiguousarray(d["mapprob"], np.float64)
@@ -117,6 +120,7 @@ def make_problem(d):
     p = Problem(N, int(d["F"]), M, int(d["nlod"]), int(d["sex_linked"]),
                 _ptr(keep["mother"], C.c_int32), _ptr(keep["father"], C.c_int32),
                 _ptr(keep["sex"], C.c_int32), _ptr(keep["typed"], C.c_int32),
+                _ptr(keep["paf"], C.c_int32) if keep["paf"] is not None else None,
                 _ptr(keep["genotypes"], C.c_uint8), _ptr(keep["disease_prob"], C.c_double),
                 _ptr(keep["mapprob"], C.c_double), _ptr(keep["mapxprob"], C.c_double),
                 _ptr(keep["theta"], C.c_double), _ptr(keep["partial"], C.c_double),

@@ -1,0 +1,99 @@
+// gpu.cc -- GPULodscores and GPUMarkovChain on top of the C ABI.  Same public surface as the
+// reference's gpu_lodscores.h:63-120 and gpu_markov_chain.h:76,125; errors print and abort()
+// as CUDA_CALLANDTEST does (gpu_lodscores.cc:30-37).  Unlike the reference's destructor
+// (gpu_lodscores.h:95-99) nothing here calls cudaDeviceReset(): several instances can coexist
+// in one process, one per GPU.
+#include "swiftlink_host.h"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace swiftlink {
+
+static void die_on(int rc, const char* what) {
+    if(rc != SLK_OK) {
+        fprintf(stderr, "error: %s: %s\n", what, slk_last_error());
+        abort();
+    }
+}
+
+GPULodscores::GPULodscores(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, double trait_prob) :
+    ped(ped), map(map), psg(psg), options(options), trait_likelihood(trait_prob), plan(0), chain(0), owns_plan(true) {
+    flatten_problem(*ped, *map, *psg, options.sex_linked, flat);
+    die_on(slk_plan_create(&flat.desc, options.device, &plan), "GPULodscores: plan");
+    die_on(slk_chain_create(plan, options.seed, 0, &chain), "GPULodscores: chain");
+}
+
+GPULodscores::~GPULodscores() {
+    slk_chain_destroy(chain);
+    if(owns_plan) slk_plan_destroy(plan);
+}
+
+void GPULodscores::calculate(DescentGraph& dg) {
+    // the upload is synchronous with respect to the caller's buffer, the scoring launch is not:
+    // CPU sampling overlaps GPU scoring exactly as in the reference
+    die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPULodscores::calculate (upload)");
+    die_on(slk_lodscore_accumulate(chain), "GPULodscores::calculate (launch)");
+}
+
+void GPULodscores::block_until_finished() {
+    die_on(slk_chain_sync(chain), "GPULodscores::block_until_finished");
+}
+
+void GPULodscores::get_results(LODscores* lod) {
+    std::vector<double> raw(lod->num_lodscores());
+    int32_t count = 0;
+    die_on(slk_lodscore_read(chain, raw.data(), &count), "GPULodscores::get_results");
+    lod->set_trait_prob(trait_likelihood);
+    lod->set_count((unsigned int) count);
+    for(unsigned int i = 0; i < raw.size(); ++i) lod->set(i, raw[i]);
+}
+
+GPUMarkovChain::GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num) :
+    ped(ped), map(map), psg(psg), options(options), plan(0), chain(0), seq_num(sequence_num) {
+    flatten_problem(*ped, *map, *psg, options.sex_linked, flat);
+    die_on(slk_plan_create(&flat.desc, options.device, &plan), "GPUMarkovChain: plan");
+    die_on(slk_chain_create(plan, options.seed, (uint32_t) sequence_num, &chain), "GPUMarkovChain: chain");
+}
+
+GPUMarkovChain::~GPUMarkovChain() {
+    slk_chain_destroy(chain);
+    slk_plan_destroy(plan);
+}
+
+double GPUMarkovChain::calc_trait_prob() {
+    double v = 0.0;
+    die_on(slk_trait_likelihood(plan, &v), "GPUMarkovChain::calc_trait_prob");
+    return v;
+}
+
+// markov_chain.cc:314-404 with both batches on the device.  The M-sampler (meiosis_sampler.cc,
+// founder_allele_graph4.cc) is outside this library: a chain that asks for M-sweeps
+// (lsampler_prob < 1) is refused rather than silently run with a different mix.
+LODscores* GPUMarkovChain::run(DescentGraph& dg) {
+    if(options.lsampler_prob < 1.0) {
+        fprintf(stderr, "error: this build runs L-sampler sweeps only; use -l 1.0 (the M-sampler is not part of the device path)\n");
+        abort();
+    }
+    LODscores* lod = new LODscores(map);
+    const double trait_prob = calc_trait_prob();
+    printf("P(T) = %.5f\n", trait_prob / log(10.0));
+    die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (upload)");
+    die_on(slk_lodscore_init(chain), "GPUMarkovChain::run (init)");
+    const int total = options.iterations + options.burnin;
+    for(int i = 0; i < total; ++i) {
+        die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (L-sampler)");
+        if(i < options.burnin) continue;
+        if((i % options.scoring_period) == 0) die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::run (scoring)");
+    }
+    die_on(slk_dg_download(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (download)");
+    std::vector<double> raw(lod->num_lodscores());
+    int32_t count = 0;
+    die_on(slk_lodscore_read(chain, raw.data(), &count), "GPUMarkovChain::run (results)");
+    lod->set_trait_prob(trait_prob);
+    lod->set_count((unsigned int) count);
+    for(unsigned int i = 0; i < raw.size(); ++i) lod->set(i, raw[i]);
+    return lod;
+}
+
+}  // namespace swiftlink

@@ -1,0 +1,398 @@
+// swiftlink_host.h -- C++ host side above the C ABI: the classes a SwiftLink caller already
+// knows (Pedigree / Person / GeneticMap / DiseaseModel / parsers / GenotypeElimination /
+// PeelSequenceGenerator / DescentGraph / LODscores / GPULodscores / GPUMarkovChain), with the
+// same names, argument meaning and error behaviour (print to stderr, abort()/exit()) as the
+// reference, re-written around flat tables that feed slk_problem directly.
+//
+// Every numeric table produced here is checked bit-for-bit against the compiled reference in
+// tests/test_host_vs_reference.py (person order, disease probabilities, marker priors, thetas,
+// elimination masks, peel operations for a given elimination order).
+#ifndef SWIFTLINK_HOST_H
+#define SWIFTLINK_HOST_H
+
+#include <stdint.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "swiftlink_b200.h"
+
+namespace swiftlink {
+
+// ---- enums (types.h:19-35, trait.h:9-27, genotype.h:18-31, peeling.h:17-23) --------------
+enum parentage { MATERNAL = 0, PATERNAL = 1, NONE = 2 };
+enum sex { UNSEXED = 0, MALE = 1, FEMALE = 2 };
+enum affection { UNKNOWN_AFFECTION = 0, UNAFFECTED = 1, AFFECTED = 2 };
+enum unphased_trait { TRAIT_HOMO_U = 0, TRAIT_HETERO = 1, TRAIT_HOMO_A = 2 };
+enum phased_trait { TRAIT_UU = 0, TRAIT_AA = 1, TRAIT_AU = 2, TRAIT_UA = 3 };
+enum unphased_genotype { UNTYPED = 0, HETERO = 1, HOMOZ_A = 2, HOMOZ_B = 3 };
+enum peeloperation { NULL_PEEL = 0, CHILD_PEEL = 1, PARENT_PEEL = 2, PARTNER_PEEL = 3, LAST_PEEL = 4 };
+enum { GENO_AA = 8, GENO_AB = 4, GENO_BA = 2, GENO_BB = 1 };
+
+const unsigned int UNKNOWN_PARENT = ~0u;
+
+// types.h:55-144 (the fields this code base reads)
+struct mcmc_options {
+    bool verbose;
+    int burnin, iterations, si_iterations, scoring_period, mcmc_runs;
+    bool coda_logging;
+    std::string coda_prefix;
+    int lodscores, peelopt_iterations;
+    double lsampler_prob;
+    int thread_count;
+    bool use_gpu;
+    std::string random_filename;
+    bool affected_only, sex_linked;
+    uint64_t seed;              // Philox seed (replaces the per-thread mt19937 seed file)
+    int device;                 // CUDA device of this chain group
+    mcmc_options();
+};
+
+// ---- disease model (disease_model.h/.cc) ---------------------------------------------------
+class DiseaseModel {
+    double frequency;
+    double penetrance[3];
+    bool sexlinked;
+ public:
+    DiseaseModel() : frequency(0.001), sexlinked(false) { penetrance[0] = penetrance[1] = penetrance[2] = 0.0; }
+    void set_freq(double f) { frequency = f; }
+    void set_penetrance(double p, enum unphased_trait t) { penetrance[t] = p; }
+    void set_sexlinked(bool s) { sexlinked = s; }
+    double get_freq() const { return frequency; }
+    double get_penetrance(enum unphased_trait t) const { return penetrance[t]; }
+    bool is_sexlinked() const { return sexlinked; }
+    void finish_init() {}
+    double get_penetrance_prob2(enum affection a, enum unphased_trait t, enum sex s) const;
+    double get_apriori_prob2(enum affection a, enum unphased_trait t, enum sex s) const;
+};
+
+// ---- genetic map (genetic_map.h/.cc) -------------------------------------------------------
+class Snp {
+    std::string name;
+    double genetic_distance;
+    double major_freq, minor_freq;
+    bool maf_set;
+    double prob[4], x_male_prob[4];
+ public:
+    Snp(const std::string& name, double genetic) :
+        name(name), genetic_distance(genetic), major_freq(1.0), minor_freq(0.0), maf_set(false) {
+        for(int i = 0; i < 4; ++i) prob[i] = x_male_prob[i] = 0.0;
+    }
+    double major() const { return major_freq; }
+    double minor() const { return minor_freq; }
+    void set_minor_freq(double m) { minor_freq = m; major_freq = 1.0 - m; maf_set = true; }
+    std::string get_name() const { return name; }
+    double get_g_distance() const { return genetic_distance; }
+    bool is_maf_set() const { return maf_set; }
+    void init_probs();
+    double get_prob(enum phased_trait pt, bool x_male) const { return x_male ? x_male_prob[pt] : prob[pt]; }
+};
+
+class GeneticMap {
+    std::vector<Snp> map;
+    std::vector<double> thetas, inversethetas, partial_thetas;
+    double temperature;
+    unsigned int partial_theta_count;
+ public:
+    explicit GeneticMap(unsigned int partial_theta_count) : temperature(1.0), partial_theta_count(partial_theta_count) {}
+    Snp& operator[](int i) { return map[i]; }
+    const Snp& operator[](int i) const { return map[i]; }
+    double haldane(double m) const;
+    double inverse_haldane(double r) const;
+    void add(const Snp& s) { map.push_back(s); }
+    void add_theta(double d) { thetas.push_back(d); inversethetas.push_back(1.0 - d); }
+    std::string get_name(unsigned int i) const { return map[i].get_name(); }
+    double get_minor(unsigned int i) const { return map[i].minor(); }
+    double get_major(unsigned int i) const { return map[i].major(); }
+    double get_prob(unsigned int i, enum phased_trait pt, bool x_male) const { return map[i].get_prob(pt, x_male); }
+    unsigned int get_lodscore_count() const { return partial_theta_count; }
+    double get_theta(unsigned int i) const { return thetas[i]; }
+    double get_inversetheta(unsigned int i) const { return inversethetas[i]; }
+    double get_theta_log(unsigned int i) const;
+    double get_inversetheta_log(unsigned int i) const;
+    double get_genetic_position(unsigned int index, unsigned int offset) const;
+    double get_theta_partial(unsigned int index, unsigned int offset) const { return partial_thetas[index] * offset; }
+    double get_theta_partial_raw(unsigned int index) const { return partial_thetas[index]; }
+    unsigned int num_markers() const { return (unsigned int) map.size(); }
+    unsigned int num_thetas() const { return (unsigned int) thetas.size(); }
+    bool sanity_check();
+    void set_temperature(double t);
+};
+
+// ---- pedigree (person.h/.cc, pedigree.h/.cc) -----------------------------------------------
+class Pedigree;
+
+class Person {
+    std::string id, mother, father;
+    enum sex gender;
+    enum affection affection_status;
+    unsigned int internal_id, maternal_id, paternal_id;
+    bool typed;
+    double disease_prob[4];
+    std::vector<unsigned char> genotypes;            // unphased_genotype per marker
+    std::vector<double> genotypes_prob;              // [M][4]
+    std::vector<unsigned int> children, mates;       // internal ids
+    friend class Pedigree;
+ public:
+    Person(const std::string& name, const std::string& father_name, const std::string& mother_name,
+           enum sex s, enum affection a, const DiseaseModel& dm);
+    void init_probs(const DiseaseModel& dm);
+    std::string get_id() const { return id; }
+    std::string get_mother() const { return mother; }
+    std::string get_father() const { return father; }
+    unsigned int get_internalid() const { return internal_id; }
+    unsigned int get_maternalid() const { return maternal_id; }
+    unsigned int get_paternalid() const { return paternal_id; }
+    enum sex get_sex() const { return gender; }
+    enum affection get_affection() const { return affection_status; }
+    enum unphased_genotype get_genotype(unsigned int i) const { return typed ? (enum unphased_genotype) genotypes[i] : UNTYPED; }
+    enum unphased_genotype get_marker(unsigned int i) const { return (enum unphased_genotype) genotypes[i]; }
+    unsigned int num_markers() const { return (unsigned int) genotypes.size(); }
+    unsigned int num_children() const { return (unsigned int) children.size(); }
+    unsigned int num_mates() const { return (unsigned int) mates.size(); }
+    unsigned int get_child(unsigned int i) const { return children[i]; }
+    unsigned int get_mate(unsigned int i) const { return mates[i]; }
+    bool is_offspring(unsigned int node) const;
+    void add_genotype(enum unphased_genotype g) { if(g != UNTYPED) typed = true; genotypes.push_back((unsigned char) g); }
+    bool ismale() const { return gender == MALE; }
+    bool isfemale() const { return gender == FEMALE; }
+    bool isaffected() const { return affection_status == AFFECTED; }
+    bool istyped() const { return typed; }
+    bool mother_unknown() const { return mother == "0"; }
+    bool father_unknown() const { return father == "0"; }
+    bool isfounder_str() const { return mother_unknown() && father_unknown(); }
+    bool isfounder() const { return maternal_id == UNKNOWN_PARENT && paternal_id == UNKNOWN_PARENT; }
+    bool isleaf() const { return children.empty(); }
+    bool is_parent(unsigned int i) const { return i == maternal_id || i == paternal_id; }
+    bool operator<(const Person& p) const { return isfounder_str() && !p.isfounder_str(); }   // person.h:171-173
+    double get_disease_prob(enum phased_trait pt) const { return disease_prob[pt]; }
+    void make_unknown_affection(const DiseaseModel& dm) { affection_status = UNKNOWN_AFFECTION; init_probs(dm); }
+    void populate_trait_prob_cache(const GeneticMap& map, bool sex_linked);
+    double get_trait_probability(unsigned int locus, enum phased_trait pt) const { return genotypes_prob[4 * locus + pt]; }
+    bool safe_to_ignore_meiosis(const Pedigree& ped, enum parentage p, bool sex_linked) const;
+};
+
+class Pedigree {
+    std::string id;
+    bool sex_linked;
+    std::vector<Person> members;
+    unsigned int number_of_founders, number_of_leaves;
+    bool mendelian_errors() const;
+    int count_components() const;
+ public:
+    Pedigree(const std::string& id, bool sex_linked) : id(id), sex_linked(sex_linked), number_of_founders(0), number_of_leaves(0) {}
+    std::string get_id() const { return id; }
+    bool is_sexlinked() const { return sex_linked; }
+    unsigned int num_members() const { return (unsigned int) members.size(); }
+    unsigned int num_markers() const { return members[0].num_markers(); }
+    unsigned int num_founders() const { return number_of_founders; }
+    unsigned int num_leaves() const { return number_of_leaves; }
+    Person* get_by_index(int i) { return &members[i]; }
+    const Person* get_by_index(int i) const { return &members[i]; }
+    Person* get_by_name(const std::string& id);
+    bool add(const Person& p);
+    bool exists(const std::string& id) { return get_by_name(id) != 0; }
+    bool sanity_check();
+};
+
+// ---- parsers (parser.h, map_parser.cc, linkage_parser.cc, pedigree_parser.cc) ---------------
+bool parse_map_file(const std::string& filename, GeneticMap& map);
+bool parse_linkage_file(const std::string& filename, GeneticMap& map, DiseaseModel& dm);
+bool parse_pedigree_file(const std::string& filename, std::vector<Pedigree>& pedigrees, const DiseaseModel& dm,
+                         const GeneticMap& map);
+// Program::read_and_check_input (program.cc:18-63): map -> dat -> (force X) -> map sanity -> ped
+bool read_and_check_input(const std::string& pedfile, const std::string& mapfile, const std::string& datfile,
+                          bool force_sex_linked, GeneticMap& map, DiseaseModel& dm, std::vector<Pedigree>& pedigrees);
+
+// ---- deterministic host RNG (replaces random.cc's GSL streams on the host side) --------------
+class HostRng {
+    uint64_t seed, counter;
+ public:
+    explicit HostRng(uint64_t seed) : seed(seed), counter(0) {}
+    uint32_t next_u32();
+    double uniform();
+    int uniform_int(int n);
+    template<typename T> void shuffle(std::vector<T>& v) {
+        for(int i = (int) v.size() - 1; i > 0; --i) { int j = uniform_int(i + 1); T t = v[i]; v[i] = v[j]; v[j] = t; }
+    }
+};
+
+// ---- genotype elimination (elimination.h/.cc) ------------------------------------------------
+class DescentGraph;
+
+class GenotypeElimination {
+    Pedigree* ped;
+    std::vector<int> possible;             // [M][N] masks
+    bool init_processing;
+    bool sex_linked;
+    void initial_elimination();
+    bool elimination_pass(int* ds);
+    int child_homoz(int* ds, int mother, int father, int child, int homoz, bool ismale);
+    int parent_homoz(int* ds, int parent, int other_parent, int child, int homoz, enum parentage p);
+ public:
+    GenotypeElimination(Pedigree* p, bool sex_linked) : ped(p), init_processing(false), sex_linked(sex_linked) {}
+    bool elimination();
+    bool random_descentgraph(DescentGraph& d, HostRng& rng);
+    bool is_legal(int id, int locus, int value) const;
+    int mask(int locus, int id) const { return possible[(size_t) locus * ped->num_members() + id]; }
+};
+
+// ---- peel planning (peeling.h, peel_sequence_generator.h/.cc) ---------------------------------
+class PeelOperation {
+    enum peeloperation type;
+    unsigned int peelnode;
+    bool used;
+    std::vector<unsigned int> cutset, children, previous;
+ public:
+    explicit PeelOperation(unsigned int peelnode) : type(NULL_PEEL), peelnode(peelnode), used(false) {}
+    unsigned int get_peelnode() const { return peelnode; }
+    void set_used() { used = true; }
+    bool is_used() const { return used; }
+    bool in_cutset(unsigned int node) const;
+    void add_cutnode(unsigned int c) { if(!in_cutset(c)) cutset.push_back(c); }
+    void remove_cutnode(unsigned int c);
+    unsigned int get_cutnode(unsigned int i) const { return cutset[i]; }
+    unsigned int get_cutset_size() const { return (unsigned int) cutset.size(); }
+    const std::vector<unsigned int>& get_cutset() const { return cutset; }
+    bool contains_cutnodes(const std::vector<unsigned int>& nodes) const;
+    unsigned int get_cost() const { return 1u << (2 * cutset.size()); }
+    void set_type(enum peeloperation po, const Pedigree& ped);
+    enum peeloperation get_type() const { return type; }
+    const std::vector<unsigned int>& get_children() const { return children; }
+    void add_prevfunction(unsigned int i) { previous.push_back(i); }
+    const std::vector<unsigned int>& get_prevfunctions() const { return previous; }
+    std::string translated_debug_string(const Pedigree& ped) const;
+};
+
+class PeelSequenceGenerator {
+    Pedigree* ped;
+    GeneticMap* map;
+    bool verbose;
+    std::vector<PeelOperation> peelorder;       // pedigree order before finalise, peel order after
+    std::vector<PeelOperation> graph;           // the initial neighbour graph (build_simple_graph)
+    std::vector<unsigned char> peeled;
+    GenotypeElimination ge;
+    HostRng rng;
+
+    void build_simple_graph();
+    void set_type(PeelOperation& p);
+    void find_prev_functions(PeelOperation& op);
+    static void eliminate_node(std::vector<PeelOperation>& tmp, unsigned int node);
+    bool greedy_search(std::vector<unsigned int>& current);
+    void random_downhill_search(std::vector<unsigned int>& current, unsigned int iterations);
+ public:
+    PeelSequenceGenerator(Pedigree* p, GeneticMap* m, bool sex_linked, bool verbose, uint64_t seed = 20261017);
+    std::vector<PeelOperation>& get_peel_order() { return peelorder; }
+    unsigned int get_peeling_cost() const;
+    void build_peel_sequence(unsigned int iterations);
+    // import an elimination order (e.g. one found by an earlier run); false if not legitimate
+    bool set_peel_sequence(const std::vector<unsigned int>& seq);
+    void finalise_peel_order(const std::vector<unsigned int>& seq);
+    unsigned int get_cost(const std::vector<unsigned int>& seq) const;           // sum of cutset sizes
+    unsigned int get_proper_cost(const std::vector<unsigned int>& seq) const;    // sum of 4^cutset
+    bool is_legit(const std::vector<unsigned int>& seq) const;
+    GenotypeElimination& get_elimination() { return ge; }
+    std::string debug_string() const;
+};
+
+// ---- descent graph (descent_graph.h/.cc) -------------------------------------------------------
+class DescentGraph {
+    std::vector<int> data;
+    Pedigree* ped;
+    GeneticMap* map;
+    double marker_transmission;
+    int graph_size;
+    bool sex_linked;
+    int offset(unsigned person_id, unsigned locus, enum parentage p) const { return graph_size * (int) locus + 2 * (int) person_id + (int) p; }
+ public:
+    DescentGraph(Pedigree* ped, GeneticMap* map, bool sex_linked);
+    int get(unsigned person_id, unsigned locus, enum parentage p) const { return data[offset(person_id, locus, p)]; }
+    void set(unsigned person_id, unsigned locus, enum parentage p, int value) { data[offset(person_id, locus, p)] = value; }
+    bool random_descentgraph(HostRng& rng);
+    double get_marker_transmission() const { return marker_transmission; }
+    double get_recombination_prob(unsigned int locus) const;
+    int* get_internal_ptr() { return data.data(); }
+    const int* get_internal_ptr() const { return data.data(); }
+    size_t get_internal_size() const { return sizeof(int) * data.size(); }
+};
+
+// ---- LOD accumulator (lod_score.h) ----------------------------------------------------------------
+class LODscores {
+    GeneticMap* map;
+    unsigned int num_scores_per_marker, num_scores, count;
+    double trait_prob;
+    std::vector<double> scores;
+    std::vector<unsigned char> initialised;
+ public:
+    explicit LODscores(GeneticMap* map);
+    void set_trait_prob(double prob) { trait_prob = prob; }
+    double get_trait_prob() const { return trait_prob; }
+    unsigned int num_lodscores() const { return num_scores; }
+    unsigned int get_lodscores_per_marker() const { return num_scores_per_marker; }
+    void add(unsigned int locus, unsigned int offset, double prob);
+    double get_raw(unsigned int index) const { return scores[index]; }
+    double get(unsigned int locus, unsigned int offset) const;
+    double get_genetic_position(unsigned int locus, unsigned int offset) const { return map->get_genetic_position(locus, offset); }
+    unsigned int get_count() const { return count; }
+    void merge_results(LODscores* tmp);
+    void set_count(unsigned int c) { count = c; }
+    void set(unsigned int index, double prob) { scores[index] = prob; initialised[index] = 1; }
+};
+
+double log_sum(double a, double b);                           // logarithms.cc:14-23
+
+// linkage_writer.cc:14-92
+bool write_linkage_results(GeneticMap* map, const std::string& filename, std::vector<LODscores*>& all_scores, bool verbose);
+
+// ---- flat problem for the C ABI ---------------------------------------------------------------------
+struct FlatProblem {
+    std::vector<int32_t> mother, father, sex, typed;
+    std::vector<uint8_t> genotypes, elimination;
+    std::vector<double> disease_prob, marker_prob, marker_xprob, theta, partial_theta;
+    std::vector<slk_peel_op> ops;
+    slk_problem desc;
+};
+// fills `out` (and out.desc, pointing into out's vectors) from the host objects
+void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg, bool sex_linked, FlatProblem& out);
+
+// ---- GPU back end (gpu_lodscores.h, gpu_markov_chain.h) -------------------------------------------------
+class GPULodscores {
+    Pedigree* ped;
+    GeneticMap* map;
+    PeelSequenceGenerator* psg;
+    struct mcmc_options options;
+    double trait_likelihood;
+    FlatProblem flat;
+    slk_plan* plan;
+    slk_chain* chain;
+    bool owns_plan;
+ public:
+    GPULodscores(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, double trait_prob);
+    ~GPULodscores();
+    void calculate(DescentGraph& dg);           // gpu_lodscores.cc:598-607
+    void block_until_finished();                // :609-619
+    void get_results(LODscores* lod);           // :621-637
+    slk_chain* get_chain() { return chain; }
+    slk_plan* get_plan() { return plan; }
+};
+
+class GPUMarkovChain {
+    Pedigree* ped;
+    GeneticMap* map;
+    PeelSequenceGenerator* psg;
+    struct mcmc_options options;
+    FlatProblem flat;
+    slk_plan* plan;
+    slk_chain* chain;
+    int seq_num;
+ public:
+    GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num = 0);
+    ~GPUMarkovChain();
+    LODscores* run(DescentGraph& dg);           // gpu_markov_chain.cc:991 / markov_chain.cc:314
+    double calc_trait_prob();                   // Peeler::calc_trait_prob on the device
+    slk_chain* get_chain() { return chain; }
+};
+
+}  // namespace swiftlink
+
+#endif

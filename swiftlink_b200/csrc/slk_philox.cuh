@@ -18,7 +18,13 @@
 
 #define SLK_SLOT_PHASE 0x7ffffff0u
 
-__host__ __device__ __forceinline__ void slk_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+#if defined(__CUDACC__)
+#define SLK_HD __host__ __device__ __forceinline__
+#else
+#define SLK_HD static inline
+#endif
+
+SLK_HD void slk_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                            uint32_t k0, uint32_t k1, uint32_t out[4]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
@@ -40,7 +46,7 @@ __host__ __device__ __forceinline__ void slk_philox4x32_10(uint32_t c0, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__host__ __device__ __forceinline__ double slk_uniform(uint64_t seed, uint32_t chain, uint64_t iteration,
+SLK_HD double slk_uniform(uint64_t seed, uint32_t chain, uint64_t iteration,
                                                        uint32_t locus, uint32_t slot) {
     uint32_t o[4];
     slk_philox4x32_10((uint32_t) iteration, (uint32_t)(iteration >> 32), locus, slot >> 1,

@@ -436,7 +436,7 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
     hp.fprior.resize((size_t) M * 8);
     for(int l = 0; l < M; ++l) {
         for(int i = 0; i < N; ++i) {
-            bool founder = i < F;
+            bool founder = pb.prior_as_founder ? (pb.prior_as_founder[i] != 0) : true;
             bool xmale = pb.sex_linked && pb.sex[i] == SLK_MALE;
             int g = pb.genotypes[(size_t) i * M + l];
             int cls = prior_class(founder, pb.typed[i] != 0, g, xmale);

@@ -1,0 +1,169 @@
+"""ctypes view of include/swiftlink_b200_host.h: the C++ host side (parsers, tables, genotype
+elimination, peel-sequence generator).  Plumbing for tests and bench.py; the logic is C++."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+SYMBOLS = [
+    "slk_host_open", "slk_host_close", "slk_host_dims", "slk_host_person_table", "slk_host_person_name",
+    "slk_host_marker_name", "slk_host_genotypes", "slk_host_marker_trait_prob", "slk_host_map_table",
+    "slk_host_disease_model", "slk_host_elim_masks", "slk_host_build_peel", "slk_host_set_peel",
+    "slk_host_num_ops", "slk_host_peel_cost", "slk_host_op_info", "slk_host_random_descentgraph",
+    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain",
+]
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Host(object):
+    """One pedigree loaded from LINKAGE ped/map/dat files by the C++ host code."""
+
+    def __init__(self, ped, mapf, dat, sex_linked=False, lodscores=5):
+        self.L = capi.lib()
+        self.L.slk_host_open.restype = C.c_void_p
+        self.L.slk_host_problem.restype = C.POINTER(capi.Problem)
+        self.L.slk_host_peel_cost.restype = C.c_uint32
+        h = self.L.slk_host_open(ped.encode(), mapf.encode(), dat.encode(), int(sex_linked), int(lodscores))
+        if not h:
+            raise RuntimeError("could not load %s / %s / %s" % (ped, mapf, dat))
+        self.h = C.c_void_p(h)
+        d = np.zeros(5, np.int32)
+        self.L.slk_host_dims(self.h, _ip(d))
+        self.N, self.F, self.M, self.nlod, self.sex_linked = [int(x) for x in d]
+
+    def close(self):
+        if self.h:
+            self.L.slk_host_close(self.h)
+            self.h = None
+
+    def person_table(self):
+        N = self.N
+        mother = np.zeros(N, np.int32); father = np.zeros(N, np.int32); sex = np.zeros(N, np.int32)
+        aff = np.zeros(N, np.int32); typed = np.zeros(N, np.int32); dprob = np.zeros((N, 4))
+        self.L.slk_host_person_table(self.h, _ip(mother), _ip(father), _ip(sex), _ip(aff), _ip(typed), _dp(dprob))
+        return dict(mother=mother, father=father, sex=sex, affection=aff, typed=typed, disease_prob=dprob)
+
+    def _names(self, fn, n):
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(n):
+            fn(self.h, i, buf, 256)
+            out.append(buf.value.decode())
+        return out
+
+    def person_names(self):
+        return self._names(self.L.slk_host_person_name, self.N)
+
+    def marker_names(self):
+        return self._names(self.L.slk_host_marker_name, self.M)
+
+    def genotypes(self):
+        g = np.zeros((self.N, self.M), np.int32)
+        self.L.slk_host_genotypes(self.h, _ip(g))
+        return g
+
+    def marker_trait_prob(self):
+        t = np.zeros((self.N, self.M, 4))
+        self.L.slk_host_marker_trait_prob(self.h, _dp(t))
+        return t
+
+    def map_table(self):
+        M = self.M
+        gdist = np.zeros(M); minor = np.zeros(M); prob = np.zeros((M, 4)); xprob = np.zeros((M, 4))
+        theta = np.zeros(M - 1); partial = np.zeros(M - 1)
+        self.L.slk_host_map_table(self.h, _dp(gdist), _dp(minor), _dp(prob), _dp(xprob), _dp(theta), _dp(partial))
+        return dict(gdist=gdist, minor=minor, prob=prob, xprob=xprob, theta=theta, partial=partial)
+
+    def disease_model(self):
+        d = np.zeros(4)
+        self.L.slk_host_disease_model(self.h, _dp(d))
+        return dict(freq=float(d[0]), penetrance=d[1:].copy())
+
+    def elim_masks(self):
+        m = np.zeros((self.M, self.N), np.int32)
+        self.L.slk_host_elim_masks(self.h, _ip(m))
+        return m
+
+    def build_peel(self, iterations=1000000, seed=20261017):
+        self.L.slk_host_build_peel(self.h, int(iterations), C.c_uint64(seed))
+
+    def set_peel(self, seq):
+        s = np.ascontiguousarray(seq, np.uint32)
+        assert s.shape == (self.N,)
+        return bool(self.L.slk_host_set_peel(self.h, s.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def set_peel_by_names(self, names):
+        """elimination order given as person ids of the ped file (robust to member re-ordering)"""
+        index = dict((n, i) for i, n in enumerate(self.person_names()))
+        return self.set_peel([index[str(n)] for n in names])
+
+    def peel_cost(self):
+        return int(self.L.slk_host_peel_cost(self.h))
+
+    def ops(self):
+        out = []
+        N = self.N
+        for i in range(int(self.L.slk_host_num_ops(self.h))):
+            info = np.zeros(5, np.int32); cut = np.zeros(N, np.int32); prev = np.zeros(N, np.int32)
+            kids = np.zeros(N, np.int32)
+            self.L.slk_host_op_info(self.h, i, _ip(info), _ip(cut), _ip(prev), _ip(kids))
+            out.append(dict(type=int(info[0]), peelnode=int(info[1]), cutset=cut[:info[2]].tolist(),
+                            previous=prev[:info[3]].tolist(), children=kids[:info[4]].tolist()))
+        return out
+
+    def random_descentgraph(self, seed=1):
+        dg = np.zeros((self.M, self.N, 2), np.int32)
+        if not self.L.slk_host_random_descentgraph(self.h, C.c_uint64(seed), _ip(dg)):
+            raise RuntimeError("genotype elimination failed: inconsistent genotypes")
+        return dg
+
+    def problem_ptr(self):
+        p = self.L.slk_host_problem(self.h)
+        if not p:
+            raise RuntimeError("peel sequence not built")
+        return p
+
+    def problem_dict(self):
+        """the same layout as oracle.orcapi.problem_from_ref, produced by the host code"""
+        pt = self.person_table(); mt = self.map_table()
+        return dict(N=self.N, F=self.F, M=self.M, nlod=self.nlod, sex_linked=self.sex_linked,
+                    mother=pt["mother"], father=pt["father"], sex=pt["sex"], affection=pt["affection"],
+                    typed=pt["typed"], disease_prob=pt["disease_prob"], marker_prob=self.marker_trait_prob(),
+                    genotypes=self.genotypes(), elim=self.elim_masks(), theta=mt["theta"], partial=mt["partial"],
+                    gdist=mt["gdist"], minor=mt["minor"], mapprob=mt["prob"], mapxprob=mt["xprob"], ops=self.ops())
+
+    def write_results(self, filename, lod):
+        lod = np.ascontiguousarray(lod, np.float64)
+        return bool(self.L.slk_host_write_results(self.h, filename.encode(), _dp(lod)))
+
+    def run_chain(self, dg, burnin, iterations, scoring_period=10, seed=1, chain_id=0, device=0):
+        dg = np.ascontiguousarray(dg, np.int32).copy()
+        lod = np.zeros((self.M - 1) * self.nlod); tp = C.c_double(0)
+        rc = self.L.slk_host_run_chain(self.h, int(device), C.c_uint64(seed), C.c_uint32(chain_id), int(burnin),
+                                       int(iterations), int(scoring_period), _ip(dg), _dp(lod), C.byref(tp))
+        if rc != 0:
+            raise capi.SlkError(rc, self.L.slk_last_error().decode())
+        return dict(lod=lod.reshape(self.M - 1, self.nlod), dg=dg, trait_prob=tp.value)
+
+
+class PlanFromHost(capi.Plan):
+    """device plan built straight from the host's flattened slk_problem (no Python copies)"""
+
+    def __init__(self, host, device=0):
+        self.L = capi.lib()
+        self.N, self.F, self.M, self.nlod = host.N, host.F, host.M, host.nlod
+        ops = host.ops()
+        self.nops = len(ops)
+        self.sum_cells = sum(4 ** len(o["cutset"]) for o in ops)
+        self.sum_presum = 4 * self.sum_cells
+        self.h = C.c_void_p()
+        capi._check(self.L.slk_plan_create(host.problem_ptr(), int(device), C.byref(self.h)))
+        self.device = device
