@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the peeling hot path (L-sampler + LOD scoring) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the synthetic
+200-member consanguineous pedigree with 10 000 SNPs (swiftlink_b200/synth.py, seed 20261017),
+scored at 5 positions per interval every 100th iteration.
+
+One MCMC iteration of the hot path = one L-sampler sweep over all M loci (both parity classes);
+every `scoring period` (100) iterations the descent graph is LOD-scored at all (M-1)*5 positions.
+One bench STEP = 100 iterations = 100 sweeps + 1 scoring pass.  The reference's M-sampler sweeps
+(the other half of its default mix) are outside the path and are run by
+neither arm.  metric = MCMC iterations / second, whole job.
+
+With N > 1 GPUs every rank runs an independent replicate chain (the reference's -R, one chain
+group per GPU, weak scaling); the LOD accumulators are merged at the end by small NCCL
+all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the counts).
+
+--impl reference times the UNMODIFIED reference (oracle/_ref/libswiftref.so, built by
+oracle/Makefile) on the host cores with all OpenMP threads: its own LocusSampler sweeps and
+Peeler::process passes (markov_chain.cc:209-266, :375-383) on a bounded sample of the same
+workload -- the first 1000 of the 10 000 SNPs of the same pedigree (the per-locus cost does not
+depend on M; the reference's per-locus index tables make M = 10 000 take minutes to set up) --
+extrapolated linearly in M and stated as such in `cpu_baseline.sample`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_MEMBERS, N_MARKERS, N_LOD, SCORING_PERIOD = 200, 10000, 5, 100
+REF_SAMPLE_MARKERS = 1000
+METRIC = "mcmc_iterations_per_sec_incl_lod_scoring"
+UNIT = "iterations/s"
+WORKLOAD = "synthetic 200-member consanguineous pedigree, 10k SNPs, LOD scoring (5 positions/interval) every 100th iteration"
+
+
+def load_order():
+    with open(os.path.join(ROOT, "swiftlink_b200", "data", "synth200_peel_order.json")) as f:
+        return json.load(f)
+
+
+def workload_files(n_markers, tag):
+    from swiftlink_b200 import synth
+    ped = synth.generate(N_MEMBERS, N_MARKERS)
+    if n_markers != N_MARKERS:
+        ped = synth.subset_markers(ped, n_markers)
+    d = os.path.join(tempfile.gettempdir(), "slk_bench_%s_%d" % (tag, os.getpid()))
+    return synth.write_linkage(ped, os.path.join(d, "synth"))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------------
+
+def reference_measure(steps, warmup, quiet=True):
+    """Times the reference's own CPU path.  Returns (iterations/s extrapolated to M = 10k, info)."""
+    from oracle import refapi
+    if not refapi.available():
+        return None, dict(error="oracle/_ref/libswiftref.so not built")
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    refapi.set_threads(threads)
+    refapi.seed(20261017)
+    paths = workload_files(REF_SAMPLE_MARKERS, "ref")
+    r = refapi.Ref(*paths, lodscores=N_LOD)
+    names = r.person_names()
+    index = dict((n, i) for i, n in enumerate(names))
+    order = [index[str(n)] for n in load_order()["order"]]
+    assert r.set_peel(order), "reference rejected the committed elimination order"
+    r.sequential_imputation(1)            # the reference's own start state: one sequential-imputation run
+    scale = float(N_MARKERS) / REF_SAMPLE_MARKERS
+    times = []
+    for s in range(warmup + steps):
+        t_old = r.bench_lsweeps(1, -1)
+        t_grp = r.bench_lsweeps(1, 4) if threads > 1 else t_old
+        t_sweep = min(t_old, t_grp)       # the reference picks the faster scheduler itself (markov_chain.cc:269-311)
+        t_lod = r.bench_lodpasses(1)
+        if s >= warmup:
+            times.append((t_sweep, t_lod))
+    t_sweep = float(np.mean([t[0] for t in times])) * scale
+    t_lod = float(np.mean([t[1] for t in times])) * float(N_MARKERS - 1) / (REF_SAMPLE_MARKERS - 1)
+    t_iter = t_sweep + t_lod / SCORING_PERIOD
+    info = dict(cores=threads, host_cores=cores, sweep_s_at_10k=t_sweep, lod_pass_s_at_10k=t_lod,
+                locus_updates_per_s=N_MARKERS / t_sweep,
+                trait_positions_per_s=(N_MARKERS - 1) * N_LOD / t_lod,
+                sample="reference LocusSampler sweep + Peeler::process pass over the first %d of %d SNPs of the same "
+                       "pedigree, %d OpenMP threads, x%d linear extrapolation in M" %
+                       (REF_SAMPLE_MARKERS, N_MARKERS, threads, int(scale)))
+    r.close()
+    return 1.0 / t_iter, info
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t0 = time.time()
+    value, info = reference_measure(args.steps, args.warmup)
+    if value is None:
+        print(json.dumps({"impl": "reference", "unavailable": info["error"]}))
+        return
+    t_iter = 1.0 / value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_iter * SCORING_PERIOD, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "100 iterations = 100 L-sampler sweeps + 1 LOD scoring pass",
+                   "n_members": N_MEMBERS, "n_markers": N_MARKERS, "n_lod": N_LOD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "reference", "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "detail": {k: info[k] for k in ("sweep_s_at_10k", "lod_pass_s_at_10k", "locus_updates_per_s",
+                                        "trait_positions_per_s", "host_cores")},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read)
+            self.thread.daemon = True
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from swiftlink_b200 import build, capi, host as H
+
+    build.build()
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t_setup = time.time()
+    paths = workload_files(N_MARKERS, "r%d" % rank)
+    hst = H.Host(*paths, lodscores=N_LOD)
+    assert hst.set_peel_by_names(load_order()["order"]), "committed elimination order rejected"
+    plan = H.PlanFromHost(hst, device=local_rank)
+    stats = plan.stats()
+    chain = capi.Chain(plan, seed=20261017, chain_id=rank)     # replicate r on GPU r
+    stream = torch.cuda.current_stream()
+    chain.set_stream(stream.cuda_stream)
+    M, N = hst.M, hst.N
+
+    # start state: one sequential-imputation run (LocusSampler::start_from), then a short burn-in
+    si_weight = chain.sequential_imputation(run=0, start_locus=M // 2)
+    it = 1
+    for _ in range(10):
+        chain.lsampler_sweep(it); it += 1
+    chain.sync()
+    trait_prob = plan.trait_likelihood()
+    t_setup = time.time() - t_setup
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    pinned_dg = torch.zeros((M, N, 2), dtype=torch.int32).pin_memory()
+    pinned_lod = torch.zeros(((M - 1) * N_LOD,), dtype=torch.float64).pin_memory()
+    chain.dg_download_ptr(pinned_dg.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def hot_step(start_it):
+        for k in range(SCORING_PERIOD):
+            chain.lsampler_sweep(start_it + k)
+        chain.lodscore_accumulate()
+        return start_it + SCORING_PERIOD
+
+    def timed(step_fn, k_steps, it0):
+        """K steps, each bracketed by its own CUDA events on the launching stream, an untimed L2
+        flush between steps; returns (seconds, next iteration)"""
+        total_ms = 0.0
+        for _ in range(k_steps):
+            flush.fill_(1)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            it0 = step_fn(it0)
+            b.record(stream)
+            b.synchronize()
+            barrier()
+            total_ms += a.elapsed_time(b)
+        return total_ms * 1e-3, it0
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    chain.lodscore_init()
+    for _ in range(args.warmup):
+        it = hot_step(it)
+    chain.sync()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    secs, it = timed(hot_step, args.steps, it)
+    chain.sync()
+    clock_info = clocks.stop()
+    if dist is not None:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    value = world * args.steps * SCORING_PERIOD / secs
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    h2d = pinned_dg.numel() * 4
+    d2h = pinned_dg.numel() * 4 + pinned_lod.numel() * 8
+
+    def e2e_step(start_it):
+        chain.dg_upload_ptr(pinned_dg.data_ptr())             # int32[M][N][2], as GPULodscores::calculate copies it
+        nxt = hot_step(start_it)
+        chain.dg_download_ptr(pinned_dg.data_ptr())
+        chain.lodscore_read_ptr(pinned_lod.data_ptr())
+        return nxt
+
+    def timed_wall(step_fn, k_steps, it0):
+        total = 0.0
+        for _ in range(k_steps):
+            flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            it0 = step_fn(it0)
+            torch.cuda.synchronize()
+            total += time.perf_counter() - t0
+            barrier()
+        return total, it0
+
+    for _ in range(min(args.warmup, 2)):
+        it = e2e_step(it)
+    e2e_secs, it = timed_wall(e2e_step, args.steps, it)
+    if dist is not None:
+        t = torch.tensor([e2e_secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_secs = float(t.item())
+    e2e_value = world * args.steps * SCORING_PERIOD / e2e_secs
+
+    # ---- per-kernel durations (CUDA events on the launching stream) -------------------------------------
+    def kernel_ms(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ctr = [it]
+
+    def one_window():
+        chain.lsampler_window(ctr[0], 2, ctr[0] & 1)
+        ctr[0] += 1
+    ls_ms = kernel_ms(one_window, 40)                              # one launch = M/2 loci
+    lod_ms = kernel_ms(chain.lodscore_accumulate, 5)               # one launch = (M-1)*5 positions
+    chain.sync()
+    fp64_peak = capi.measure_fp64_peak(local_rank)
+
+    # ---- merge replicates (LODscores::merge_results, lod_score.h:98-105) -----------------------------------
+    raw, count = chain.lodscore_read()
+    raw = torch.from_numpy(raw.ravel().copy()).cuda()
+    merged_count = count
+    if dist is not None:
+        mx = raw.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        ex = torch.exp(raw - mx)
+        dist.all_reduce(ex, op=dist.ReduceOp.SUM)
+        raw = mx + torch.log(ex)
+        c = torch.tensor([count], device="cuda", dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        merged_count = int(c.item())
+    lod = (raw - np.log(max(merged_count, 1)) - trait_prob) / np.log(10.0)
+    lod_max = float(lod.max().item())
+    lod_argmax = int(lod.argmax().item()) // N_LOD
+
+    # ---- roofline --------------------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (IOError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    loci_per_launch = M / 2.0
+    ls_flops = stats["flops_ls"] * loci_per_launch
+    ls_tflops = ls_flops / (ls_ms * 1e-3) / 1e12
+    lod_flops = stats["flops_lod"] * (M - 1) * N_LOD
+    lod_tflops = lod_flops / (lod_ms * 1e-3) / 1e12
+    nf = N - hst.F
+    # algorithmic bytes (minimal encodings): per locus update read 2x2(N-F) bits of
+    # neighbouring meioses + 2N bits of genotypes + 16 B theta, write 2(N-F) bits
+    ls_bytes = loci_per_launch * ((4 * nf + 2 * N + 2 * nf) / 8.0 + 16)
+    roofline = {
+        "kernel": "slk_lsampler_kernel", "bound": "fp64", "achieved": ls_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ls_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+        "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+        "algorithmic_flops_per_launch": ls_flops, "launch_ms": ls_ms, "units_per_launch": loci_per_launch,
+        "hbm": {"achieved": ls_bytes / (ls_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ls_bytes / (ls_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": ls_bytes},
+        "lodscore_kernel": {"achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
+                            "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops,
+                            "trait_positions_per_s": (M - 1) * N_LOD / (lod_ms * 1e-3)},
+        "share_of_step": {"slk_lsampler_kernel": 2 * SCORING_PERIOD * ls_ms / (2 * SCORING_PERIOD * ls_ms + lod_ms),
+                          "slk_lodscore_kernel": lod_ms / (2 * SCORING_PERIOD * ls_ms + lod_ms)},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "100 iterations = 100 L-sampler sweeps + 1 LOD scoring pass",
+                   "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU",
+                   "l2": "256 MiB buffer written between timed steps (working set is L2-resident by design)",
+                   "peel_cost_sum4c": stats["sum_cells"], "max_cutset": stats["max_cutset"],
+                   "ls_team_threads": stats["ls_team_threads"], "lod_team_threads": stats["lod_team_threads"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_secs / args.steps},
+        "gpu_launches": args.steps * (2 * SCORING_PERIOD + 1),
+        "clocks": clock_info,
+        "roofline": roofline,
+        "derived": {"locus_updates_per_s": world * M * SCORING_PERIOD * args.steps / secs,
+                    "trait_positions_per_s_kernel": (M - 1) * N_LOD / (lod_ms * 1e-3),
+                    "lod_max": lod_max, "lod_argmax_interval": lod_argmax, "scoring_passes_merged": merged_count,
+                    "setup_s": t_setup, "si_log10_weight": si_weight / np.log(10.0)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = reference_measure(1, 0)
+            if v is not None:
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "reference",
+                                        "sample": info["sample"],
+                                        "trait_positions_per_s": info["trait_positions_per_s"],
+                                        "locus_updates_per_s": info["locus_updates_per_s"]}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": info["error"]}
+        except Exception as e:                                       # the baseline must not take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+    chain.close()
+    plan.close()
+    hst.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,20 @@ int slk_lsampler_window(slk_chain* chain, uint64_t iteration, int window_length,
    (gpu_markov_chain.cc:1101-1126 shuffles {0,1} the same way). */
 int slk_lsampler_sweep(slk_chain* chain, uint64_t iteration);
 
+/* Independent draw of every locus from its single-locus posterior (neighbours ignored): the
+   reference's start state when -s 0, LocusSampler::locus_by_locus (locus_sampler2.cc:183-207,
+   sequential_imputation.cc:52-62).  One launch over all loci; needs no previous graph. */
+int slk_lsampler_locus_by_locus(slk_chain* chain, uint64_t iteration);
+
+/* One sequential-imputation run: LocusSampler::start_from(dg, start_locus)
+   (locus_sampler2.cc:209-241) -- the start locus drawn on its own, then the loci to its left
+   each conditioned on its right neighbour, then the loci to its right each conditioned on its
+   left neighbour.  Inherently sequential in the loci: one team walks them in one launch.
+   `run` takes the place of the iteration in the Philox key.  log_weight (optional) receives the
+   importance weight sum ln(likelihood) the reference uses to pick the best of -s runs
+   (sequential_imputation.cc:76-108); reading it synchronises. */
+int slk_sequential_imputation(slk_chain* chain, uint64_t run, int start_locus, double* log_weight);
+
 /* ---- LOD scoring: replaces run_gpu_lodscoreinit_kernel / run_gpu_lodscore_kernel /
         run_gpu_lodscorenormalise_kernel (cuda_common.h:249-252, cuda_lodscore.cu:389-541) ---- */
 

@@ -45,7 +45,7 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(LIB_PATH)
-        for name in ("orc_ls_forward", "orc_ls_step", "orc_homo_p0", "orc_trait_prob",
+        for name in ("orc_ls_forward", "orc_ls_step", "orc_homo_p0", "orc_si_start_from", "orc_trait_prob",
                      "orc_recombination_prob", "orc_marker_transmission", "orc_log_sum",
                      "orc_lod_normalise", "orc_uniform_draw"):
             getattr(L, name).restype = C.c_double
@@ -132,6 +132,11 @@ class Problem(object):
         assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
         return int(self.L.orc_ls_sweep(self.p, _ip(dg), C.c_uint64(seed), C.c_uint32(chain),
                                        C.c_uint64(iteration)))
+
+    def si_start_from(self, dg, start_locus, seed, chain, run):
+        assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
+        return float(self.L.orc_si_start_from(self.p, _ip(dg), int(start_locus), C.c_uint64(seed),
+                                              C.c_uint32(chain), C.c_uint64(run)))
 
     def homo_p0(self, dg, locus, person, parent, ignore_left=False, ignore_right=False):
         dg = np.ascontiguousarray(dg, dtype=np.int32)

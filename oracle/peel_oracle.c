@@ -472,6 +472,24 @@ int orc_ls_sweep(const orc_problem* p, int* dg, uint64_t seed, uint32_t chain, u
     return 0;
 }
 
+double orc_si_start_from(const orc_problem* p, int* dg, int start_locus, uint64_t seed, uint32_t chain, uint64_t run) {
+    double weight = 0.0, res;
+    res = orc_ls_step(p, dg, start_locus, 1, 1, seed, chain, run, 0, 0);
+    if(res == 0.0) return LOG_ZERO;
+    weight += log(res);
+    for(int l = start_locus - 1; l >= 0; --l) {
+        res = orc_ls_step(p, dg, l, 1, 0, seed, chain, run, 0, 0);
+        if(res == 0.0) return LOG_ZERO;
+        weight += log(res);
+    }
+    for(int l = start_locus + 1; l < p->M; ++l) {
+        res = orc_ls_step(p, dg, l, 0, 1, seed, chain, run, 0, 0);
+        if(res == 0.0) return LOG_ZERO;
+        weight += log(res);
+    }
+    return weight;
+}
+
 /* ---- trait R-function -------------------------------------------------------------- */
 
 /* trait_rfunction.cc:9-22 */

@@ -78,6 +78,11 @@ double orc_ls_step(const orc_problem* p, int* dg, int locus, int ignore_left, in
    first class chosen by the ORC_SLOT_PHASE draw.  Returns 0, or 1+locus if a likelihood was 0. */
 int orc_ls_sweep(const orc_problem* p, int* dg, uint64_t seed, uint32_t chain, uint64_t iteration);
 
+/* LocusSampler::start_from (locus_sampler2.cc:209-241): one sequential-imputation run from
+   start_locus, Philox keyed with `run` in place of the iteration.  Returns sum ln(likelihood),
+   or -DBL_MAX if a locus had likelihood 0. */
+double orc_si_start_from(const orc_problem* p, int* dg, int start_locus, uint64_t seed, uint32_t chain, uint64_t run);
+
 /* locus_sampler2.cc:44-65: P(indicator = 0) for a homozygous parent */
 double orc_homo_p0(const orc_problem* p, const int* dg, int locus, int person, int parent,
                    int ignore_left, int ignore_right);

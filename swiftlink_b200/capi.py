@@ -23,7 +23,7 @@ SYMBOLS = [
     "slk_plan_create", "slk_plan_destroy", "slk_plan_stats", "slk_plan_validate",
     "slk_chain_create", "slk_chain_destroy", "slk_chain_set_stream", "slk_chain_sync",
     "slk_dg_upload", "slk_dg_download",
-    "slk_lsampler_window", "slk_lsampler_sweep",
+    "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval",
@@ -210,6 +210,15 @@ class Chain(object):
 
     def lsampler_sweep(self, iteration):
         _check(self.L.slk_lsampler_sweep(self.h, C.c_uint64(iteration)))
+
+    def lsampler_locus_by_locus(self, iteration=0):
+        _check(self.L.slk_lsampler_locus_by_locus(self.h, C.c_uint64(iteration)))
+
+    def sequential_imputation(self, run=0, start_locus=0, want_weight=True):
+        w = C.c_double(0)
+        _check(self.L.slk_sequential_imputation(self.h, C.c_uint64(run), int(start_locus),
+                                                C.byref(w) if want_weight else None))
+        return w.value if want_weight else None
 
     def lodscore_init(self):
         _check(self.L.slk_lodscore_init(self.h))

@@ -151,6 +151,7 @@ SlkLaunch base_launch(slk_chain* c) {
     L.chain = c->chain_id;
     L.window = 2;
     L.dump_k = -1;
+    L.si_start = -1;
     return L;
 }
 
@@ -407,6 +408,49 @@ int slk_lsampler_window(slk_chain* c, uint64_t iteration, int window_length, int
     const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
     launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
     CU(cudaGetLastError());
+    return SLK_OK;
+}
+
+int slk_lsampler_locus_by_locus(slk_chain* c, uint64_t iteration) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    CU(cudaSetDevice(p->device));
+    SlkLaunch L = base_launch(c);
+    L.iteration = iteration;
+    L.window = 1;
+    L.offset = 0;
+    L.nunits = d.M;
+    L.ignore_left = L.ignore_right = 1;
+    const int tpc = d.ls.cta_threads / d.ls.team_threads;
+    const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
+    launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    return SLK_OK;
+}
+
+int slk_sequential_imputation(slk_chain* c, uint64_t run, int start_locus, double* log_weight) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    if(start_locus < 0 || start_locus >= d.M) return fail(SLK_ERR_INVALID, "start locus out of range");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_debug(c);
+    if(rc != SLK_OK) return rc;
+    SlkLaunch L = base_launch(c);
+    L.iteration = run;
+    L.window = 1;
+    L.offset = 0;
+    L.nunits = d.M;
+    L.si_start = start_locus;
+    L.dump_result = c->dbg_res;
+    // one team walks the loci in sequence: a single CTA whose team 0 owns every unit
+    launch_ls_by_team(d.ls.team_threads, L, 1, d.ls.team_threads, d.ls.prog_smem_bytes + d.ls.team_smem_bytes, c->stream);
+    CU(cudaGetLastError());
+    if(log_weight) {
+        CU(cudaMemcpyAsync(log_weight, c->dbg_res, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        return check_device_error(c);
+    }
     return SLK_OK;
 }
 

@@ -43,6 +43,7 @@ struct SlkLaunch {
     int window, offset;          // sampler units: locus = offset + unit * window
     int nunits;
     int ignore_left, ignore_right;
+    int si_start;                // >= 0: sequential imputation walk from this locus (one team, loci in sequence)
     int no_dg;                   // trait peel without a descent graph (P(T))
     int accumulate;              // LOD: 1 = log-sum into lod[], 0 = write dump_result/dump_prob
     int unit_base;               // LOD: first unit (debug: interval * nlod)
@@ -516,7 +517,15 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
     const bool sex_linked = P.sex_linked != 0;
 
     for(int unit = gteam; unit < L.nunits; unit += total_teams) {
-        const int locus = L.offset + unit * L.window;
+        int locus = L.offset + unit * L.window;
+        bool ign_left = L.ignore_left != 0, ign_right = L.ignore_right != 0;
+        if(L.si_start >= 0) {
+            // LocusSampler::start_from (locus_sampler2.cc:209-241): the start locus alone, then
+            // leftwards conditioning on the right neighbour only, then rightwards on the left one
+            if(unit == 0)               { locus = L.si_start; ign_left = true; ign_right = true; }
+            else if(unit <= L.si_start) { locus = L.si_start - unit; ign_left = true; ign_right = false; }
+            else                        { locus = unit; ign_left = false; ign_right = true; }
+        }
         const bool has_left = (locus != 0), has_right = (locus != M - 1);
 
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
@@ -529,8 +538,8 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         if(tid == 0) {
             // sampler_rfunction.h:84-100: theta2 (left interval) / theta (right interval)
             double th2 = 1.0, ath2 = 1.0, th = 1.0, ath = 1.0;
-            if(has_left && !L.ignore_left)   { th2 = P.theta[locus - 1]; ath2 = 1.0 - th2; }
-            if(has_right && !L.ignore_right) { th = P.theta[locus]; ath = 1.0 - th; }
+            if(has_left && !ign_left)   { th2 = P.theta[locus - 1]; ath2 = 1.0 - th2; }
+            if(has_right && !ign_right) { th = P.theta[locus]; ath = 1.0 - th; }
             tm.scal[0] = th; tm.scal[1] = ath; tm.scal[2] = th2; tm.scal[3] = ath2;
         }
         team_sync<T>(team);
@@ -575,7 +584,10 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
 
         const uint32_t* last_rec = pg.stream + pg.op_start[P.last_op];
         const double result = mat_load(mat_ref(tm, (int) last_rec[1]), 0);
-        if(L.dump_result && tid == 0) L.dump_result[0] = result;
+        if(L.dump_result && tid == 0) {
+            if(L.si_start >= 0) L.dump_result[0] = (unit == 0 ? 0.0 : L.dump_result[0]) + log(result);   // SI weight
+            else L.dump_result[0] = result;
+        }
         if(result == 0.0) {
             // locus_sampler2.cc:137-142 exits the program; here the locus is left untouched
             if(tid == 0) raise_error(L.err, SLK_ERR_ZERO_LIKELIHOOD, locus);
@@ -654,13 +666,13 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
                 }
                 else {
                     double p0 = 1.0, p1 = 1.0;                              // :44-65
-                    if(has_left && !L.ignore_left) {
+                    if(has_left && !ign_left) {
                         const uint32_t v = (tm.dgl[i] >> parent) & 1u;
                         const double th = P.theta[locus - 1], ith = 1.0 - th;
                         p0 *= (v == 0) ? ith : th;
                         p1 *= (v == 1) ? ith : th;
                     }
-                    if(has_right && !L.ignore_right) {
+                    if(has_right && !ign_right) {
                         const uint32_t v = (tm.dgr[i] >> parent) & 1u;
                         const double th = P.theta[locus], ith = 1.0 - th;
                         p0 *= (v == 0) ? ith : th;
@@ -675,6 +687,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
             L.dgp[(size_t) locus * N + i] = (uint8_t) out;
         }
         if(L.dump_pmk) for(int i = tid; i < N; i += T) L.dump_pmk[i] = tm.pmk[i];
+        if(L.si_start >= 0) __threadfence();        // the next locus of the walk reads the row just written
         team_sync<T>(team);
     }
 }

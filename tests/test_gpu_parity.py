@@ -197,3 +197,28 @@ def test_descent_graph_stays_legal_under_sweeps(gpu, name):
     assert set(np.unique(dg)) <= {0, 1} and (dg[:, :orc.F, :] == 0).all()
     for l in range(orc.M):
         assert orc.ls_forward(dg, l)[0] > 0.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sequential_imputation_matches_oracle(gpu, name):
+    """LocusSampler::start_from: one team walks the loci in sequence; graph and weight == oracle"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    for run, start in ((0, 0), (1, orc.M // 2), (2, orc.M - 1)):
+        dg = np.ascontiguousarray(fx["dgs"][0]).copy()
+        ch.dg_upload(dg)
+        w_gpu = ch.sequential_imputation(run=run, start_locus=start)
+        w_orc = orc.si_start_from(dg, start, 77, 3, run)
+        assert (ch.dg_download() == dg).all(), (name, run, start)
+        assert abs(w_gpu - w_orc) <= LOG_TOL * abs(w_orc)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_locus_by_locus_matches_oracle(gpu, name):
+    """the -s 0 start state: every locus drawn on its own, all loci in one launch"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    dg = np.ascontiguousarray(fx["dgs"][0]).copy()
+    ch.dg_upload(dg)
+    ch.lsampler_locus_by_locus(9)
+    for l in range(orc.M):
+        orc.ls_step(dg, l, 77, 3, 9, ignore_left=True, ignore_right=True)
+    assert (ch.dg_download() == dg).all()
