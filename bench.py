@@ -203,7 +203,10 @@ def run_ours(args, rank, world, local_rank):
     plan = H.PlanFromHost(hst, device=local_rank)
     stats = plan.stats()
     chain = capi.Chain(plan, seed=20261017, chain_id=rank)     # replicate r on GPU r
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch's events and the library's launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     chain.set_stream(stream.cuda_stream)
     M, N = hst.M, hst.N
 

@@ -79,24 +79,41 @@ struct slk_chain {
 namespace {
 
 template<int T> void launch_ls(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    slk_lsampler_kernel<T><<<grid, cta, smem, s>>>(L);
+    slk_lsampler_kernel<T, false><<<grid, cta, smem, s>>>(L);
 }
 template<int T> void launch_lod(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    slk_lodscore_kernel<T><<<grid, cta, smem, s>>>(L);
+    slk_lodscore_kernel<T, false><<<grid, cta, smem, s>>>(L);
+}
+
+// parity hooks: one team of 128 threads whatever the plan's production geometry (the team size
+// is a launch parameter only, the shared-memory layout does not depend on it)
+const int kDebugTeam = 128;
+cudaError_t prep_debug(int, int) {
+    // the attribute belongs to the function, not to a plan: always allow the maximum so that
+    // plans of different sizes can coexist in one process
+    cudaError_t e = cudaFuncSetAttribute(slk_lsampler_kernel<kDebugTeam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    if(e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(slk_lodscore_kernel<kDebugTeam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+}
+void launch_ls_debug(const SlkLaunch& L, int smem, cudaStream_t s) {
+    slk_lsampler_kernel<kDebugTeam, true><<<1, kDebugTeam, smem, s>>>(L);
+}
+void launch_lod_debug(const SlkLaunch& L, int grid, int smem, cudaStream_t s) {
+    slk_lodscore_kernel<kDebugTeam, true><<<grid, kDebugTeam, smem, s>>>(L);
 }
 
 template<int T> cudaError_t prep_kernels(int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
     cudaError_t e;
     if(ls) {
-        e = cudaFuncSetAttribute(slk_lsampler_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ls_smem);
+        e = cudaFuncSetAttribute(slk_lsampler_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
         if(e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ls_occ, slk_lsampler_kernel<T>, ls_cta, ls_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ls_occ, slk_lsampler_kernel<T, false>, ls_cta, ls_smem);
         if(e != cudaSuccess) return e;
     }
     if(lod) {
-        e = cudaFuncSetAttribute(slk_lodscore_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, lod_smem);
+        e = cudaFuncSetAttribute(slk_lodscore_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
         if(e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(lod_occ, slk_lodscore_kernel<T>, lod_cta, lod_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(lod_occ, slk_lodscore_kernel<T, false>, lod_cta, lod_smem);
         if(e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -235,10 +252,9 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         const slk::HostProgram& hp = k ? h.lod : h.ls;
         SlkProgram& dp = k ? d.lod : d.ls;
 #define UPP(field) if(e == cudaSuccess) e = upload(hp.field, &dp.field, p->owned)
-        UPP(stream); UPP(op_start); UPP(items); UPP(flevel_start); UPP(bops); UPP(blevel_start);
+        UPP(stream); UPP(op_start); UPP(lops); UPP(lpf); UPP(flevel_quads); UPP(flevel_start); UPP(bops); UPP(blevel_start);
 #undef UPP
         dp.stream_words = (int) hp.stream.size();
-        dp.n_items = (int) hp.items.size();
         dp.n_flevels = (int) hp.flevel_start.size() - 1;
         dp.n_blevels = (int) hp.blevel_start.size() - 1;
         dp.arena_doubles = hp.arena_doubles;
@@ -247,6 +263,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         dp.cta_threads = hp.cta_threads;
         dp.prog_smem_bytes = hp.prog_smem_bytes;
         dp.team_smem_bytes = hp.team_smem_bytes;
+        dp.table_doubles_per_child = hp.table_doubles_per_child;
     }
 #undef UP
     if(e != cudaSuccess) {
@@ -265,6 +282,8 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
     e = prep_by_team(d.ls.team_threads, p->ls_cta_smem, 0, d.ls.cta_threads, 0, &p->ls_blocks_per_sm, 0, true, false);
     if(e == cudaSuccess)
         e = prep_by_team(d.lod.team_threads, 0, p->lod_cta_smem, 0, d.lod.cta_threads, 0, &p->lod_blocks_per_sm, false, true);
+    if(e == cudaSuccess)
+        e = prep_debug(d.ls.prog_smem_bytes + d.ls.team_smem_bytes, d.lod.prog_smem_bytes + d.lod.team_smem_bytes);
     if(e != cudaSuccess || p->ls_blocks_per_sm < 1 || p->lod_blocks_per_sm < 1) {
         std::string msg = cudaGetErrorString(e);
         slk_plan_destroy(p);
@@ -563,7 +582,7 @@ static int debug_ls(slk_chain* c, uint64_t iteration, int locus, int il, int ir,
     L.ignore_left = il; L.ignore_right = ir;
     L.dump_mat = c->dbg_mat; L.dump_pre = c->dbg_pre; L.dump_dist4 = c->dbg_dist4; L.dump_pmk = c->dbg_pmk;
     L.dump_result = c->dbg_res;
-    launch_ls_by_team(d.ls.team_threads, L, 1, d.ls.cta_threads, p->ls_cta_smem, c->stream);
+    launch_ls_debug(L, d.ls.prog_smem_bytes + d.ls.team_smem_bytes, c->stream);
     CU(cudaGetLastError());
     if(forward_only) {
         CU(cudaMemcpyAsync(c->dgp + (size_t) locus * d.N, saved, d.N, cudaMemcpyDeviceToDevice, c->stream));
@@ -609,8 +628,8 @@ int slk_debug_lod_interval(slk_chain* c, int interval, double* result, double* p
     L.nunits = d.nlod;
     L.dump_result = c->dbg_res;
     L.dump_prob = c->dbg_prob;
-    launch_lod_by_team(d.lod.team_threads, L, grid_for(L.nunits, tpc, p->lod_blocks_per_sm, p->sm_count),
-                       d.lod.cta_threads, p->lod_cta_smem, c->stream);
+    (void) tpc;
+    launch_lod_debug(L, L.nunits, d.lod.prog_smem_bytes + d.lod.team_smem_bytes, c->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(result, c->dbg_res, sizeof(double) * d.nlod, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(prob, c->dbg_prob, sizeof(double) * d.nlod, cudaMemcpyDeviceToHost, c->stream));
@@ -622,7 +641,7 @@ int slk_debug_lod_interval(slk_chain* c, int interval, double* result, double* p
         L2.dump_mat = c->dbg_mat;
         L2.dump_result = c->dbg_res + d.nlod;
         L2.dump_prob = c->dbg_prob + d.nlod;
-        launch_lod_by_team(d.lod.team_threads, L2, 1, d.lod.cta_threads, p->lod_cta_smem, c->stream);
+        launch_lod_debug(L2, 1, d.lod.prog_smem_bytes + d.lod.team_smem_bytes, c->stream);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(matrices, c->dbg_mat, sizeof(double) * hp.sum_cells, cudaMemcpyDeviceToHost, c->stream));
     }

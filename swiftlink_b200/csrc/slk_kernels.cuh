@@ -7,8 +7,9 @@
 //     every peel matrix of that unit in its shared-memory arena; persistent CTAs stride over
 //     the units, grid = SMs x resident CTAs;
 //   * inside a unit the peel ops are walked level by level (dependency levels of the peel
-//     forest); one warp executes one item = (op, chunk of 128 valid cells), four cells per
-//     lane, sixteen independent product chains per lane;
+//     forest); the valid cells of all ops of a level form one index space that the whole team
+//     strides over, four cells (sixteen independent product chains) per thread, so a level of
+//     many tiny ops costs one pass;
 //   * only VALID cells are enumerated: the valid set of an op is a Cartesian product of
 //     per-person legal genotype sets (4-bit masks), so the j-th valid cell is a mixed-radix
 //     decode of j -- no per-locus index lists (the reference's matrix_indices[locus] tables,
@@ -157,28 +158,17 @@ __device__ __forceinline__ double sel4(const double v[4], uint32_t i) {
     return (i & 2u) ? b : a;
 }
 
-// sampler_rfunction.cc:102-157: P(transmitted allele | parent genotype); u0/u1 are the
-// dist[TRAIT_U] values of an AU / UA parent
-__device__ __forceinline__ double dist_of(uint32_t pg, uint32_t allele, double u_au, double u_ua) {
-    if(pg == SLK_UU) return allele == 0 ? 1.0 : 0.0;
-    if(pg == SLK_AA) return allele == 1 ? 1.0 : 0.0;
-    double d0 = (pg == SLK_AU) ? u_au : u_ua;
-    return allele == 0 ? d0 : 1.0 - d0;
-}
-
-// sampler_rfunction.cc:350-419: one entry of the 64-entry transmission table
+// sampler_rfunction.cc:350-419: one entry of the 64-entry transmission table, from the
+// per-child tables staged at the start of the locus: tb[2*pg + a] = P(maternal allele a | mother
+// genotype pg), tb[8 + 2*pg + a] the paternal one (sampler_rfunction.cc:102-157).  Under X
+// linkage a heterozygous father transmits nothing (both entries 0) and a son copies the
+// maternal allele (paternal entries of a homozygous father are 1, hetero kid genotypes are 0).
 __device__ __forceinline__ double trans_prob(bool sex_linked, bool male, uint32_t m, uint32_t f, uint32_t kg,
-                                             const double* u) {
-    uint32_t am = ((kg >> 1) ^ kg) & 1u;       // maternal allele of the kid: AA, AU carry A
-    uint32_t ap = kg & 1u;                     // paternal allele: AA, UA carry A
-    if(sex_linked) {
-        if(f >= 2u) return 0.0;                // hetero father: dist = (0,0) (:116-121, :398-403)
-        if(male) {
-            if(kg >= 2u) return 0.0;
-            return dist_of(m, kg == SLK_AA ? 1u : 0u, u[0], u[1]);
-        }
-    }
-    return dist_of(m, am, u[0], u[1]) * dist_of(f, ap, u[2], u[3]);
+                                             const double* tb) {
+    const uint32_t am = ((kg >> 1) ^ kg) & 1u;       // maternal allele of the kid: AA, AU carry A
+    const uint32_t ap = kg & 1u;                     // paternal allele: AA, UA carry A
+    if(sex_linked && male && kg >= 2u) return 0.0;
+    return tb[2u * m + am] * tb[8u + 2u * f + ap];
 }
 
 // rfunction.h:81-107
@@ -211,7 +201,9 @@ __device__ __forceinline__ double trait_child_sum(bool sex_linked, bool male, ui
 struct Prog {
     const uint32_t* stream;
     const uint16_t* op_start;
-    const uint32_t* items;
+    const uint16_t* lops;
+    const uint32_t* lpf;
+    const uint32_t* flevel_quads;
     const uint16_t* flevel_start;
     const uint16_t* bops;
     const uint16_t* blevel_start;
@@ -220,26 +212,30 @@ struct Prog {
 // copies the program into shared memory (whole CTA), returns the shared views
 __device__ __forceinline__ Prog stage_program(const SlkProgram& p, int nops, unsigned char* smem) {
     uint32_t* s_stream = (uint32_t*) smem;
-    uint32_t* s_items = s_stream + p.stream_words;
-    uint16_t* s_op_start = (uint16_t*)(s_items + p.n_items);
-    uint16_t* s_fl = s_op_start + nops;
+    uint32_t* s_lpf = s_stream + p.stream_words;
+    uint32_t* s_fq = s_lpf + nops;
+    uint16_t* s_op_start = (uint16_t*)(s_fq + p.n_flevels);
+    uint16_t* s_lops = s_op_start + nops;
+    uint16_t* s_fl = s_lops + nops;
     uint16_t* s_bops = s_fl + (p.n_flevels + 1);
     uint16_t* s_bl = s_bops + nops;
     for(int i = threadIdx.x; i < p.stream_words; i += blockDim.x) s_stream[i] = p.stream[i];
-    for(int i = threadIdx.x; i < p.n_items; i += blockDim.x) s_items[i] = p.items[i];
-    for(int i = threadIdx.x; i < nops; i += blockDim.x) { s_op_start[i] = p.op_start[i]; s_bops[i] = p.bops[i]; }
+    for(int i = threadIdx.x; i < nops; i += blockDim.x) {
+        s_lpf[i] = p.lpf[i]; s_op_start[i] = p.op_start[i]; s_lops[i] = p.lops[i]; s_bops[i] = p.bops[i];
+    }
+    for(int i = threadIdx.x; i < p.n_flevels; i += blockDim.x) s_fq[i] = p.flevel_quads[i];
     for(int i = threadIdx.x; i <= p.n_flevels; i += blockDim.x) s_fl[i] = p.flevel_start[i];
     for(int i = threadIdx.x; i <= p.n_blevels; i += blockDim.x) s_bl[i] = p.blevel_start[i];
     __syncthreads();
     Prog g;
-    g.stream = s_stream; g.items = s_items; g.op_start = s_op_start;
+    g.stream = s_stream; g.lpf = s_lpf; g.flevel_quads = s_fq; g.op_start = s_op_start; g.lops = s_lops;
     g.flevel_start = s_fl; g.bops = s_bops; g.blevel_start = s_bl;
     return g;
 }
 
 __device__ __forceinline__ TeamMem carve_team(const SlkLaunch& L, const SlkProgram& p, unsigned char* base, int gteam) {
     const SlkDevPlan& P = L.plan;
-    SlkTeamLayout lay = slk_team_layout(P.N, P.F, P.nops, p.smem_doubles);
+    SlkTeamLayout lay = slk_team_layout(P.N, P.F, P.nops, p.smem_doubles, p.table_doubles_per_child);
     TeamMem tm;
     tm.arena = (double*)(base + lay.arena);
     tm.arena_saddr = (uint32_t) __cvta_generic_to_shared(tm.arena);
@@ -263,29 +259,102 @@ __device__ __forceinline__ void load_prior(const TeamMem& tm, int person, double
     for(int g = 0; g < 4; ++g) tc[g] = (cls < 5u) ? c_prior[cls < 5u ? cls : 0u][g] : tm.scal[8 + (cls - 5u) * 4 + g];
 }
 
-// ---- one forward item: (op, chunk) executed by one warp ---------------------------------
+// ---- one forward tile, executed by one thread -----------------------------------------------
 //
-// TRAIT = false: SamplerRfunction::evaluate_element on 4 cells per lane
-// TRAIT = true : TraitRfunction::evaluate_element
-template<bool TRAIT>
-__device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, const TeamMem& tm, uint32_t item, int lane) {
+// A tile is one valid assignment of cutset digits 1..c-1 (a "row") times the four values of
+// cutset digit 0 (slots) times the four genotypes of the peel node (variants): 16 product
+// chains per thread.  The gather index of a previous function is computed once per tile; a
+// previous function that is not keyed on digit 0 (or not on the peel node) is loaded once per
+// slot group instead of 16 times.
+//
+// TRAIT = false: SamplerRfunction::evaluate_element, TRAIT = true: TraitRfunction::evaluate_element
+// DBG adds the dense parity dumps (separate instantiation, keeps the hot kernels lean).
+
+// applies one previous function to the 16 products; SM selects shared vs global arena loads
+template<int NS, bool SM, bool PERM>
+__device__ __forceinline__ void apply_prev(double (&tmp)[NS][4], const bool (&act)[NS],
+                                           const uint32_t (&gvp)[NS], uint32_t saddr, const double* gptr,
+                                           uint32_t base, uint32_t d0shift, uint32_t pshift, uint32_t s0) {
+    auto ld = [&](uint32_t i) -> double { return SM ? lds_f64(saddr + i * 8u) : gptr[i]; };
+    const bool has0 = d0shift != SLK_NO_SHIFT, hasp = pshift != SLK_NO_SHIFT;
+    if(!hasp) {
+        if(!has0) {
+            // same cell for the whole tile
+            bool any = false;
+#pragma unroll
+            for(int s = 0; s < NS; ++s) any = any || act[s];
+            if(any) {
+                const double x = ld(base);
+#pragma unroll
+                for(int s = 0; s < NS; ++s)
+#pragma unroll
+                    for(int v = 0; v < 4; ++v) tmp[s][v] *= x;
+            }
+        }
+        else {
+#pragma unroll
+            for(int s = 0; s < NS; ++s) {
+                if(act[s]) {
+                    const double x = ld(base + ((s0 + (uint32_t) s) << d0shift));
+#pragma unroll
+                    for(int v = 0; v < 4; ++v) tmp[s][v] *= x;
+                }
+            }
+        }
+    }
+    else if(!has0 && !PERM) {
+        // keyed on the peel node only: one load per genotype, shared by the four slots
+#pragma unroll
+        for(int v = 0; v < 4; ++v) {
+            bool any = false;
+#pragma unroll
+            for(int s = 0; s < NS; ++s) any = any || (tmp[s][v] != 0.0);
+            if(any) {
+                const double x = ld(base + ((uint32_t) v << pshift));
+#pragma unroll
+                for(int s = 0; s < NS; ++s) tmp[s][v] *= x;
+            }
+        }
+    }
+    else {
+#pragma unroll
+        for(int s = 0; s < NS; ++s) {
+            const uint32_t bs = base + (has0 ? ((s0 + (uint32_t) s) << d0shift) : 0u);
+#pragma unroll
+            for(int v = 0; v < 4; ++v) {
+                if(tmp[s][v] != 0.0) {
+                    const uint32_t g = PERM ? ((gvp[s] >> (2 * v)) & 3u) : (uint32_t) v;
+                    tmp[s][v] *= ld(bs + (g << pshift));
+                }
+            }
+        }
+    }
+}
+
+// NS = 4: the thread owns the whole tile (throughput mode, big levels); NS = 1: the thread owns
+// slot s0 only (latency mode: a level with few rows is spread over four times as many threads)
+template<bool TRAIT, bool DBG, int NS>
+__device__ __forceinline__ void run_tile(const SlkLaunch& L, const Prog& pg, const TeamMem& tm, uint32_t op, uint32_t row, uint32_t s0) {
     const SlkDevPlan& P = L.plan;
     const bool sex_linked = P.sex_linked != 0;
-    const uint32_t op = item & 0xffffu, chunk = item >> 16;
     const uint32_t* rec = pg.stream + pg.op_start[op];
     const uint32_t w0 = rec[0];
     const int type = w0 & 7u, c = (w0 >> 4) & 15u, nprev = (w0 >> 8) & 15u, nkids = (w0 >> 12) & 15u;
     const int peel = w0 >> 16;
     const int mat_off = (int) rec[1];
     const unsigned long long lmw = TRAIT ? ((unsigned long long) rec[4] | ((unsigned long long) rec[5] << 32)) : tm.lmw[op];
-    const uint32_t nvalid = nvalid_of(lmw, c);
-    const uint32_t j0 = chunk * SLK_CHUNK;
-    if(j0 >= nvalid) return;
-    const bool dense = (lmw == full_lmw(c));
+    const int ch = c > 0 ? c - 1 : 0;
+    const unsigned long long lmw_hi = lmw >> 4;
+    const uint32_t nrows = nvalid_of(lmw_hi, ch);
+    if(row >= nrows) return;
+    const uint32_t lm0 = c > 0 ? ((uint32_t) lmw & 15u) : 1u;             // legal values of digit 0 (c = 0: one cell)
+    const uint32_t rowcell = ((lmw_hi == full_lmw(ch)) ? row : decode_cell(row, lmw_hi, ch)) << 2;
     const uint32_t peel_lm = TRAIT ? (rec[6] & 15u) : ((uint32_t) tm.gc[peel] & 15u);
     const bool peel_in_prev = (rec[3] & 1u) != 0;
-    const uint32_t* kids = rec + SLK_REC_HEADER + ((c + 1) >> 1);
-    // (children words come after the previous-function words; located below)
+    const uint32_t* pw = rec + SLK_REC_HEADER + ((c + 1) >> 1);
+    const uint32_t* kw = pw;
+    for(int jp = 0; jp < nprev; ++jp) kw += 2 + ((((kw[1] >> 8) & 0xffu) + 1) >> 1);
+    const bool perm = TRAIT && type == SLK_CHILD_PEEL;
 
     double tc[4];
     if(TRAIT) {
@@ -294,49 +363,39 @@ __device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, con
     }
     else load_prior(tm, peel, tc);
 
-    uint32_t cell[SLK_SLOTS];
-    bool act[SLK_SLOTS];
-#pragma unroll
-    for(int s = 0; s < SLK_SLOTS; ++s) {
-        uint32_t j = j0 + s * 32 + lane;
-        act[s] = j < nvalid;
-        cell[s] = act[s] ? (dense ? j : decode_cell(j, lmw, c)) : 0u;
-    }
-
-    // locate the children words
-    const uint32_t* pw = kids;
-    for(int jp = 0; jp < nprev; ++jp) pw += 2 + ((((pw[1] >> 8) & 0xffu) + 1) >> 1);
-    const uint32_t* kw = pw;
-    pw = kids;
+    bool act[NS];
+    uint32_t gvp[NS];
+    double tmp[NS][4];
+    // digit value of cutset position `pos` in slot s
+#define SLK_DIG(pos, s) (((pos) == 0u) ? (s0 + (uint32_t)(s)) : ((rowcell >> (2u * (pos))) & 3u))
 
     // ---- initial factor: prior of the peel-node genotype (x transmission for a sampler child peel)
-    double tmp[SLK_SLOTS][4];
-    uint32_t gvp[SLK_SLOTS];         // genotype of the peel node for each of the four variants
+    const uint32_t k0 = (type == SLK_CHILD_PEEL) ? kw[0] : 0u;
+    const uint32_t mpos0 = (k0 >> 20) & 15u, fpos0 = (k0 >> 24) & 15u;
+    const bool male0 = (k0 >> 28) & 1u;
 #pragma unroll
-    for(int s = 0; s < SLK_SLOTS; ++s) {
+    for(int s = 0; s < NS; ++s) {
+        act[s] = (lm0 >> (s0 + (uint32_t) s)) & 1u;
         gvp[s] = 0xE4u;
-        if(TRAIT && type == SLK_CHILD_PEEL) {
+        if(perm) {
             // variants are the four (maternal, paternal) transmitted-allele choices (trait_rfunction.cc:44-66)
-            uint32_t k0 = kw[0];
-            uint32_t m = digit(cell[s], (k0 >> 20) & 15u), f = digit(cell[s], (k0 >> 24) & 15u);
-            bool male = (k0 >> 28) & 1u;
+            const uint32_t m = SLK_DIG(mpos0, s), f = SLK_DIG(fpos0, s);
             uint32_t g = 0;
 #pragma unroll
-            for(uint32_t ij = 0; ij < 4; ++ij) g |= phased_trait(sex_linked, male, m, f, ij >> 1, ij & 1u) << (2 * ij);
+            for(uint32_t ij = 0; ij < 4; ++ij) g |= phased_trait(sex_linked, male0, m, f, ij >> 1, ij & 1u) << (2 * ij);
             gvp[s] = g;
         }
 #pragma unroll
         for(int v = 0; v < 4; ++v) {
-            uint32_t g = (gvp[s] >> (2 * v)) & 3u;
-            double t = act[s] ? sel4(tc, g) : 0.0;
+            const uint32_t g = perm ? ((gvp[s] >> (2 * v)) & 3u) : (uint32_t) v;
+            double t = act[s] ? (perm ? sel4(tc, g) : tc[v]) : 0.0;
             if(!TRAIT) {
                 // a previous function keyed on the peel node is 0 wherever that genotype was
                 // eliminated (its cell is not in valid_indices): the product is 0
-                if(peel_in_prev && !((peel_lm >> g) & 1u)) t = 0.0;
+                if(peel_in_prev && !((peel_lm >> v) & 1u)) t = 0.0;
                 if(type == SLK_CHILD_PEEL && t != 0.0) {
-                    uint32_t k0 = kw[0];
-                    uint32_t m = digit(cell[s], (k0 >> 20) & 15u), f = digit(cell[s], (k0 >> 24) & 15u);
-                    t *= trans_prob(sex_linked, (k0 >> 28) & 1u, m, f, g, tm.tables + 4 * (peel - P.F));
+                    const uint32_t m = SLK_DIG(mpos0, s), f = SLK_DIG(fpos0, s);
+                    t *= trans_prob(sex_linked, male0, m, f, (uint32_t) v, tm.tables + 16 * (peel - P.F));
                 }
             }
             tmp[s][v] = t;
@@ -345,39 +404,24 @@ __device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, con
 
     // ---- previous functions, in the reference's order
     for(int jp = 0; jp < nprev; ++jp) {
-        const MatRef mr = mat_ref(tm, (int) pw[0]);
+        const int poff = (int) pw[0];
         const uint32_t meta = pw[1];
-        const uint32_t pshift = meta & 0xffu, nruns = (meta >> 8) & 0xffu;
-        uint32_t idx[SLK_SLOTS];
-#pragma unroll
-        for(int s = 0; s < SLK_SLOTS; ++s) idx[s] = 0;
+        const uint32_t pshift = meta & 0xffu, nruns = (meta >> 8) & 0xffu, d0shift = (meta >> 16) & 0xffu;
+        uint32_t base = 0;
         for(uint32_t r = 0; r < nruns; ++r) {
-            uint32_t run = (pw[2 + (r >> 1)] >> (16 * (r & 1u))) & 0xffffu;
-            uint32_t src = run & 31u, dst = (run >> 5) & 31u, mask = (1u << (run >> 10)) - 1u;
-#pragma unroll
-            for(int s = 0; s < SLK_SLOTS; ++s) idx[s] |= ((cell[s] >> src) & mask) << dst;
+            const uint32_t run = (pw[2 + (r >> 1)] >> (16 * (r & 1u))) & 0xffffu;
+            base |= ((rowcell >> (run & 31u)) & ((1u << (run >> 10)) - 1u)) << ((run >> 5) & 31u);
         }
-        if(pshift == SLK_NO_SHIFT) {
-#pragma unroll
-            for(int s = 0; s < SLK_SLOTS; ++s) {
-                if(act[s]) {
-                    double x = mat_load(mr, idx[s]);
-#pragma unroll
-                    for(int v = 0; v < 4; ++v) tmp[s][v] *= x;
-                }
-            }
+        const bool in_smem = poff < tm.smem_doubles;
+        const uint32_t saddr = tm.arena_saddr + (uint32_t) poff * 8u;
+        const double* gptr = tm.garena + (poff - tm.smem_doubles);
+        if(perm) {
+            if(in_smem) apply_prev<NS, true, true>(tmp, act, gvp, saddr, gptr, base, d0shift, pshift, s0);
+            else        apply_prev<NS, false, true>(tmp, act, gvp, saddr, gptr, base, d0shift, pshift, s0);
         }
         else {
-#pragma unroll
-            for(int s = 0; s < SLK_SLOTS; ++s) {
-#pragma unroll
-                for(int v = 0; v < 4; ++v) {
-                    if(tmp[s][v] != 0.0) {
-                        uint32_t g = (gvp[s] >> (2 * v)) & 3u;
-                        tmp[s][v] *= mat_load(mr, idx[s] + (g << pshift));
-                    }
-                }
-            }
+            if(in_smem) apply_prev<NS, true, false>(tmp, act, gvp, saddr, gptr, base, d0shift, pshift, s0);
+            else        apply_prev<NS, false, false>(tmp, act, gvp, saddr, gptr, base, d0shift, pshift, s0);
         }
         pw += 2 + ((nruns + 1) >> 1);
     }
@@ -385,31 +429,12 @@ __device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, con
     // ---- transmission to the children / recombination weights, then the sum over the peel node
     const int dense_off = (int) rec[2];
 #pragma unroll
-    for(int s = 0; s < SLK_SLOTS; ++s) {
+    for(int s = 0; s < NS; ++s) {
         if(!act[s]) continue;
-        if(TRAIT) {
-            if(type == SLK_CHILD_PEEL) {
-                const double* w = tm.tables + 4 * (peel - P.F);
+        if(TRAIT && type == SLK_CHILD_PEEL) {
+            const double* w = tm.tables + 4 * (peel - P.F);
 #pragma unroll
-                for(int v = 0; v < 4; ++v) tmp[s][v] *= w[v];
-            }
-            else if(type == SLK_PARENT_PEEL) {
-#pragma unroll
-                for(int v = 0; v < 4; ++v) {
-                    if(tmp[s][v] == 0.0) continue;
-                    double cp = 1.0;
-                    for(int k = 0; k < nkids; ++k) {
-                        uint32_t kd = kw[k];
-                        uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u;
-                        uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : digit(cell[s], mp);
-                        uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : digit(cell[s], fp);
-                        uint32_t kg = digit(cell[s], (kd >> 16) & 15u);
-                        cp *= trait_child_sum(sex_linked, (kd >> 28) & 1u, m, f, kg,
-                                              tm.tables + 4 * ((int)(kd & 0xffffu) - P.F));
-                    }
-                    tmp[s][v] *= cp;
-                }
-            }
+            for(int v = 0; v < 4; ++v) tmp[s][v] *= w[v];
         }
         else if(type == SLK_PARENT_PEEL) {
 #pragma unroll
@@ -417,13 +442,14 @@ __device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, con
                 if(tmp[s][v] == 0.0) continue;
                 double cp = 1.0;
                 for(int k = 0; k < nkids; ++k) {
-                    uint32_t kd = kw[k];
-                    uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u;
-                    uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : digit(cell[s], mp);
-                    uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : digit(cell[s], fp);
-                    uint32_t kg = digit(cell[s], (kd >> 16) & 15u);
-                    cp *= trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg,
-                                     tm.tables + 4 * ((int)(kd & 0xffffu) - P.F));
+                    const uint32_t kd = kw[k];
+                    const uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u, kp = (kd >> 16) & 15u;
+                    const uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(mp, s);
+                    const uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(fp, s);
+                    const uint32_t kg = SLK_DIG(kp, s);
+                    const double* tb = tm.tables + (TRAIT ? 4 : 16) * ((int)(kd & 0xffffu) - P.F);
+                    cp *= TRAIT ? trait_child_sum(sex_linked, (kd >> 28) & 1u, m, f, kg, tb)
+                                : trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tb);
                 }
                 tmp[s][v] *= cp;
             }
@@ -431,13 +457,17 @@ __device__ __forceinline__ void run_item(const SlkLaunch& L, const Prog& pg, con
         double total = 0.0;
 #pragma unroll
         for(int v = 0; v < 4; ++v) total += tmp[s][v];
-        mat_store(tm, mat_off + (int) cell[s], total);
-        if(L.dump_mat) L.dump_mat[dense_off + cell[s]] = total;
-        if(!TRAIT && L.dump_pre) {
+        const uint32_t cell = rowcell | (s0 + (uint32_t) s);
+        mat_store(tm, mat_off + (int) cell, total);
+        if(DBG) {
+            if(L.dump_mat) L.dump_mat[dense_off + cell] = total;
+            if(!TRAIT && L.dump_pre) {
 #pragma unroll
-            for(int v = 0; v < 4; ++v) L.dump_pre[4 * (size_t) dense_off + cell[s] + ((size_t) v << (2 * c))] = tmp[s][v];
+                for(int v = 0; v < 4; ++v) L.dump_pre[4 * (size_t) dense_off + cell + ((size_t) v << (2 * c))] = tmp[s][v];
+            }
         }
     }
+#undef SLK_DIG
 }
 
 // ---- one term of the backward pass: presum(cell, g) of op recomputed (sampler only) --------
@@ -459,18 +489,20 @@ __device__ __forceinline__ double sampler_term(const SlkLaunch& L, const Prog& p
     if(type == SLK_CHILD_PEEL && t != 0.0) {
         uint32_t k0 = kw[0];
         uint32_t m = digit(cell, (k0 >> 20) & 15u), f = digit(cell, (k0 >> 24) & 15u);
-        t *= trans_prob(sex_linked, (k0 >> 28) & 1u, m, f, g, tm.tables + 4 * (peel - P.F));
+        t *= trans_prob(sex_linked, (k0 >> 28) & 1u, m, f, g, tm.tables + 16 * (peel - P.F));
     }
     for(int jp = 0; jp < nprev; ++jp) {
         const MatRef mr = mat_ref(tm, (int) pw[0]);
         const uint32_t meta = pw[1];
         const uint32_t pshift = meta & 0xffu, nruns = (meta >> 8) & 0xffu;
+        const uint32_t d0shift = (meta >> 16) & 0xffu;
         uint32_t idx = 0;
         for(uint32_t r = 0; r < nruns; ++r) {
             uint32_t run = (pw[2 + (r >> 1)] >> (16 * (r & 1u))) & 0xffffu;
             uint32_t src = run & 31u, dst = (run >> 5) & 31u, mask = (1u << (run >> 10)) - 1u;
             idx |= ((cell >> src) & mask) << dst;
         }
+        if(d0shift != SLK_NO_SHIFT) idx += (cell & 3u) << d0shift;
         if(pshift != SLK_NO_SHIFT) idx += g << pshift;
         if(pshift == SLK_NO_SHIFT || t != 0.0) t *= mat_load(mr, idx);
         pw += 2 + ((nruns + 1) >> 1);
@@ -483,7 +515,7 @@ __device__ __forceinline__ double sampler_term(const SlkLaunch& L, const Prog& p
             uint32_t m = (mp == SLK_POS_PEEL) ? g : digit(cell, mp);
             uint32_t f = (fp == SLK_POS_PEEL) ? g : digit(cell, fp);
             uint32_t kg = digit(cell, (kd >> 16) & 15u);
-            cp *= trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tm.tables + 4 * ((int)(kd & 0xffffu) - P.F));
+            cp *= trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tm.tables + 16 * ((int)(kd & 0xffffu) - P.F));
         }
         t *= cp;
     }
@@ -498,7 +530,7 @@ __device__ __forceinline__ void raise_error(int* err, int code, int unit) {
 // L-sampler: LocusSampler::set_locus_minimal + step (locus_sampler2.cc:128-181) for every locus
 // of one window class.  Replaces lsampler_kernel (cuda_lsampler.cu:403-449).
 // ============================================================================================
-template<int T>
+template<int T, bool DBG>
 __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
@@ -508,8 +540,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
     const int teams_per_cta = blockDim.x / T;
     const int team = threadIdx.x / T;
     const int tid = threadIdx.x % T;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nwarps = T / 32;
+    const int lane = tid & 31;
     const int gteam = blockIdx.x * teams_per_cta + team;
     const int total_teams = gridDim.x * teams_per_cta;
     const TeamMem tm = carve_team(L, pr, smem + pr.prog_smem_bytes + (size_t) team * pr.team_smem_bytes, gteam);
@@ -544,7 +575,8 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         }
         team_sync<T>(team);
 
-        // per-child u-values: dist[TRAIT_U] of an AU and of a UA parent (sampler_rfunction.cc:129-156)
+        // per-child transmission tables (sampler_rfunction.cc:102-157): for parent genotype UU / AA
+        // the transmitted allele is certain; for AU / UA it follows the neighbouring meioses
         for(int q = tid; q < 2 * (N - F); q += T) {
             const int person = F + (q >> 1), parent = q & 1;
             double tmp0 = 0.5, tmp1 = 0.5;
@@ -558,9 +590,17 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
                 tmp0 *= cross ? tm.scal[0] : tm.scal[1];
                 tmp1 *= cross ? tm.scal[1] : tm.scal[0];
             }
-            double total = tmp0 + tmp1;
-            tm.tables[4 * (person - F) + 2 * parent + 0] = tmp1 / total;     // parent AU
-            tm.tables[4 * (person - F) + 2 * parent + 1] = tmp0 / total;     // parent UA
+            const double total = tmp0 + tmp1;
+            const double u_au = tmp1 / total, u_ua = tmp0 / total;
+            double* tb = tm.tables + 16 * (person - F) + 8 * parent;
+            const bool xpat = sex_linked && parent == 1;
+            const bool son = sex_linked && P.male[person];
+            // homozygous parent
+            tb[2 * SLK_UU + 0] = 1.0; tb[2 * SLK_UU + 1] = (xpat && son) ? 1.0 : 0.0;
+            tb[2 * SLK_AA + 0] = (xpat && son) ? 1.0 : 0.0; tb[2 * SLK_AA + 1] = 1.0;
+            // heterozygous parent
+            tb[2 * SLK_AU + 0] = xpat ? 0.0 : u_au; tb[2 * SLK_AU + 1] = xpat ? 0.0 : 1.0 - u_au;
+            tb[2 * SLK_UA + 0] = xpat ? 0.0 : u_ua; tb[2 * SLK_UA + 1] = xpat ? 0.0 : 1.0 - u_ua;
         }
         // per-op legal masks of the cutset at this locus
         for(int op = tid; op < P.nops; op += T) {
@@ -578,7 +618,23 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         // ---- forward peel, level by level
         for(int lv = 0; lv < pr.n_flevels; ++lv) {
             const int b = pg.flevel_start[lv], e = pg.flevel_start[lv + 1];
-            for(int it = b + warp; it < e; it += nwarps) run_item<false>(L, pg, tm, pg.items[it], lane);
+            const uint32_t nq = pg.flevel_quads[lv];            // rows of this level
+            if(nq * 4u <= 2u * T) {
+                // latency mode: one (row, slot) per thread
+                for(uint32_t q = tid; q < nq * 4u; q += T) {
+                    const uint32_t row = q >> 2;
+                    int lo = b, hi = e - 1;
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= row) lo = mid; else hi = mid - 1; }
+                    run_tile<false, DBG, 1>(L, pg, tm, pg.lops[lo], row - pg.lpf[lo], q & 3u);
+                }
+            }
+            else {
+                for(uint32_t q = tid; q < nq; q += T) {
+                    int lo = b, hi = e - 1;
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= q) lo = mid; else hi = mid - 1; }
+                    run_tile<false, DBG, 4>(L, pg, tm, pg.lops[lo], q - pg.lpf[lo], 0u);
+                }
+            }
             team_sync<T>(team);
         }
 
@@ -621,7 +677,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
 #pragma unroll
                 for(int k = 0; k < 4; ++k) dd[k] = __shfl_sync(0xffffffffu, d, lbase + k);
                 if(live && g == 0) {
-                    if(L.dump_dist4) {
+                    if(DBG && L.dump_dist4) {
 #pragma unroll
                         for(int k = 0; k < 4; ++k) L.dump_dist4[4 * op + k] = dd[k];
                     }
@@ -686,7 +742,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
             }
             L.dgp[(size_t) locus * N + i] = (uint8_t) out;
         }
-        if(L.dump_pmk) for(int i = tid; i < N; i += T) L.dump_pmk[i] = tm.pmk[i];
+        if(DBG && L.dump_pmk) for(int i = tid; i < N; i += T) L.dump_pmk[i] = tm.pmk[i];
         if(L.si_start >= 0) __threadfence();        // the next locus of the walk reads the row just written
         team_sync<T>(team);
     }
@@ -696,7 +752,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
 // LOD scoring: Peeler::process (peeler.cc:79-103) with one team per (interval, position).
 // Replaces lodscore_kernel (cuda_lodscore.cu:389-467).
 // ============================================================================================
-template<int T>
+template<int T, bool DBG>
 __global__ void __launch_bounds__(512, 1) slk_lodscore_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
@@ -706,8 +762,7 @@ __global__ void __launch_bounds__(512, 1) slk_lodscore_kernel(const SlkLaunch L)
     const int teams_per_cta = blockDim.x / T;
     const int team = threadIdx.x / T;
     const int tid = threadIdx.x % T;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nwarps = T / 32;
+    const int lane = tid & 31;
     const int gteam = blockIdx.x * teams_per_cta + team;
     const int total_teams = gridDim.x * teams_per_cta;
     const TeamMem tm = carve_team(L, pr, smem + pr.prog_smem_bytes + (size_t) team * pr.team_smem_bytes, gteam);
@@ -764,7 +819,23 @@ __global__ void __launch_bounds__(512, 1) slk_lodscore_kernel(const SlkLaunch L)
 
         for(int lv = 0; lv < pr.n_flevels; ++lv) {
             const int b = pg.flevel_start[lv], e = pg.flevel_start[lv + 1];
-            for(int it = b + warp; it < e; it += nwarps) run_item<true>(L, pg, tm, pg.items[it], lane);
+            const uint32_t nq = pg.flevel_quads[lv];            // rows of this level
+            if(nq * 4u <= 2u * T) {
+                // latency mode: one (row, slot) per thread
+                for(uint32_t q = tid; q < nq * 4u; q += T) {
+                    const uint32_t row = q >> 2;
+                    int lo = b, hi = e - 1;
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= row) lo = mid; else hi = mid - 1; }
+                    run_tile<true, DBG, 1>(L, pg, tm, pg.lops[lo], row - pg.lpf[lo], q & 3u);
+                }
+            }
+            else {
+                for(uint32_t q = tid; q < nq; q += T) {
+                    int lo = b, hi = e - 1;
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= q) lo = mid; else hi = mid - 1; }
+                    run_tile<true, DBG, 4>(L, pg, tm, pg.lops[lo], q - pg.lpf[lo], 0u);
+                }
+            }
             team_sync<T>(team);
         }
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <tuple>
 
 namespace slk {
 
@@ -141,7 +142,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     }
 
     // ---- static validity: cells per op ----
-    std::vector<long> ncells(nops);
+    std::vector<long> ncells(nops), nrows(nops);
     std::vector<uint64_t> static_lmw(nops, 0);
     std::vector<uint8_t> dmask(pb.n_members, 0);
     for(int i = 0; i < pb.n_members; ++i)
@@ -156,6 +157,8 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
             n *= __builtin_popcount(m);
         }
         ncells[i] = n;
+        // rows = valid assignments of digits 1..c-1 (digit 0 is the register tile's slot axis)
+        nrows[i] = (op.ncut > 0) ? n / __builtin_popcount((unsigned)(static_lmw[i] & 15u)) : 1;
         pr.valid_cells += n;
     }
 
@@ -199,21 +202,28 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         pr.arena_doubles = off;
     }
 
-    // ---- items: (op, chunk) per forward level ----
-    pr.items.clear();
+    // ---- forward schedule: ops per level, quads (4 cells per thread) per op ----
+    pr.lops.clear(); pr.lpf.clear(); pr.flevel_quads.clear();
     pr.flevel_start.assign(1, 0);
     for(int l = 0; l < n_flevels; ++l) {
-        // big ops first inside a level so the tail of the level is made of small items
+        // big ops first inside a level so that the threads of a warp mostly share an op
         std::vector<int> ops_here;
         for(int i = 0; i < nops; ++i) if(flevel[i] == l) ops_here.push_back(i);
-        std::stable_sort(ops_here.begin(), ops_here.end(), [&](int a, int b) { return ncells[a] > ncells[b]; });
+        // ... and ops of the same shape next to each other so that the threads of a warp that
+        // do hold different ops still follow the same control flow
+        auto shape = [&](int i) {
+            const slk_peel_op& o = pb.ops[i];
+            return std::make_tuple(-nrows[i], o.type, o.nprev, o.nchild, o.ncut);
+        };
+        std::stable_sort(ops_here.begin(), ops_here.end(), [&](int a, int b) { return shape(a) < shape(b); });
+        uint32_t quads = 0;
         for(size_t q = 0; q < ops_here.size(); ++q) {
-            int i = ops_here[q];
-            long chunks = (ncells[i] + SLK_CHUNK - 1) / SLK_CHUNK;
-            if(chunks < 1) chunks = 1;
-            for(long ch = 0; ch < chunks; ++ch) pr.items.push_back((uint32_t) i | ((uint32_t) ch << 16));
+            pr.lops.push_back((uint16_t) ops_here[q]);
+            pr.lpf.push_back(quads);
+            quads += (uint32_t) nrows[ops_here[q]];
         }
-        pr.flevel_start.push_back((uint16_t) pr.items.size());
+        pr.flevel_quads.push_back(quads);
+        pr.flevel_start.push_back((uint16_t) pr.lops.size());
     }
 
     pr.bops.clear();
@@ -254,12 +264,14 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         }
         for(int j = 0; j < op.nprev; ++j) {
             const slk_peel_op& pv = pb.ops[op.prev[j]];
-            uint32_t peel_shift = SLK_NO_SHIFT;
-            // (dst digit in the consumed matrix) <- (src digit of the consumer's cutset)
+            uint32_t peel_shift = SLK_NO_SHIFT, d0_shift = SLK_NO_SHIFT;
+            // (dst digit in the consumed matrix) <- (src digit of the consumer's cutset);
+            // digit 0 of the consumer is the register tile's slot axis and is kept out of the runs
             std::vector<std::pair<int,int> > maps;
             for(int d = 0; d < pv.ncut; ++d) {
                 int pos = find_pos(op, pv.cutset[d]);
                 if(pos == SLK_POS_PEEL) peel_shift = 2 * d;
+                else if(pos == 0) d0_shift = 2 * d;
                 else maps.push_back(std::make_pair(d, pos));
             }
             std::vector<uint32_t> runs;
@@ -271,7 +283,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
                 q = e;
             }
             pr.stream.push_back((uint32_t) pr.mat_off[op.prev[j]]);
-            pr.stream.push_back(peel_shift | ((uint32_t) runs.size() << 8));
+            pr.stream.push_back(peel_shift | ((uint32_t) runs.size() << 8) | (d0_shift << 16));
             for(size_t q = 0; q < runs.size(); q += 2) {
                 uint32_t w = runs[q];
                 if(q + 1 < runs.size()) w |= runs[q + 1] << 16;
@@ -291,16 +303,19 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
 
     // ---- geometry ----
     const int N = pb.n_members;
-    pr.prog_smem_bytes = round_up((int)(pr.stream.size() * 4 + pr.op_start.size() * 2 + pr.items.size() * 4 +
+    pr.prog_smem_bytes = round_up((int)(pr.stream.size() * 4 + pr.lpf.size() * 4 + pr.flevel_quads.size() * 4 +
+                                        pr.op_start.size() * 2 + pr.lops.size() * 2 +
                                         pr.flevel_start.size() * 2 + pr.bops.size() * 2 +
                                         pr.blevel_start.size() * 2 + 64), 16);
-    const int table_bytes = slk_team_layout(N, pb.n_founders, nops, 0).total;
+    const int tpc_doubles = trait ? 4 : 16;
+    pr.table_doubles_per_child = tpc_doubles;
+    const int table_bytes = slk_team_layout(N, pb.n_founders, nops, 0, tpc_doubles).total;
     const long work = trait ? pr.valid_cells : hp.sum_cells;
     int team = 32;
     if(work > 1024)  team = 64;
     if(work > 4096)  team = 128;
-    if(work > 12288) team = 256;
-    if(work > 49152) team = 512;
+    if(work > 8192)  team = 256;
+    if(work > 16384) team = 512;
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
     if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
     pr.team_threads = team;
@@ -335,7 +350,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         smem_doubles = cut;
     }
     pr.smem_doubles = smem_doubles;
-    pr.team_smem_bytes = slk_team_layout(N, pb.n_founders, nops, smem_doubles).total;
+    pr.team_smem_bytes = slk_team_layout(N, pb.n_founders, nops, smem_doubles, tpc_doubles).total;
 }
 
 bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
@@ -463,7 +478,7 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
     hp.ls.arena_doubles = hp.lod.arena_doubles = 0;
     emit_program(pb, hp, false, hp.ls);
     emit_program(pb, hp, true, hp.lod);
-    if(hp.ls.stream.size() > 65535 || hp.ls.items.size() > 65535 || hp.lod.items.size() > 65535) {
+    if(hp.ls.stream.size() > 65535 || hp.lod.stream.size() > 65535) {
         err = "peel program too large for 16-bit offsets"; return false;
     }
     return true;

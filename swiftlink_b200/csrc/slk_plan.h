@@ -14,7 +14,9 @@ namespace slk {
 struct HostProgram {
     std::vector<uint32_t> stream;
     std::vector<uint16_t> op_start;
-    std::vector<uint32_t> items;
+    std::vector<uint16_t> lops;
+    std::vector<uint32_t> lpf;
+    std::vector<uint32_t> flevel_quads;
     std::vector<uint16_t> flevel_start;
     std::vector<uint16_t> bops;
     std::vector<uint16_t> blevel_start;
@@ -25,6 +27,7 @@ struct HostProgram {
     int cta_threads;
     int prog_smem_bytes;
     int team_smem_bytes;
+    int table_doubles_per_child;
     long valid_cells;                // static valid cells (trait) or dense cells (sampler)
 };
 

@@ -6,8 +6,12 @@
 //
 //   program stream   one variable-length record of 32-bit words per peel op (layout below),
 //                    staged once per CTA into shared memory;
-//   items            the forward schedule: ops grouped into dependency levels, each op split
-//                    into chunks of SLK_CHUNK valid cells; one warp executes one item;
+//   lops / lpf       the forward schedule: ops grouped into dependency levels; inside a level the
+//                    ROWS of all ops (a row = one valid assignment of cutset digits 1..c-1; the
+//                    thread that owns it evaluates the 4 values of digit 0 x 4 peel genotypes)
+//                    form one index space, lpf = exclusive prefix of rows per op, so every thread
+//                    of the team finds its (op, row) by a short binary search -- a level of 60
+//                    small ops costs one pass, not 60 warp-items;
 //   bops             the backward (sampling) schedule: ops grouped into levels by "who peels
 //                    my cutset", four lanes per op;
 //   arena            one slab of doubles per team holding every live peel matrix; offsets
@@ -22,8 +26,7 @@
 
 #include <stdint.h>
 
-#define SLK_CHUNK      128          // valid cells per forward item (4 per lane)
-#define SLK_SLOTS      (SLK_CHUNK / 32)
+#define SLK_SLOTS      4            // cells per thread per quad (16 independent product chains)
 #define SLK_POS_PEEL   15           // digit position meaning "the peel node itself"
 #define SLK_NO_SHIFT   0xFF
 
@@ -39,7 +42,9 @@
 //  then per previous function:
 //        word A  arena offset of the consumed matrix
 //        word B  peel_shift[0:8) (SLK_NO_SHIFT if the peel node is not one of its keys) | nruns[8:16)
-//        ceil(nruns/2) words of 16-bit runs: src_shift[0:5) | dst_shift[5:10) | nbits[10:15)
+//                | d0_shift[16:24) (where the consumer's cutset digit 0 sits in it, or SLK_NO_SHIFT)
+//        ceil(nruns/2) words of 16-bit runs over the consumer's digits 1..c-1:
+//                src_shift[0:5) | dst_shift[5:10) | nbits[10:15)
 //  then per child (CHILD_PEEL: the peel node itself; PARENT_PEEL: cutset members that are its
 //  offspring, cutset order):
 //        person[0:16) | kid_pos[16:20) | mat_pos[20:24) | pat_pos[24:28) | male[28]
@@ -48,12 +53,13 @@
 struct SlkProgram {
     const uint32_t* stream;         // [stream_words]
     const uint16_t* op_start;       // [nops] word offset of each record
-    const uint32_t* items;          // op[0:16) | chunk[16:32)
-    const uint16_t* flevel_start;   // [n_flevels + 1] into items
+    const uint16_t* lops;           // [nops] ops in forward-level order (largest first inside a level)
+    const uint32_t* lpf;            // [nops] quads before this op inside its level
+    const uint32_t* flevel_quads;   // [n_flevels] quads of each level
+    const uint16_t* flevel_start;   // [n_flevels + 1] into lops
     const uint16_t* bops;           // ops in backward-level order
     const uint16_t* blevel_start;   // [n_blevels + 1] into bops
     int stream_words;
-    int n_items;
     int n_flevels;
     int n_blevels;
     int arena_doubles;              // whole arena
@@ -62,6 +68,7 @@ struct SlkProgram {
     int cta_threads;
     int prog_smem_bytes;            // CTA-shared staging of stream/op_start/items/levels
     int team_smem_bytes;            // per team: arena prefix + tables
+    int table_doubles_per_child;    // 16 (sampler) or 4 (trait)
 };
 
 struct SlkDevPlan {
@@ -86,7 +93,7 @@ struct SlkDevPlan {
 // launches and by the kernels to carve the slab.
 struct SlkTeamLayout {
     int arena;      // smem_doubles doubles
-    int tables;     // (N-F)*4 doubles: sampler transmission u-values / trait recombination weights
+    int tables;     // (N-F)*k doubles: sampler transmission tables (k = 16) / trait recombination weights (k = 4)
     int scal;       // 16 doubles of per-unit scalars (thetas, founder priors)
     int lmw;        // nops x uint64 per-locus legal masks of each op's cutset (sampler)
     int bytes;      // 4 byte arrays of round16(N): gcode row, dg left, dg right, sampled genotypes
@@ -98,11 +105,11 @@ struct SlkTeamLayout {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline SlkTeamLayout slk_team_layout(int N, int F, int nops, int smem_doubles) {
+static inline SlkTeamLayout slk_team_layout(int N, int F, int nops, int smem_doubles, int table_doubles_per_child) {
     SlkTeamLayout L;
     L.arena = 0;
     L.tables = (smem_doubles * 8 + 15) & ~15;
-    L.scal = L.tables + (N - F) * 4 * 8;
+    L.scal = L.tables + (N - F) * table_doubles_per_child * 8;
     L.lmw = L.scal + 16 * 8;
     L.bytes = L.lmw + nops * 8;
     L.nbytes = (N + 15) & ~15;

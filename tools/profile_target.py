@@ -1,0 +1,46 @@
+"""Small driver for ncu / timing experiments on the bench workload (not part of the product).
+
+    python tools/profile_target.py [--markers M] [--sweeps S] [--lod L]
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--markers", type=int, default=bench.N_MARKERS)
+    ap.add_argument("--sweeps", type=int, default=5)
+    ap.add_argument("--lod", type=int, default=1)
+    ap.add_argument("--time", action="store_true")
+    args = ap.parse_args()
+    from swiftlink_b200 import capi, host as H
+    paths = bench.workload_files(args.markers, "prof")
+    hst = H.Host(*paths, lodscores=bench.N_LOD)
+    assert hst.set_peel_by_names(bench.load_order()["order"])
+    plan = H.PlanFromHost(hst)
+    print({k: v for k, v in plan.stats().items()})
+    chain = capi.Chain(plan, seed=1)
+    chain.sequential_imputation(0, hst.M // 2)
+    chain.sync()
+    t0 = time.time()
+    for it in range(args.sweeps):
+        chain.lsampler_sweep(1 + it)
+    chain.sync()
+    t1 = time.time()
+    for _ in range(args.lod):
+        chain.lodscore_accumulate()
+    chain.sync()
+    t2 = time.time()
+    if args.time:
+        print("sweep ms %.3f   lod pass ms %.3f" % (1e3 * (t1 - t0) / max(args.sweeps, 1), 1e3 * (t2 - t1) / max(args.lod, 1)))
+
+
+if __name__ == "__main__":
+    main()
