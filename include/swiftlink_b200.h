@@ -196,6 +196,10 @@ int slk_debug_lsampler_step(slk_chain* chain, uint64_t iteration, int locus, int
    and, if matrices != NULL, the dense peel matrices of position dump_k */
 int slk_debug_lod_interval(slk_chain* chain, int interval, double* result, double* prob,
                            int dump_k, double* matrices);
+/* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
+   clock64() stamps of the first team's first locus: start, after staging, after every forward
+   level, after every backward level, after the indicators.  Returns the number of stamps. */
+int slk_debug_lsampler_trace(slk_chain* chain, uint64_t iteration, int offset, long long* stamps, int cap);
 /* Philox block and the uniform draw used by the kernels, evaluated on the device */
 int slk_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int slk_debug_uniform(int device, uint64_t seed, uint32_t chain, uint64_t iteration, uint32_t locus,

@@ -26,7 +26,7 @@ SYMBOLS = [
     "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood",
-    "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval",
+    "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
     "slk_debug_philox", "slk_debug_uniform", "slk_measure_fp64_peak",
 ]
 
@@ -257,6 +257,13 @@ class Chain(object):
                                               int(ignore_right), _ptr(pmk, C.c_int32), _ptr(dist, C.c_double),
                                               C.byref(res)))
         return res.value, pmk, dist
+
+    def debug_trace(self, iteration=0, offset=0):
+        buf = (C.c_longlong * 512)()
+        n = self.L.slk_debug_lsampler_trace(self.h, C.c_uint64(iteration), int(offset), buf, 512)
+        if n < 0:
+            _check(n)
+        return np.array(buf[:n], dtype=np.int64)
 
     def debug_lod_interval(self, interval, dump_k=-1):
         res = np.zeros(self.plan.nlod); prob = np.zeros(self.plan.nlod)

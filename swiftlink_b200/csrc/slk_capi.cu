@@ -648,6 +648,31 @@ int slk_debug_lod_interval(slk_chain* c, int interval, double* result, double* p
     return check_device_error(c);
 }
 
+int slk_debug_lsampler_trace(slk_chain* c, uint64_t iteration, int offset, long long* stamps, int cap) {
+    if(!c || !stamps || cap < 8) return fail(SLK_ERR_INVALID, "bad argument");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    CU(cudaSetDevice(p->device));
+    const int n = d.ls.n_flevels + d.ls.n_blevels + 3;
+    if(n > cap) return fail(SLK_ERR_INVALID, "need room for %d stamps", n);
+    long long* dev = 0;
+    CU(cudaMalloc((void**) &dev, sizeof(long long) * n));
+    CU(cudaMemsetAsync(dev, 0, sizeof(long long) * n, c->stream));
+    SlkLaunch L = base_launch(c);
+    L.iteration = iteration;
+    L.window = 2;
+    L.offset = offset & 1;
+    L.nunits = (d.M - L.offset + 1) / 2;
+    L.trace = dev;
+    const int tpc = d.ls.cta_threads / d.ls.team_threads;
+    launch_ls_by_team(d.ls.team_threads, L, grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count), d.ls.cta_threads, p->ls_cta_smem, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(stamps, dev, sizeof(long long) * n, cudaMemcpyDeviceToHost, c->stream));
+    int rc = check_device_error(c);
+    cudaFree(dev);
+    return rc == SLK_OK ? n : rc;
+}
+
 int slk_debug_philox(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     if(slk_device_count() <= device) return fail(SLK_ERR_NO_DEVICE, "no usable CUDA device %d", device);
     CU(cudaSetDevice(device));

@@ -55,6 +55,7 @@ struct SlkLaunch {
     int* dump_pmk;               // [N]
     double* dump_result;         // sampler: [1]; LOD: [nunits]
     double* dump_prob;           // LOD: [nunits]
+    long long* trace;            // optional: clock64() stamps of team 0's first unit (tuning aid)
 };
 
 __constant__ uint8_t c_glist[16] = {
@@ -103,6 +104,7 @@ struct TeamMem {
     double* tables;              // (N-F)*4
     double* scal;                // 16
     unsigned long long* lmw;     // nops
+    double* ru;                  // nops uniform draws of the current locus (sampler)
     uint8_t* gc;                 // gcode row of this locus
     uint8_t* dgl;                // descent graph at the left neighbour / interval start
     uint8_t* dgr;                // right neighbour / interval end
@@ -244,6 +246,7 @@ __device__ __forceinline__ TeamMem carve_team(const SlkLaunch& L, const SlkProgr
     tm.tables = (double*)(base + lay.tables);
     tm.scal = (double*)(base + lay.scal);
     tm.lmw = (unsigned long long*)(base + lay.lmw);
+    tm.ru = (double*)(base + lay.ru);
     tm.gc = base + lay.bytes;
     tm.dgl = tm.gc + lay.nbytes;
     tm.dgr = tm.dgl + lay.nbytes;
@@ -256,7 +259,7 @@ __device__ __forceinline__ TeamMem carve_team(const SlkLaunch& L, const SlkProgr
 __device__ __forceinline__ void load_prior(const TeamMem& tm, int person, double tc[4]) {
     uint32_t cls = tm.gc[person] >> 4;
 #pragma unroll
-    for(int g = 0; g < 4; ++g) tc[g] = (cls < 5u) ? c_prior[cls < 5u ? cls : 0u][g] : tm.scal[8 + (cls - 5u) * 4 + g];
+    for(int g = 0; g < 4; ++g) tc[g] = tm.scal[16 + cls * 4 + g];      // classes 0-4 fixed, 5-6 founder priors of this locus
 }
 
 // ---- one forward tile, executed by one thread -----------------------------------------------
@@ -559,13 +562,20 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         }
         const bool has_left = (locus != 0), has_right = (locus != M - 1);
 
+        const bool tracing = L.trace != 0 && gteam == 0 && unit == gteam && tid == 0;
+        int tstamp = 0;
+        if(tracing) L.trace[tstamp++] = clock64();
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
         for(int i = tid; i < N; i += T) {
             tm.gc[i] = P.gcode[(size_t) locus * N + i];
             tm.dgl[i] = has_left ? L.dgp[(size_t)(locus - 1) * N + i] : 0;
             tm.dgr[i] = has_right ? L.dgp[(size_t)(locus + 1) * N + i] : 0;
         }
-        if(tid < 8) tm.scal[8 + tid] = P.fprior[(size_t) locus * 8 + tid];
+        for(int i = tid; i < 28; i += T)
+            tm.scal[16 + i] = (i < 20) ? c_prior[i >> 2][i & 3] : P.fprior[(size_t) locus * 8 + (i - 20)];
+        // the genotype draws of this locus, one per peel op (Philox keyed by chain, iteration, locus, op)
+        for(int op = tid; op < P.nops; op += T)
+            tm.ru[op] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) locus, (uint32_t) op);
         if(tid == 0) {
             // sampler_rfunction.h:84-100: theta2 (left interval) / theta (right interval)
             double th2 = 1.0, ath2 = 1.0, th = 1.0, ath = 1.0;
@@ -615,6 +625,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         }
         team_sync<T>(team);
 
+        if(tracing) L.trace[tstamp++] = clock64();
         // ---- forward peel, level by level
         for(int lv = 0; lv < pr.n_flevels; ++lv) {
             const int b = pg.flevel_start[lv], e = pg.flevel_start[lv + 1];
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
                 }
             }
             team_sync<T>(team);
+            if(tracing) L.trace[tstamp++] = clock64();
         }
 
         const uint32_t* last_rec = pg.stream + pg.op_start[P.last_op];
@@ -686,7 +698,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
 #pragma unroll
                         for(int k = 0; k < 4; ++k) dd[k] /= total;
                     }
-                    const double r = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) locus, (uint32_t) op);
+                    const double r = tm.ru[op];
                     double cum = 0.0;
                     int last = 0, chosen = -1;
 #pragma unroll
@@ -701,6 +713,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
                 }
             }
             team_sync<T>(team);
+            if(tracing) L.trace[tstamp++] = clock64();
         }
 
         // ---- meiosis indicators (locus_sampler2.cc:32-125)
@@ -742,6 +755,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
             }
             L.dgp[(size_t) locus * N + i] = (uint8_t) out;
         }
+        if(tracing) L.trace[tstamp++] = clock64();
         if(DBG && L.dump_pmk) for(int i = tid; i < N; i += T) L.dump_pmk[i] = tm.pmk[i];
         if(L.si_start >= 0) __threadfence();        // the next locus of the walk reads the row just written
         team_sync<T>(team);

@@ -229,7 +229,14 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     pr.bops.clear();
     pr.blevel_start.assign(1, 0);
     for(int l = 0; l < n_blevels; ++l) {
-        for(int i = nops - 1; i >= 0; --i) if(blevel[i] == l) pr.bops.push_back((uint16_t) i);
+        // four lanes per op: keep ops of the same shape together so a warp follows one control flow
+        std::vector<int> here;
+        for(int i = nops - 1; i >= 0; --i) if(blevel[i] == l) here.push_back(i);
+        std::stable_sort(here.begin(), here.end(), [&](int a, int b) {
+            const slk_peel_op& x = pb.ops[a]; const slk_peel_op& y = pb.ops[b];
+            return std::make_tuple(x.type, x.nprev, x.nchild, x.ncut) < std::make_tuple(y.type, y.nprev, y.nchild, y.ncut);
+        });
+        for(size_t q = 0; q < here.size(); ++q) pr.bops.push_back((uint16_t) here[q]);
         pr.blevel_start.push_back((uint16_t) pr.bops.size());
     }
 
@@ -315,17 +322,26 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     if(work > 1024)  team = 64;
     if(work > 4096)  team = 128;
     if(work > 8192)  team = 256;
-    if(work > 16384) team = 512;
+    if(work > 16384 && trait) team = 512;
+    // One unit is latency bound (a chain of ~50 dependent levels), so the SM needs several units in
+    // flight.  When the whole arena of a team would crowd the others out of shared memory, only the
+    // small matrices (cutset <= 4, the ones hit by the many small latency-bound ops) stay in shared
+    // memory and the few large ones go to the L2-resident global slab (measured on B200 with the
+    // 200-member pedigree: 8.4 ms per sweep against 11.5 ms with everything in shared memory).
+    int small_doubles = 0;
+    for(int i = 0; i < nops; ++i) if(pb.ops[i].ncut <= 4) small_doubles = std::max(small_doubles, pr.mat_off[i] + (1 << (2 * pb.ops[i].ncut)));
+    bool hybrid = !trait && (size_t) pr.arena_doubles * 8 + table_bytes > 100 * 1024;
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
     if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
     pr.team_threads = team;
-    pr.cta_threads = std::max(team, env_int("SLK_CTA_THREADS", 128));
+    pr.cta_threads = std::max(team, env_int("SLK_CTA_THREADS", hybrid ? 512 : 128));
 
     const int teams_per_cta = pr.cta_threads / team;
     const int budget = kSmemPerBlockMax - pr.prog_smem_bytes;           // one CTA per SM worst case
     int per_team_budget = budget / teams_per_cta - table_bytes;
     if(per_team_budget < 0) per_team_budget = 0;
     int smem_doubles = std::min(pr.arena_doubles, per_team_budget / 8);
+    if(hybrid) smem_doubles = std::min(smem_doubles, small_doubles);
     smem_doubles = env_int(trait ? "SLK_LOD_SMEM_DOUBLES" : "SLK_LS_SMEM_DOUBLES", smem_doubles);
     smem_doubles = std::min(smem_doubles, std::min(pr.arena_doubles, per_team_budget / 8));
     if(smem_doubles < pr.arena_doubles) {

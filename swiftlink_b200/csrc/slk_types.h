@@ -94,8 +94,9 @@ struct SlkDevPlan {
 struct SlkTeamLayout {
     int arena;      // smem_doubles doubles
     int tables;     // (N-F)*k doubles: sampler transmission tables (k = 16) / trait recombination weights (k = 4)
-    int scal;       // 16 doubles of per-unit scalars (thetas, founder priors)
+    int scal;       // 48 doubles: thetas [0..4), class priors [16..36), founder priors of the locus [36..44)
     int lmw;        // nops x uint64 per-locus legal masks of each op's cutset (sampler)
+    int ru;         // nops doubles: the genotype draws of the current locus (sampler)
     int bytes;      // 4 byte arrays of round16(N): gcode row, dg left, dg right, sampled genotypes
     int nbytes;     // round16(N)
     int red;        // 32 ints of reduction scratch
@@ -110,8 +111,9 @@ static inline SlkTeamLayout slk_team_layout(int N, int F, int nops, int smem_dou
     L.arena = 0;
     L.tables = (smem_doubles * 8 + 15) & ~15;
     L.scal = L.tables + (N - F) * table_doubles_per_child * 8;
-    L.lmw = L.scal + 16 * 8;
-    L.bytes = L.lmw + nops * 8;
+    L.lmw = L.scal + 48 * 8;
+    L.ru = L.lmw + nops * 8;
+    L.bytes = L.ru + nops * 8;
     L.nbytes = (N + 15) & ~15;
     L.red = L.bytes + 4 * L.nbytes;
     L.total = (L.red + 32 * 4 + 15) & ~15;

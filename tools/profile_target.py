@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=5)
     ap.add_argument("--lod", type=int, default=1)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--trace", action="store_true")
     args = ap.parse_args()
     from swiftlink_b200 import capi, host as H
     paths = bench.workload_files(args.markers, "prof")
@@ -38,6 +39,15 @@ def main():
         chain.lodscore_accumulate()
     chain.sync()
     t2 = time.time()
+    if args.trace:
+        import numpy as np
+        st = plan.stats()
+        t = chain.debug_trace(99, 0)
+        d = np.diff(t)
+        nf, nb = int(st["ls_flevels"]), int(st["ls_blevels"])
+        print("stage %d | forward levels (sum %d): %s | backward levels (sum %d): %s | indicators %d | total %d cycles" %
+              (d[0], d[1:1 + nf].sum(), d[1:1 + nf].tolist(), d[1 + nf:1 + nf + nb].sum(), d[1 + nf:1 + nf + nb].tolist(),
+               d[1 + nf + nb], t[-1] - t[0]))
     if args.time:
         print("sweep ms %.3f   lod pass ms %.3f" % (1e3 * (t1 - t0) / max(args.sweeps, 1), 1e3 * (t2 - t1) / max(args.lod, 1)))
 
