@@ -189,14 +189,31 @@ __device__ __forceinline__ uint32_t phased_trait(bool sex_linked, bool male, uin
     return pa ? SLK_UA : SLK_UU;
 }
 
-// trait_rfunction.cc:106-127: sum over the (i, j) that produce the kid's genotype
+// trait_rfunction.cc:106-127: sum, in (i, j) order, of the recombination weights of the
+// transmitted-allele choices that produce the kid's genotype.  The choices factorise: the kid's
+// genotype fixes whether the maternal (paternal) allele must be the A allele, and the parent's
+// genotype fixes which of its two alleles (i = 0, 1) qualify -- a 2-bit mask per parent, read
+// from a packed table indexed by (parent genotype, required) [rfunction.h:81-107].
 __device__ __forceinline__ double trait_child_sum(bool sex_linked, bool male, uint32_t m, uint32_t f,
                                                   uint32_t kg, const double* w) {
-    double s = 0.0;
-#pragma unroll
-    for(uint32_t ij = 0; ij < 4; ++ij) {
-        if(phased_trait(sex_linked, male, m, f, ij >> 1, ij & 1u) == kg) s += w[ij];
+    const uint32_t LUT = 0x96C3u;       // nibble per parent genotype: (mask if A required) << 2 | (mask if U required)
+    uint32_t mi, mj;
+    if(sex_linked && male) {
+        if(kg >= 2u) return 0.0;                       // a son is never heterozygous (rfunction.cc:101-103)
+        mi = (LUT >> (4u * m + 2u * (kg == SLK_AA ? 1u : 0u))) & 3u;
+        mj = 3u;
     }
+    else {
+        const uint32_t ma = ((kg >> 1) ^ kg) & 1u;     // AA, AU: maternal allele is A
+        const uint32_t pa = kg & 1u;                   // AA, UA: paternal allele is A
+        mi = (LUT >> (4u * m + 2u * ma)) & 3u;
+        mj = (LUT >> (4u * f + 2u * pa)) & 3u;
+    }
+    double s = 0.0;
+    if((mi & 1u) && (mj & 1u)) s += w[0];
+    if((mi & 1u) && (mj & 2u)) s += w[1];
+    if((mi & 2u) && (mj & 1u)) s += w[2];
+    if((mi & 2u) && (mj & 2u)) s += w[3];
     return s;
 }
 
@@ -429,34 +446,62 @@ __device__ __forceinline__ void run_tile(const SlkLaunch& L, const Prog& pg, con
         pw += 2 + ((nruns + 1) >> 1);
     }
 
-    // ---- transmission to the children / recombination weights, then the sum over the peel node
+    // ---- transmission to the children / recombination weights
+    if(TRAIT && type == SLK_CHILD_PEEL) {
+        const double* w = tm.tables + 4 * (peel - P.F);
+#pragma unroll
+        for(int s = 0; s < NS; ++s)
+#pragma unroll
+            for(int v = 0; v < 4; ++v) tmp[s][v] *= w[v];
+    }
+    else if(type == SLK_PARENT_PEEL) {
+        // child_prob = prod_k T_k (sampler_rfunction.cc:258-279 / trait_rfunction.cc:91-129).  A child
+        // whose own, mother's and father's digits are all outside cutset digit 0 has the same factor
+        // in the four slots of the tile: it is evaluated once per peel genotype, not sixteen times.
+#pragma unroll
+        for(int v = 0; v < 4; ++v) {
+            bool any = false;
+#pragma unroll
+            for(int s = 0; s < NS; ++s) any = any || (tmp[s][v] != 0.0);
+            if(!any) continue;
+            double cp[NS];
+#pragma unroll
+            for(int s = 0; s < NS; ++s) cp[s] = 1.0;
+            for(int k = 0; k < nkids; ++k) {
+                const uint32_t kd = kw[k];
+                const uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u, kp = (kd >> 16) & 15u;
+                const bool male = (kd >> 28) & 1u;
+                const double* tb = tm.tables + (TRAIT ? 4 : 16) * ((int)(kd & 0xffffu) - P.F);
+                if(NS > 1 && mp != 0u && fp != 0u && kp != 0u) {
+                    const uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : ((rowcell >> (2u * mp)) & 3u);
+                    const uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : ((rowcell >> (2u * fp)) & 3u);
+                    const uint32_t kg = (rowcell >> (2u * kp)) & 3u;
+                    const double t = TRAIT ? trait_child_sum(sex_linked, male, m, f, kg, tb)
+                                           : trans_prob(sex_linked, male, m, f, kg, tb);
+#pragma unroll
+                    for(int s = 0; s < NS; ++s) cp[s] *= t;
+                }
+                else {
+#pragma unroll
+                    for(int s = 0; s < NS; ++s) {
+                        const uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(mp, s);
+                        const uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(fp, s);
+                        const uint32_t kg = SLK_DIG(kp, s);
+                        cp[s] *= TRAIT ? trait_child_sum(sex_linked, male, m, f, kg, tb)
+                                       : trans_prob(sex_linked, male, m, f, kg, tb);
+                    }
+                }
+            }
+#pragma unroll
+            for(int s = 0; s < NS; ++s) tmp[s][v] *= cp[s];
+        }
+    }
+
+    // ---- the sum over the peel node
     const int dense_off = (int) rec[2];
 #pragma unroll
     for(int s = 0; s < NS; ++s) {
         if(!act[s]) continue;
-        if(TRAIT && type == SLK_CHILD_PEEL) {
-            const double* w = tm.tables + 4 * (peel - P.F);
-#pragma unroll
-            for(int v = 0; v < 4; ++v) tmp[s][v] *= w[v];
-        }
-        else if(type == SLK_PARENT_PEEL) {
-#pragma unroll
-            for(int v = 0; v < 4; ++v) {
-                if(tmp[s][v] == 0.0) continue;
-                double cp = 1.0;
-                for(int k = 0; k < nkids; ++k) {
-                    const uint32_t kd = kw[k];
-                    const uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u, kp = (kd >> 16) & 15u;
-                    const uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(mp, s);
-                    const uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(fp, s);
-                    const uint32_t kg = SLK_DIG(kp, s);
-                    const double* tb = tm.tables + (TRAIT ? 4 : 16) * ((int)(kd & 0xffffu) - P.F);
-                    cp *= TRAIT ? trait_child_sum(sex_linked, (kd >> 28) & 1u, m, f, kg, tb)
-                                : trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tb);
-                }
-                tmp[s][v] *= cp;
-            }
-        }
         double total = 0.0;
 #pragma unroll
         for(int v = 0; v < 4; ++v) total += tmp[s][v];
