@@ -711,12 +711,18 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
         // ---- backward pass: SamplerRfunction::sample (sampler_rfunction.cc:159-188), 4 lanes per op
         for(int lv = 0; lv < pr.n_blevels; ++lv) {
             const int b = pg.blevel_start[lv], e = pg.blevel_start[lv + 1];
-            for(int base = b; base < e; base += T / 4) {
-                const int q = base + (tid >> 2);
+            // one op per warp (lanes 0-3 = the four candidate genotypes): ops of different shapes in
+            // one warp would serialise each other's control flow on this latency-critical chain
+            // When the level has no more ops than the team has warps every op gets its own warp (lanes
+            // 0-3 = the four candidate genotypes): ops of different shapes packed in one warp would
+            // serialise each other's control flow on this latency-critical chain.
+            const bool spread = (e - b) <= T / 32;
+            for(int base = b; base < e; base += (spread ? T / 32 : T / 4)) {
+                const int q = base + (spread ? (tid >> 5) : (tid >> 2));
                 const uint32_t g = tid & 3u;
                 double d = 0.0;
                 int op = 0, peel = 0;
-                const bool live = q < e;
+                const bool live = q < e && (!spread || lane < 4);
                 if(live) {
                     op = pg.bops[q];
                     const uint32_t* rec = pg.stream + pg.op_start[op];

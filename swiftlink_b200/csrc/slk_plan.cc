@@ -322,7 +322,6 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     if(work > 1024)  team = 64;
     if(work > 4096)  team = 128;
     if(work > 8192)  team = 256;
-    if(work > 16384 && trait) team = 512;
     // One unit is latency bound (a chain of ~50 dependent levels), so the SM needs several units in
     // flight.  When the whole arena of a team would crowd the others out of shared memory, only the
     // small matrices (cutset <= 4, the ones hit by the many small latency-bound ops) stay in shared
@@ -330,7 +329,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     // 200-member pedigree: 8.4 ms per sweep against 11.5 ms with everything in shared memory).
     int small_doubles = 0;
     for(int i = 0; i < nops; ++i) if(pb.ops[i].ncut <= 4) small_doubles = std::max(small_doubles, pr.mat_off[i] + (1 << (2 * pb.ops[i].ncut)));
-    bool hybrid = !trait && (size_t) pr.arena_doubles * 8 + table_bytes > 100 * 1024;
+    const bool hybrid = (size_t) pr.arena_doubles * 8 + table_bytes > 100 * 1024;
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
     if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
     pr.team_threads = team;
@@ -341,7 +340,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     int per_team_budget = budget / teams_per_cta - table_bytes;
     if(per_team_budget < 0) per_team_budget = 0;
     int smem_doubles = std::min(pr.arena_doubles, per_team_budget / 8);
-    if(hybrid) smem_doubles = std::min(smem_doubles, small_doubles);
+    if(hybrid && !trait) smem_doubles = std::min(smem_doubles, small_doubles);
     smem_doubles = env_int(trait ? "SLK_LOD_SMEM_DOUBLES" : "SLK_LS_SMEM_DOUBLES", smem_doubles);
     smem_doubles = std::min(smem_doubles, std::min(pr.arena_doubles, per_team_budget / 8));
     if(smem_doubles < pr.arena_doubles) {
