@@ -322,19 +322,11 @@ def run_ours(args, rank, world, local_rank):
     fp64_peak = capi.measure_fp64_peak(local_rank)
 
     # ---- merge replicates (LODscores::merge_results, lod_score.h:98-105) -----------------------------------
+    from swiftlink_b200 import dist as sdist
     raw, count = chain.lodscore_read()
     raw = torch.from_numpy(raw.ravel().copy()).cuda()
-    merged_count = count
-    if dist is not None:
-        mx = raw.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        ex = torch.exp(raw - mx)
-        dist.all_reduce(ex, op=dist.ReduceOp.SUM)
-        raw = mx + torch.log(ex)
-        c = torch.tensor([count], device="cuda", dtype=torch.int64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        merged_count = int(c.item())
-    lod = (raw - np.log(max(merged_count, 1)) - trait_prob) / np.log(10.0)
+    raw, merged_count = sdist.merge_lod(raw, count)
+    lod = sdist.normalise(raw, merged_count, trait_prob)
     lod_max = float(lod.max().item())
     lod_argmax = int(lod.argmax().item()) // N_LOD
 

@@ -209,18 +209,19 @@ KNOWN_ATTEMPT = {(200, 10000, DEFAULT_SEED): 533}
 
 
 def generate(n_members=200, n_markers=10000, seed=DEFAULT_SEED, spacing_cm=0.01, n_generations=6,
-             trait_freq=1e-4, start_cm=10.0, penetrance=(0.001, 0.001, 0.999)):
+             trait_freq=1e-4, start_cm=10.0, penetrance=(0.001, 0.001, 0.999),
+             loops=(4, 12), min_generation=5, founder_frac=(0.25, 0.36), min_affected=2, cousin_prob=0.1):
     """Returns a dict describing the pedigree (arrays indexed by file order, ids are 1-based)."""
     hint = KNOWN_ATTEMPT.get((n_members, n_markers, seed))
     attempts = ([hint] if hint is not None else []) + list(range(1000))
     for attempt in attempts:
         rng = np.random.default_rng([seed, attempt])
-        father, mother, sex, gen, loops = _build_structure(rng, n_members, n_generations)
+        father, mother, sex, gen, nloops = _build_structure(rng, n_members, n_generations, cousin_prob)
         n = len(father)
         n_founders = int((father < 0).sum())
-        if n != n_members or loops < 4 or loops > 12 or gen.max() < 5:
+        if n != n_members or nloops < loops[0] or nloops > loops[1] or gen.max() < min_generation:
             continue
-        if not (0.25 <= n_founders / float(n) <= 0.36):
+        if not (founder_frac[0] <= n_founders / float(n) <= founder_frac[1]):
             continue
 
         theta = 0.5 * (1.0 - np.exp(-2.0 * spacing_cm / 100.0))
@@ -231,7 +232,7 @@ def generate(n_members=200, n_markers=10000, seed=DEFAULT_SEED, spacing_cm=0.01,
         carrier_label = 0               # maternal strand of founder 0
         affected = (labels[:, 0, mid] == carrier_label) & (labels[:, 1, mid] == carrier_label)
         typed = gen >= gen.max() - 1
-        if int((affected & typed).sum()) < 2:
+        if int((affected & typed).sum()) < min_affected:
             continue
 
         maf = rng.uniform(0.1, 0.5, size=n_markers)
@@ -245,7 +246,7 @@ def generate(n_members=200, n_markers=10000, seed=DEFAULT_SEED, spacing_cm=0.01,
         pos_cm = start_cm + spacing_cm * np.arange(n_markers)
         return dict(father=father, mother=mother, sex=sex, generation=gen, typed=typed,
                     affected=affected, allele1=a_mat, allele2=a_pat, maf=maf, pos_cm=pos_cm,
-                    loops=loops, n_founders=n_founders, trait_freq=trait_freq, seed=seed,
+                    loops=nloops, n_founders=n_founders, trait_freq=trait_freq, seed=seed,
                     attempt=attempt, penetrance=tuple(penetrance))
     raise RuntimeError("could not build a pedigree meeting the constraints")
 

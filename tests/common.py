@@ -9,7 +9,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["loop", "xlinked", "east"]
+CASES = ["loop", "xlinked", "east", "inbred"]
+FORCE_X = {"loop": 0, "xlinked": 1, "east": 0, "inbred": 0}
+
+# the generated pedigree behind tests/golden/inbred.npz (must match tests/golden/make_golden.py)
+INBRED = dict(n_members=64, n_markers=16, seed=7, spacing_cm=0.8, n_generations=5, loops=(3, 8), min_generation=4,
+              founder_frac=(0.2, 0.45), min_affected=1, cousin_prob=0.25)
 
 _cache = {}
 
@@ -60,3 +65,15 @@ def matrix_offsets(ops):
         offs.append(o)
         o += 4 ** len(op["cutset"])
     return offs
+
+
+def case_files(name, tmpdir=None):
+    """LINKAGE ped/map/dat of a test case: the reference's examples (shipped inside oracle/_ref)
+    or, for `inbred`, files written by the generator"""
+    if name == "inbred":
+        import tempfile
+        from swiftlink_b200 import synth
+        d = tmpdir or tempfile.mkdtemp(prefix="slk_inbred_")
+        return synth.write_linkage(synth.generate(**INBRED), os.path.join(str(d), "inbred"))
+    from oracle import refapi
+    return refapi.example(name)

@@ -37,7 +37,24 @@ CASES = [
     ("loop", 0, 100000, [0, 1, 2], [0, 1], list(range(101, 111))),
     ("xlinked", 1, 100000, [0, 3, 9], [0, 4, 8], list(range(201, 211))),
     ("east", 0, 1000000, [0, 1, 37, 98, 99], [0, 50, 98], list(range(301, 311))),
+    # not one of the reference's examples: a generated 64-member pedigree with 8 marriage loops,
+    # cutsets up to 5, allele frequencies != 0.5 and untyped non-founders (swiftlink_b200/synth.py);
+    # it is what exposes the reference's "everyone is a founder" marker prior (person.cc:224-299
+    # called from pedigree_parser.cc:153) and exercises 1024-cell peel matrices
+    ("inbred", 0, 200000, [0, 7, 15], [0, 8, 14], list(range(401, 406))),
 ]
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import INBRED               # noqa: E402
+
+
+def case_files(name):
+    if name != "inbred":
+        return R.example(name)
+    import tempfile
+    from swiftlink_b200 import synth
+    ped = synth.generate(**INBRED)
+    return synth.write_linkage(ped, os.path.join(tempfile.mkdtemp(prefix="slk_golden_"), "inbred"))
 
 
 def pack_ops(ops):
@@ -57,10 +74,13 @@ def pack_ops(ops):
 
 
 def main():
+    only = sys.argv[1:]
     R.set_threads(1)
     for name, force_x, peel_iters, loci, intervals, seeds in CASES:
         R.seed(20261017)
-        r = R.Ref(*R.example(name), sex_linked=bool(force_x))
+        if only and name not in only:
+            continue
+        r = R.Ref(*case_files(name), sex_linked=bool(force_x))
         r.build_peel(peel_iters)
         d = O.problem_from_ref(r)
         fx = dict(N=d["N"], F=d["F"], M=d["M"], nlod=d["nlod"], sex_linked=d["sex_linked"])
