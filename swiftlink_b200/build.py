@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswiftlink_b200.so")
+SWIFT = os.path.join(HERE, "swift")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,14 +26,14 @@ NVCC_FLAGS = [
 
 def sources():
     src = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc")) +
-                 glob.glob(os.path.join(CSRC, "host", "*.cc")))
+                 [f for f in glob.glob(os.path.join(CSRC, "host", "*.cc")) if not f.endswith("swift_main.cc")])
     hdr = sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
                  glob.glob(os.path.join(CSRC, "host", "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
     return src, hdr
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(SWIFT):
         return True
     src, hdr = sources()
     t = os.path.getmtime(LIB)
@@ -50,6 +51,10 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # the `swift` command line (swiftlink_b200/swift), linked against the library next to it
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                           "-I", os.path.join(CSRC, "host"), "-o", SWIFT, os.path.join(CSRC, "host", "swift_main.cc"),
+                           "-L", HERE, "-lswiftlink_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

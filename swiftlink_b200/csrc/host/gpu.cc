@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace swiftlink {
 
@@ -65,6 +66,29 @@ double GPUMarkovChain::calc_trait_prob() {
     double v = 0.0;
     die_on(slk_trait_likelihood(plan, &v), "GPUMarkovChain::calc_trait_prob");
     return v;
+}
+
+double GPUMarkovChain::sequential_imputation(DescentGraph& dg, int iterations) {
+    const int M = (int) map->num_markers();
+    if(iterations == 0) {
+        die_on(slk_lsampler_locus_by_locus(chain, 0), "sequential imputation (locus by locus)");
+        die_on(slk_dg_download(chain, dg.get_internal_ptr()), "sequential imputation (download)");
+        return 0.0;
+    }
+    HostRng rng(options.seed ^ (0x5349ull << 32) ^ (uint64_t) seq_num);
+    double best = -1e300;
+    std::vector<int> keep(dg.get_internal_size() / sizeof(int));
+    for(int run = 0; run < iterations; ++run) {
+        double w = 0.0;
+        die_on(slk_sequential_imputation(chain, (uint64_t) run, rng.uniform_int(M), &w), "sequential imputation");
+        if(w > best) {
+            best = w;
+            die_on(slk_dg_download(chain, keep.data()), "sequential imputation (download)");
+        }
+    }
+    memcpy(dg.get_internal_ptr(), keep.data(), dg.get_internal_size());
+    printf("starting likelihood (log10) = %.3f\n", best / log(10.0));
+    return best;
 }
 
 // markov_chain.cc:314-404 with both batches on the device.  The M-sampler (meiosis_sampler.cc,

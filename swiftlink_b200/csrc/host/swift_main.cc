@@ -1,0 +1,164 @@
+// swift_main.cc -- the `swift` command line on top of the device path.  Same flags, input order,
+// messages and output file as the reference's main.cc:185-557 / linkage_program.cc:26-171 for
+// the linkage mode; every chain runs on the GPU (-g is implied, -X is allowed with it, which the
+// reference refuses at main.cc:534-537).  Not supported by this build, and refused explicitly:
+// M-sampler sweeps (-l < 1), --elod, --trace (both need the founder-allele-graph likelihood).
+#include <getopt.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swiftlink_host.h"
+
+using namespace swiftlink;
+
+static void usage(const char* prog) {
+    struct mcmc_options d;
+    fprintf(stderr,
+"Usage: %s [OPTIONS] -p pedfile -m mapfile -d datfile\n"
+"       %s [OPTIONS] -p pedfile -m mapfile -d datfile -l 1.0\n"
+"\n"
+"Input files:\n"
+"  -p pedfile, --pedigree=pedfile\n"
+"  -m mapfile, --map=mapfile\n"
+"  -d datfile, --dat=datfile\n"
+"\n"
+"Output files:\n"
+"  -o outfile, --output=outfile            (default = 'swiftlink.out')\n"
+"\n"
+"MCMC options:\n"
+"  -i NUM,     --iterations=NUM            (default = %d)\n"
+"  -b NUM,     --burnin=NUM                (default = %d)\n"
+"  -s NUM,     --sequentialimputation=NUM  (default = %d)\n"
+"  -x NUM,     --scoringperiod=NUM         (default = %d)\n"
+"  -l FLOAT,   --lsamplerprobability=FLOAT (default = %.1f; this build runs L-sampler sweeps only: pass 1.0)\n"
+"  -n NUM,     --lodscores=NUM             (default = %d)\n"
+"  -R NUM,     --runs=NUM                  (default = %d)\n"
+"\n"
+"Runtime options:\n"
+"  -c NUM,     --cores=NUM                 (accepted, ignored: the samplers run on the GPU)\n"
+"  -g,         --gpu                       (always on)\n"
+"  -D NUM,     --device=NUM                CUDA device (default = 0)\n"
+"\n"
+"Misc:\n"
+"  -X,         --sexlinked\n"
+"  -a,         --affectedonly\n"
+"  -q NUM,     --peelseqiter=NUM           (default = %d)\n"
+"  -S NUM,     --seed=NUM                  Philox seed (default = %llu)\n"
+"  -v,         --verbose\n"
+"  -h,         --help\n"
+"\n",
+    prog, prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
+    d.peelopt_iterations, (unsigned long long) d.seed);
+}
+
+static bool str2int(int& out, const char* s) {
+    char* end;
+    long v = strtol(s, &end, 10);
+    if(*s == '\0' || *end != '\0') return false;
+    out = (int) v;
+    return true;
+}
+
+int main(int argc, char** argv) {
+    struct mcmc_options o;
+    std::string pedfile, mapfile, datfile, outfile = "swiftlink.out";
+    static struct option longopts[] = {
+        {"affectedonly", no_argument, 0, 'a'}, {"burnin", required_argument, 0, 'b'}, {"cores", required_argument, 0, 'c'},
+        {"dat", required_argument, 0, 'd'}, {"elod", no_argument, 0, 'e'}, {"gpu", no_argument, 0, 'g'},
+        {"help", no_argument, 0, 'h'}, {"iterations", required_argument, 0, 'i'},
+        {"lsamplerprobability", required_argument, 0, 'l'}, {"map", required_argument, 0, 'm'},
+        {"lodscores", required_argument, 0, 'n'}, {"output", required_argument, 0, 'o'},
+        {"pedigree", required_argument, 0, 'p'}, {"peelseqiter", required_argument, 0, 'q'},
+        {"sequentialimputation", required_argument, 0, 's'}, {"verbose", no_argument, 0, 'v'},
+        {"scoringperiod", required_argument, 0, 'x'}, {"sexlinked", no_argument, 0, 'X'},
+        {"runs", required_argument, 0, 'R'}, {"trace", no_argument, 0, 'T'}, {"device", required_argument, 0, 'D'},
+        {"seed", required_argument, 0, 'S'}, {0, 0, 0, 0}};
+    int ch, tmp;
+    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:", longopts, 0)) != -1) {
+        switch(ch) {
+            case 'p': pedfile = optarg; break;
+            case 'm': mapfile = optarg; break;
+            case 'd': datfile = optarg; break;
+            case 'o': outfile = optarg; break;
+            case 'v': o.verbose = true; break;
+            case 'g': o.use_gpu = true; break;
+            case 'a': o.affected_only = true; break;
+            case 'X': o.sex_linked = true; break;
+            case 'h': usage(argv[0]); return EXIT_SUCCESS;
+            case 'e': fprintf(stderr, "error: --elod is not part of this build\n"); return EXIT_FAILURE;
+            case 'T': fprintf(stderr, "error: --trace needs the founder-allele-graph likelihood, which is not part of this build\n"); return EXIT_FAILURE;
+            case 'l': o.lsampler_prob = atof(optarg);
+                      if(o.lsampler_prob < 0.0 || o.lsampler_prob > 1.0) { fprintf(stderr, "%s: option '-l' requires a floating point argument between 0.0 and 1.0\n", argv[0]); return EXIT_FAILURE; }
+                      break;
+            case 'S': o.seed = strtoull(optarg, 0, 10); break;
+            case 'i': case 'b': case 's': case 'x': case 'q': case 'n': case 'R': case 'c': case 'D':
+                if(!str2int(tmp, optarg) || tmp < 0) { fprintf(stderr, "%s: option '-%c' requires a non-negative integer argument ('%s' given)\n", argv[0], ch, optarg); return EXIT_FAILURE; }
+                if(ch == 'i') o.iterations = tmp; else if(ch == 'b') o.burnin = tmp; else if(ch == 's') o.si_iterations = tmp;
+                else if(ch == 'x') o.scoring_period = tmp; else if(ch == 'q') o.peelopt_iterations = tmp;
+                else if(ch == 'n') o.lodscores = tmp; else if(ch == 'R') o.mcmc_runs = tmp; else if(ch == 'c') o.thread_count = tmp;
+                else o.device = tmp;
+                break;
+            case ':': fprintf(stderr, "%s: option '-%c' requires an argument\n", argv[0], optopt); return EXIT_FAILURE;
+            default:  fprintf(stderr, "%s: option '-%c' is invalid: ignored\n", argv[0], optopt); break;
+        }
+    }
+    if(pedfile.empty() || mapfile.empty() || datfile.empty()) {
+        fprintf(stderr, "%s: the pedigree, map and dat files are all required\n", argv[0]);
+        usage(argv[0]);
+        return EXIT_FAILURE;
+    }
+    if(o.scoring_period < 1 || o.lodscores < 1 || o.mcmc_runs < 1) { fprintf(stderr, "%s: -x, -n and -R must be at least 1\n", argv[0]); return EXIT_FAILURE; }
+    if(o.lsampler_prob < 1.0) {
+        fprintf(stderr, "error: this build runs L-sampler sweeps only (the M-sampler is not part of the device path); pass -l 1.0\n");
+        return EXIT_FAILURE;
+    }
+
+    GeneticMap map(o.lodscores);
+    DiseaseModel dm;
+    std::vector<Pedigree> pedigrees;
+    if(!read_and_check_input(pedfile, mapfile, datfile, o.sex_linked, map, dm, pedigrees)) {
+        fprintf(stderr, "Exiting...\n");
+        return EXIT_FAILURE;
+    }
+    o.sex_linked = dm.is_sexlinked();
+
+    fprintf(stderr, "\nLinkage parameters:\n\tpenetrance = %.2f:%.2f:%.2f\n\ttrait freq = %.2e\n\tsex-linked = %s\n"
+                    "\tburnin iterations = %d\n\tsampling iterations = %d\n\tsampling period = %d\n"
+                    "\tlocus sampler prob = %.3f\n\tnumber of runs = %d\n\n",
+            dm.get_penetrance(TRAIT_HOMO_U), dm.get_penetrance(TRAIT_HETERO), dm.get_penetrance(TRAIT_HOMO_A), dm.get_freq(),
+            dm.is_sexlinked() ? "true" : "false", o.burnin, o.iterations, o.scoring_period, o.lsampler_prob, o.mcmc_runs);
+
+    std::vector<LODscores*> all_scores;
+    for(size_t pi = 0; pi < pedigrees.size(); ++pi) {
+        Pedigree& p = pedigrees[pi];
+        if(o.affected_only) {
+            for(unsigned int i = 0; i < p.num_members(); ++i)
+                if(!p.get_by_index(i)->isaffected()) p.get_by_index(i)->make_unknown_affection(dm);
+        }
+        // the peel sequence depends only on the pedigree: found once, shared by the replicates
+        // (the reference repeats the search per replicate, linkage_program.cc:136-137)
+        PeelSequenceGenerator psg(&p, &map, dm.is_sexlinked(), o.verbose, o.seed);
+        psg.build_peel_sequence(o.peelopt_iterations);
+        if(o.verbose) fprintf(stderr, "\n\n%s\n\n", psg.debug_string().c_str());
+
+        LODscores* total = 0;
+        for(int r = 0; r < o.mcmc_runs; ++r) {
+            DescentGraph dg(&p, &map, dm.is_sexlinked());
+            GPUMarkovChain chain(&p, &map, &psg, o, r);
+            chain.sequential_imputation(dg, o.si_iterations);
+            LODscores* lod = chain.run(dg);
+            if(!total) total = lod;
+            else { total->merge_results(lod); delete lod; }
+        }
+        all_scores.push_back(total);
+    }
+    bool ok = write_linkage_results(&map, outfile, all_scores, o.verbose);
+    if(!ok) fprintf(stderr, "error: could not write output file '%s'\n", outfile.c_str());
+    for(size_t i = 0; i < all_scores.size(); ++i) delete all_scores[i];
+    return ok ? EXIT_SUCCESS : EXIT_FAILURE;
+}

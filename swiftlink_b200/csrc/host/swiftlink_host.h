@@ -389,6 +389,9 @@ class GPUMarkovChain {
     GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num = 0);
     ~GPUMarkovChain();
     LODscores* run(DescentGraph& dg);           // gpu_markov_chain.cc:991 / markov_chain.cc:314
+    // SequentialImputation::parallel_run (sequential_imputation.cc:47-115) on the device: best of
+    // `iterations` runs of LocusSampler::start_from, or locus_by_locus when iterations == 0
+    double sequential_imputation(DescentGraph& dg, int iterations);
     double calc_trait_prob();                   // Peeler::calc_trait_prob on the device
     slk_chain* get_chain() { return chain; }
 };

@@ -1,0 +1,56 @@
+"""The `swift` command line (swiftlink_b200/swift): flags, refusals and the output file."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import ROOT, golden, ref_available
+
+SWIFT = os.path.join(ROOT, "swiftlink_b200", "swift")
+needs_ref = pytest.mark.skipif(not ref_available(), reason="example inputs live in oracle/_ref/examples")
+
+
+def test_cli_builds_and_prints_usage():
+    from swiftlink_b200 import build
+    build.build()
+    out = subprocess.run([SWIFT, "-h"], capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ("--pedigree", "--map", "--dat", "--iterations", "--burnin", "--scoringperiod", "--lodscores",
+                 "--runs", "--sexlinked", "--affectedonly", "--peelseqiter"):
+        assert flag in out.stderr
+
+
+@needs_ref
+def test_cli_refuses_what_it_cannot_do():
+    from oracle import refapi
+    ped, mapf, dat = refapi.example("loop")
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat], capture_output=True, text=True)
+    assert out.returncode != 0 and "-l 1.0" in out.stderr            # default mix needs the M-sampler
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf], capture_output=True, text=True)
+    assert out.returncode != 0 and "required" in out.stderr
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.0", "-e"], capture_output=True, text=True)
+    assert out.returncode != 0
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_end_to_end_east(tmp_path):
+    """swift -p east.ped -m east.map -d east.dat -l 1.0 (short run) writes the reference's
+    marker / position / lod table and the reference's P(T)"""
+    from oracle import refapi
+    ped, mapf, dat = refapi.example("east")
+    out_file = tmp_path / "swiftlink.out"
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.0", "-b", "300", "-i", "600", "-s", "5",
+                          "-q", "20000", "-R", "2", "-o", str(out_file)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "P(T) = -9.31939" in out.stdout                          # BASELINE.md known-answer scalar
+    rows = out_file.read_text().splitlines()
+    fx = golden("east")
+    M, n = int(fx["M"]), int(fx["nlod"])
+    assert rows[0] == "marker\tposition\tlod"
+    assert len(rows) == 1 + M + (M - 1) * n
+    assert rows[1].split("\t")[0] == "marker1" and abs(float(rows[1].split("\t")[1]) - 10.0) < 1e-9
+    lods = np.array([float(r.split("\t")[2]) for r in rows[1:] if r.startswith("-")])
+    assert lods.shape == ((M - 1) * n,) and np.isfinite(lods).all()
+    assert -5.0 < lods.mean() < 8.0
