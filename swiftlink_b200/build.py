@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
         return LIB
     src, _ = sources()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    extra = os.environ.get("SLK_NVCC_DEFS", "").split()        # tuning experiments only
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                                  "-I", os.path.join(CSRC, "host"), "-o", LIB] + src
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -25,6 +25,14 @@
 #ifndef SLK_KERNELS_CUH
 #define SLK_KERNELS_CUH
 
+#ifndef SLK_TILE_NS
+#define SLK_TILE_NS 2          // slots (values of cutset digit 0) per thread in throughput mode: 2 keeps the
+                               // kernels under 85 registers so that three 256-thread teams fit on an SM
+#endif
+#ifndef SLK_LS_MAXTHREADS
+#define SLK_LS_MAXTHREADS 768
+#endif
+
 #include <stdint.h>
 #include <float.h>
 
@@ -579,7 +587,7 @@ __device__ __forceinline__ void raise_error(int* err, int code, int unit) {
 // of one window class.  Replaces lsampler_kernel (cuda_lsampler.cu:403-449).
 // ============================================================================================
 template<int T, bool DBG>
-__global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L) {
+__global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
     const SlkProgram& pr = P.ls;
@@ -685,10 +693,11 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
                 }
             }
             else {
-                for(uint32_t q = tid; q < nq; q += T) {
+                for(uint32_t q = tid; q < nq * (4u / SLK_TILE_NS); q += T) {
+                    const uint32_t row = q / (4u / SLK_TILE_NS);
                     int lo = b, hi = e - 1;
-                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= q) lo = mid; else hi = mid - 1; }
-                    run_tile<false, DBG, 4>(L, pg, tm, pg.lops[lo], q - pg.lpf[lo], 0u);
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= row) lo = mid; else hi = mid - 1; }
+                    run_tile<false, DBG, SLK_TILE_NS>(L, pg, tm, pg.lops[lo], row - pg.lpf[lo], (q % (4u / SLK_TILE_NS)) * SLK_TILE_NS);
                 }
             }
             team_sync<T>(team);
@@ -818,7 +827,7 @@ __global__ void __launch_bounds__(512, 1) slk_lsampler_kernel(const SlkLaunch L)
 // Replaces lodscore_kernel (cuda_lodscore.cu:389-467).
 // ============================================================================================
 template<int T, bool DBG>
-__global__ void __launch_bounds__(512, 1) slk_lodscore_kernel(const SlkLaunch L) {
+__global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lodscore_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
     const SlkProgram& pr = P.lod;
@@ -895,10 +904,11 @@ __global__ void __launch_bounds__(512, 1) slk_lodscore_kernel(const SlkLaunch L)
                 }
             }
             else {
-                for(uint32_t q = tid; q < nq; q += T) {
+                for(uint32_t q = tid; q < nq * (4u / SLK_TILE_NS); q += T) {
+                    const uint32_t row = q / (4u / SLK_TILE_NS);
                     int lo = b, hi = e - 1;
-                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= q) lo = mid; else hi = mid - 1; }
-                    run_tile<true, DBG, 4>(L, pg, tm, pg.lops[lo], q - pg.lpf[lo], 0u);
+                    while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(pg.lpf[mid] <= row) lo = mid; else hi = mid - 1; }
+                    run_tile<true, DBG, SLK_TILE_NS>(L, pg, tm, pg.lops[lo], row - pg.lpf[lo], (q % (4u / SLK_TILE_NS)) * SLK_TILE_NS);
                 }
             }
             team_sync<T>(team);

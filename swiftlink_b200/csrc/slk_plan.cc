@@ -333,7 +333,7 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
     if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
     pr.team_threads = team;
-    pr.cta_threads = std::max(team, env_int("SLK_CTA_THREADS", hybrid ? 512 : 128));
+    pr.cta_threads = std::max(team, env_int(trait ? "SLK_LOD_CTA_THREADS" : "SLK_LS_CTA_THREADS", env_int("SLK_CTA_THREADS", hybrid ? 768 : 128)));
 
     const int teams_per_cta = pr.cta_threads / team;
     const int budget = kSmemPerBlockMax - pr.prog_smem_bytes;           // one CTA per SM worst case
