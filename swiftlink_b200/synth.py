@@ -210,7 +210,8 @@ KNOWN_ATTEMPT = {(200, 10000, DEFAULT_SEED): 533}
 
 def generate(n_members=200, n_markers=10000, seed=DEFAULT_SEED, spacing_cm=0.01, n_generations=6,
              trait_freq=1e-4, start_cm=10.0, penetrance=(0.001, 0.001, 0.999),
-             loops=(4, 12), min_generation=5, founder_frac=(0.25, 0.36), min_affected=2, cousin_prob=0.1):
+             loops=(4, 12), min_generation=5, founder_frac=(0.25, 0.36), min_affected=2, cousin_prob=0.1,
+             typed_depth=2):
     """Returns a dict describing the pedigree (arrays indexed by file order, ids are 1-based)."""
     hint = KNOWN_ATTEMPT.get((n_members, n_markers, seed))
     attempts = ([hint] if hint is not None else []) + list(range(1000))
@@ -231,7 +232,7 @@ def generate(n_members=200, n_markers=10000, seed=DEFAULT_SEED, spacing_cm=0.01,
         mid = n_markers // 2
         carrier_label = 0               # maternal strand of founder 0
         affected = (labels[:, 0, mid] == carrier_label) & (labels[:, 1, mid] == carrier_label)
-        typed = gen >= gen.max() - 1
+        typed = gen >= gen.max() - (typed_depth - 1)          # bottom `typed_depth` generations are genotyped
         if int((affected & typed).sum()) < min_affected:
             continue
 
