@@ -27,7 +27,8 @@ class OrcProblem(C.Structure):
                 ("disease_prob", C.POINTER(C.c_double)), ("marker_prob", C.POINTER(C.c_double)),
                 ("elim", C.POINTER(C.c_int)), ("theta", C.POINTER(C.c_double)),
                 ("partial", C.POINTER(C.c_double)),
-                ("nops", C.c_int), ("ops", C.POINTER(OrcOp))]
+                ("nops", C.c_int), ("ops", C.POINTER(OrcOp)),
+                ("typed", C.POINTER(C.c_int)), ("genotypes", C.POINTER(C.c_int)), ("minor", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -36,7 +37,7 @@ _lib = None
 def build(force=False):
     if force or not os.path.exists(LIB_PATH) or \
             os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f))
-                                             for f in ("peel_oracle.c", "peel_oracle.h", "philox.h")):
+                                             for f in ("peel_oracle.c", "msampler_oracle.c", "peel_oracle.h", "philox.h")):
         subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=subprocess.DEVNULL)
 
 
@@ -47,10 +48,13 @@ def lib():
         L = C.CDLL(LIB_PATH)
         for name in ("orc_ls_forward", "orc_ls_step", "orc_homo_p0", "orc_si_start_from", "orc_trait_prob",
                      "orc_recombination_prob", "orc_marker_transmission", "orc_log_sum",
-                     "orc_lod_normalise", "orc_uniform_draw"):
+                     "orc_lod_normalise", "orc_uniform_draw", "orc_fag_likelihood", "orc_dg_sum_prior_prob",
+                     "orc_dg_likelihood"):
             getattr(L, name).restype = C.c_double
         L.orc_matrix_doubles.restype = C.c_long
         L.orc_presum_doubles.restype = C.c_long
+        L.orc_ms_create.restype = C.c_void_p
+        L.orc_ms_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -78,7 +82,7 @@ class Problem(object):
         self._keep = {}
         for k, dt in (("mother", np.int32), ("father", np.int32), ("sex", np.int32), ("elim", np.int32),
                       ("disease_prob", np.float64), ("marker_prob", np.float64), ("theta", np.float64),
-                      ("partial", np.float64)):
+                      ("partial", np.float64), ("typed", np.int32), ("genotypes", np.int32), ("minor", np.float64)):
             self._keep[k] = np.ascontiguousarray(d[k], dtype=dt)
         ops = d["ops"]
         self.nops = len(ops)
@@ -99,7 +103,8 @@ class Problem(object):
         self.c = OrcProblem(self.N, self.F, self.M, self.nlod, self.sex_linked,
                             _ip(k["mother"]), _ip(k["father"]), _ip(k["sex"]),
                             _dp(k["disease_prob"]), _dp(k["marker_prob"]), _ip(k["elim"]),
-                            _dp(k["theta"]), _dp(k["partial"]), self.nops, arr)
+                            _dp(k["theta"]), _dp(k["partial"]), self.nops, arr,
+                            _ip(k["typed"]), _ip(k["genotypes"]), _dp(k["minor"]))
         self.p = C.byref(self.c)
         self.matrix_doubles = int(self.L.orc_matrix_doubles(self.p))
         self.presum_doubles = int(self.L.orc_presum_doubles(self.p))
@@ -143,6 +148,40 @@ class Problem(object):
         return float(self.L.orc_homo_p0(self.p, _ip(dg), int(locus), int(person), int(parent),
                                         int(ignore_left), int(ignore_right)))
 
+    # ---- M-sampler ----------------------------------------------------------------------
+    def fag(self, dg, locus, flip=None):
+        dg = np.ascontiguousarray(dg, dtype=np.int32)
+        edge = np.zeros(2 * self.N, np.int32)
+        self.L.orc_fag_reset(self.p, _ip(dg), int(locus), _ip(edge))
+        if flip is not None:
+            self.L.orc_fag_flip(self.p, _ip(dg), int(locus), int(flip[0]), int(flip[1]), _ip(edge))
+        return edge, float(self.L.orc_fag_likelihood(self.p, int(locus), _ip(edge)))
+
+    def ms_ordering(self):
+        out = np.zeros(2 * self.N + 1, np.int32)
+        n = int(self.L.orc_ms_ordering(self.p, _ip(out)))
+        return out[:n].copy()
+
+    def ms_shuffle(self, order, seed, chain, iteration):
+        v = np.ascontiguousarray(order, dtype=np.int32).copy()
+        self.L.orc_ms_shuffle(_ip(v), len(v), C.c_uint64(seed), C.c_uint32(chain), C.c_uint64(iteration))
+        return v
+
+    def msampler(self):
+        return MSampler(self)
+
+    def ms_sweep(self, dg, seed, chain, iteration):
+        assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
+        return int(self.L.orc_ms_sweep(self.p, _ip(dg), C.c_uint64(seed), C.c_uint32(chain), C.c_uint64(iteration)))
+
+    def dg_likelihood(self, dg):
+        dg = np.ascontiguousarray(dg, dtype=np.int32)
+        return float(self.L.orc_dg_likelihood(self.p, _ip(dg)))
+
+    def dg_sum_prior_prob(self, dg):
+        dg = np.ascontiguousarray(dg, dtype=np.int32)
+        return float(self.L.orc_dg_sum_prior_prob(self.p, _ip(dg)))
+
     # ---- LOD ----------------------------------------------------------------------------
     def lod_interval(self, dg, interval, dump_k=-1):
         dg = np.ascontiguousarray(dg, dtype=np.int32)
@@ -166,6 +205,43 @@ class Problem(object):
         dg = np.ascontiguousarray(dg, dtype=np.int32)
         assert scores.dtype == np.float64 and scores.size == (self.M - 1) * self.nlod
         self.L.orc_lod_pass(self.p, _ip(dg), _dp(scores), int(first))
+
+
+class MSampler(object):
+    """MeiosisSampler restatement (oracle/msampler_oracle.c); dg arrays are int32 [M,N,2], updated in place"""
+
+    def __init__(self, prob):
+        self.P = prob
+        self.L = prob.L
+        self.h = C.c_void_p(self.L.orc_ms_create(prob.p))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ms_destroy(self.h)
+            self.h = None
+
+    def reset(self, dg, parameter):
+        assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
+        return int(self.L.orc_ms_reset(self.h, _ip(dg), int(parameter)))
+
+    def step_stream(self, dg, parameter, us):
+        assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
+        us = np.ascontiguousarray(us, dtype=np.float64)
+        used = C.c_int(0)
+        rc = int(self.L.orc_ms_step_stream(self.h, _ip(dg), int(parameter), _dp(us), len(us), C.byref(used)))
+        return rc, used.value
+
+    def step(self, dg, parameter, seed, chain, iteration):
+        assert dg.dtype == np.int32 and dg.flags["C_CONTIGUOUS"]
+        return int(self.L.orc_ms_step(self.h, _ip(dg), int(parameter), C.c_uint64(seed), C.c_uint32(chain),
+                                      C.c_uint64(iteration)))
+
+    def state(self, edges=False):
+        M, N = self.P.M, self.P.N
+        raw = np.zeros((M, 2)); fwd = np.zeros((M, 2)); fb = np.zeros((M, 2))
+        e = np.zeros((M, 2 * N), np.int32) if edges else None
+        self.L.orc_ms_state(self.h, _dp(raw), _dp(fwd), _dp(fb), _ip(e) if edges else None)
+        return dict(raw=raw, fwd=fwd, fb=fb, edges=e)
 
 
 def marker_prob(isfounder, typed, genotype, xmale, mapprob):

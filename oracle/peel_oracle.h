@@ -48,6 +48,10 @@ typedef struct {
     const double* partial;        /* [M-1]    GeneticMap::get_theta_partial_raw   */
     int nops;
     const orc_op* ops;
+    /* M-sampler / founder allele graph inputs (msampler_oracle.c) */
+    const int* typed;             /* [N]      Person::istyped()                    */
+    const int* genotypes;         /* [N][M]   Person::get_marker (ORC_UNTYPED..)   */
+    const double* minor;          /* [M]      Snp::minor(); major = 1 - minor      */
 } orc_problem;
 
 /* sizes of the concatenated dense matrices (sum 4^c) and presum matrices (sum 4^(c+1)) */
@@ -106,6 +110,36 @@ double orc_lod_normalise(double score, int count, double trait_prob);
 
 /* one scoring pass over all intervals (markov_chain.cc:375-383) accumulated into scores[(M-1)*nlod] */
 void orc_lod_pass(const orc_problem* p, const int* dg, double* scores, int first);
+
+/* ---- M-sampler and descent-graph likelihood (msampler_oracle.c) ------------------------- */
+
+typedef struct orc_msampler orc_msampler;
+
+void orc_fag_sequence(const orc_problem* p, int* seq);                                  /* meiosis_sampler.cc:41-72 */
+void orc_fag_reset(const orc_problem* p, const int* dg, int locus, int* edge);          /* founder_allele_graph4.cc:548-572 */
+void orc_fag_flip(const orc_problem* p, const int* dg, int locus, int person, int parent, int* edge); /* :574-598 */
+double orc_fag_likelihood(const orc_problem* p, int locus, const int* edge);            /* :34-424 */
+
+orc_msampler* orc_ms_create(const orc_problem* p);
+void orc_ms_destroy(orc_msampler* m);
+/* MeiosisSampler::reset (meiosis_sampler.cc:17-39); 0, or 1 + locus of an illegal graph */
+int orc_ms_reset(orc_msampler* m, const int* dg, int parameter);
+/* MeiosisSampler::step (meiosis_sampler.cc:104-191), dg updated in place.  _stream takes the
+   caller's uniforms in the reference's order of consumption; the other the Philox schedule. */
+int orc_ms_step_stream(orc_msampler* m, int* dg, int parameter, const double* us, int n, int* used);
+int orc_ms_step(orc_msampler* m, int* dg, int parameter, uint64_t seed, uint32_t chain, uint64_t iteration);
+/* raw_matrix [M][2], fb_matrix after the forward pass [M][2], fb_matrix as the step leaves it
+   [M][2], edge lists [M][2N]; any pointer may be NULL */
+void orc_ms_state(const orc_msampler* m, double* raw, double* fwd, double* fb, int* edges);
+/* markov_chain.cc:68-80: meioses visited by a sweep (pedigree order); returns the count */
+int orc_ms_ordering(const orc_problem* p, int* out);
+void orc_ms_shuffle(int* v, int n, uint64_t seed, uint32_t chain, uint64_t iteration);
+/* one M-sweep (markov_chain.cc:342-349): shuffle, reset, step every meiosis */
+int orc_ms_sweep(const orc_problem* p, int* dg, uint64_t seed, uint32_t chain, uint64_t iteration);
+
+/* descent_graph.cc:150-265 */
+double orc_dg_sum_prior_prob(const orc_problem* p, const int* dg);
+double orc_dg_likelihood(const orc_problem* p, const int* dg);
 
 /* philox.h, exported for the known-answer test */
 void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -14,6 +14,10 @@
  *
  * slot = peel-op index for the genotype draw of that op, nops + 2*person + parent for the
  * meiosis-indicator draw, and SLK_SLOT_PHASE for the per-sweep even/odd order draw (locus = 0).
+ * M-sampler: ORC_SLOT_MEIOSIS + meiosis (= 2*(person - F) + parent) for the indicator draw of that
+ * meiosis at `locus`; ORC_SLOT_MSHUFFLE with locus = i for step i of the Fisher-Yates shuffle of
+ * the sweep's meiosis order; ORC_SLOT_KIND (locus = 0) for the L-sweep / M-sweep choice of an
+ * iteration (markov_chain.cc:332).
  */
 #ifndef SLK_ORACLE_PHILOX_H
 #define SLK_ORACLE_PHILOX_H
@@ -25,6 +29,9 @@
 #define ORC_PHILOX_W0 0x9E3779B9u
 #define ORC_PHILOX_W1 0xBB67AE85u
 #define ORC_SLOT_PHASE 0x7ffffff0u
+#define ORC_SLOT_MSHUFFLE 0x7ffffff1u
+#define ORC_SLOT_KIND 0x7ffffff2u
+#define ORC_SLOT_MEIOSIS 0x40000000u
 
 static inline void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];

@@ -92,8 +92,9 @@ struct RefCtx {
     LocusSampler* ls;
     LODscores* lod;
     Peeler* peeler;
+    MeiosisSampler* ms;
 
-    RefCtx(int nlod) : opt(), map(nlod), dm(), peds(), ped(0), psg(0), dg(0), ls(0), lod(0), peeler(0) {}
+    RefCtx(int nlod) : opt(), map(nlod), dm(), peds(), ped(0), psg(0), dg(0), ls(0), lod(0), peeler(0), ms(0) {}
 };
 
 bool rng_ready = false;
@@ -122,6 +123,7 @@ void drop_samplers(RefCtx* c) {
     delete c->ls;     c->ls = 0;
     delete c->peeler; c->peeler = 0;
     delete c->lod;    c->lod = 0;
+    delete c->ms;     c->ms = 0;
 }
 
 void need_samplers(RefCtx* c) {
@@ -486,6 +488,90 @@ void ref_ls_sample_indicators(void* h, const int* pmk_in) {
     RefCtx* c = (RefCtx*) h;
     std::vector<int> pmk(pmk_in, pmk_in + c->ped->num_members());
     c->ls->sample_meiosis_indicators(pmk, *c->dg);
+}
+
+/* ---- M-sampler and descent-graph likelihood ------------------------------------------ */
+
+/* FounderAlleleGraph4 of one locus on the current descent graph (founder_allele_graph4.cc:548-572,
+   :34-424): edge_list[2N] and the likelihood */
+double ref_fag(void* h, int locus, int* edge) {
+    RefCtx* c = (RefCtx*) h;
+    FounderAlleleGraph4 f(c->ped, &c->map, c->dm.is_sexlinked());
+    f.set_sequence(&c->dg->seq);
+    f.set_locus(locus);
+    f.reset(*c->dg);
+    for(unsigned i = 0; i < 2 * c->ped->num_members(); ++i) edge[i] = f.edge_list[i];
+    return f.likelihood();
+}
+
+/* same graph after FounderAlleleGraph4::flip(dg, person, parent) (:574-598) */
+double ref_fag_flipped(void* h, int locus, int person, int parent, int* edge) {
+    RefCtx* c = (RefCtx*) h;
+    FounderAlleleGraph4 f(c->ped, &c->map, c->dm.is_sexlinked());
+    f.set_sequence(&c->dg->seq);
+    f.set_locus(locus);
+    f.reset(*c->dg);
+    f.flip(*c->dg, person, static_cast<enum parentage>(parent));
+    for(unsigned i = 0; i < 2 * c->ped->num_members(); ++i) edge[i] = f.edge_list[i];
+    return f.likelihood();
+}
+
+/* MarkovChain::_init's m_ordering (markov_chain.cc:68-80); returns the count */
+int ref_ms_ordering(void* h, int* out) {
+    RefCtx* c = (RefCtx*) h;
+    int n = 0;
+    unsigned num_meioses = 2 * (c->ped->num_members() - c->ped->num_founders());
+    for(unsigned i = 0; i < num_meioses; ++i) {
+        unsigned person_id = c->ped->num_founders() + (i / 2);
+        enum parentage p = static_cast<enum parentage>(i % 2);
+        if(not c->ped->get_by_index(person_id)->safe_to_ignore_meiosis(p)) out[n++] = (int) i;
+    }
+    return n;
+}
+
+/* MeiosisSampler::reset (meiosis_sampler.cc:17-39) on the context's descent graph */
+void ref_ms_reset(void* h, int parameter) {
+    RefCtx* c = (RefCtx*) h;
+    if(!c->ms) c->ms = new MeiosisSampler(c->ped, &c->map, c->dm.is_sexlinked());
+    c->ms->reset(*c->dg, parameter);
+}
+
+/* MeiosisSampler::step (meiosis_sampler.cc:104-191).  Before the call the calling thread's
+   mt19937 state is cloned and the next `cap` uniforms it would produce are written to us[], so a
+   restatement can be fed the very same draws.  Afterwards raw[M][2] / fb[M][2] receive
+   raw_matrix / fb_matrix as the step left them. */
+void ref_ms_step(void* h, int parameter, double* us, int cap, double* raw, double* fb) {
+    RefCtx* c = (RefCtx*) h;
+    if(us) {
+        gsl_rng clone = *r[get_thread_num()];
+        for(int i = 0; i < cap; ++i) us[i] = gsl_rng_uniform(&clone);
+    }
+    c->ms->step(*c->dg, parameter);
+    unsigned M = c->map.num_markers();
+    if(raw) for(unsigned i = 0; i < 2 * M; ++i) raw[i] = c->ms->raw_matrix[i];
+    if(fb)  for(unsigned i = 0; i < 2 * M; ++i) fb[i] = c->ms->fb_matrix[i];
+}
+
+void ref_ms_raw(void* h, double* raw) {
+    RefCtx* c = (RefCtx*) h;
+    unsigned M = c->map.num_markers();
+    for(unsigned i = 0; i < 2 * M; ++i) raw[i] = c->ms->raw_matrix[i];
+}
+
+/* `reps` M-sweeps exactly as markov_chain.cc:342-349 runs them; returns seconds */
+double ref_bench_msweeps(void* h, int reps) {
+    RefCtx* c = (RefCtx*) h;
+    Quiet q(quiet_mode());
+    std::vector<int> order(2 * c->ped->num_members());
+    order.resize(ref_ms_ordering(h, &order[0]));
+    MeiosisSampler ms(c->ped, &c->map, c->dm.is_sexlinked());
+    double t0 = omp_get_wtime();
+    for(int k = 0; k < reps; ++k) {
+        random_shuffle(order.begin(), order.end());
+        ms.reset(*c->dg, order[0]);
+        for(unsigned j = 0; j < order.size(); ++j) ms.step(*c->dg, order[j]);
+    }
+    return omp_get_wtime() - t0;
 }
 
 /* ---- LOD scoring ----------------------------------------------------------------- */

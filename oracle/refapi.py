@@ -32,7 +32,7 @@ def lib():
         L.ref_peel_cost.restype = C.c_uint
         for name in ("ref_dg_likelihood", "ref_dg_recombination_prob", "ref_dg_marker_transmission",
                      "ref_chain_run", "ref_ls_forward", "ref_calc_trait_prob", "ref_bench_lsweeps",
-                     "ref_bench_lodpasses"):
+                     "ref_bench_lodpasses", "ref_fag", "ref_fag_flipped", "ref_bench_msweeps"):
             getattr(L, name).restype = C.c_double
         _lib = L
     return _lib
@@ -220,6 +220,40 @@ class Ref(object):
     def ls_sample_indicators(self, pmk):
         p = np.ascontiguousarray(pmk, dtype=np.int32)
         self.L.ref_ls_sample_indicators(self.h, _ip(p))
+
+    # ---- M-sampler --------------------------------------------------------------------
+    def fag(self, locus, flip=None):
+        """(edge_list[2N], likelihood) of the founder allele graph at `locus`; flip = (person, parent)
+        applies FounderAlleleGraph4::flip first"""
+        edge = np.zeros(2 * self.N, np.int32)
+        if flip is None:
+            lik = self.L.ref_fag(self.h, int(locus), _ip(edge))
+        else:
+            lik = self.L.ref_fag_flipped(self.h, int(locus), int(flip[0]), int(flip[1]), _ip(edge))
+        return edge, float(lik)
+
+    def ms_ordering(self):
+        out = np.zeros(2 * self.N, np.int32)
+        n = int(self.L.ref_ms_ordering(self.h, _ip(out)))
+        return out[:n].copy()
+
+    def ms_reset(self, parameter):
+        self.L.ref_ms_reset(self.h, int(parameter))
+
+    def ms_raw(self):
+        raw = np.zeros((self.M, 2))
+        self.L.ref_ms_raw(self.h, _dp(raw))
+        return raw
+
+    def ms_step(self, parameter):
+        """returns (uniforms the step had available, raw_matrix, fb_matrix) -- the context's descent
+        graph is updated in place"""
+        us = np.zeros(self.M); raw = np.zeros((self.M, 2)); fb = np.zeros((self.M, 2))
+        self.L.ref_ms_step(self.h, int(parameter), _dp(us), self.M, _dp(raw), _dp(fb))
+        return us, raw, fb
+
+    def bench_msweeps(self, reps):
+        return float(self.L.ref_bench_msweeps(self.h, int(reps)))
 
     # ---- LOD ------------------------------------------------------------------------
     def calc_trait_prob(self):
