@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SLK_ABI_VERSION 1
+#define SLK_ABI_VERSION 2
 
 typedef enum {
     SLK_OK = 0,
@@ -40,7 +40,8 @@ typedef enum {
     SLK_ERR_NO_DEVICE = -3,      /* no usable sm_100 device: the product has no CPU fallback */
     SLK_ERR_ZERO_LIKELIHOOD = -4,/* an L-sampler peel returned 0 (locus_sampler2.cc:137-142) */
     SLK_ERR_NONPOSITIVE_TRAIT = -5, /* a trait peel returned <= 0 (peeler.cc:92-95) */
-    SLK_ERR_UNSUPPORTED = -6
+    SLK_ERR_UNSUPPORTED = -6,
+    SLK_ERR_ILLEGAL_GRAPH = -7   /* descent graph with likelihood 0 given to the M-sampler (meiosis_sampler.cc:31-34) */
 } slk_status;
 
 enum { SLK_UU = 0, SLK_AA = 1, SLK_AU = 2, SLK_UA = 3 };
@@ -95,6 +96,9 @@ typedef struct {
                                                   (genotype.h:18-24, elimination.cc:393-395) */
     int32_t n_ops;                             /* == N */
     const slk_peel_op* ops;                    /* PeelSequenceGenerator::get_peel_order() */
+    const double* minor_freq;                  /* [M] Snp::minor() (genetic_map.h:42); only the M-sampler and the
+                                                  descent-graph likelihood read it -- NULL makes those entry
+                                                  points fail with SLK_ERR_UNSUPPORTED (ABI 1 callers) */
 } slk_problem;
 
 typedef struct slk_plan slk_plan;              /* device-resident flattened peel plan (shared, read-only) */
@@ -167,6 +171,32 @@ int slk_lsampler_locus_by_locus(slk_chain* chain, uint64_t iteration);
    (sequential_imputation.cc:76-108); reading it synchronises. */
 int slk_sequential_imputation(slk_chain* chain, uint64_t run, int start_locus, double* log_weight);
 
+/* ---- M-sampler: replaces run_gpu_msampler_reset_kernel / run_gpu_msampler_likelihood_kernel /
+        run_gpu_msampler_sampling_kernel (cuda_common.h:240-244, cuda_msampler2.cu) and the CPU
+        MeiosisSampler (meiosis_sampler.cc:17-203) the live reference falls back to --------------- */
+
+/* A meiosis is numbered 2 * (person - F) + parent (0 maternal, 1 paternal), the reference's M-sampler
+   `parameter`.  slk_msampler_ordering returns the meioses a sweep visits: MarkovChain::_init's
+   m_ordering (markov_chain.cc:68-80), i.e. all but Person::safe_to_ignore_meiosis (person.cc:208-222).
+   Writes at most cap entries, returns the count. */
+int slk_msampler_ordering(const slk_plan* plan, int32_t* out, int cap);
+/* MeiosisSampler::reset: founder-allele-graph likelihood of the chain's current graph at every
+   locus, kept on the device and carried from step to step.  Needed after anything but an M-sampler
+   step changed the graph. */
+int slk_msampler_reset(slk_chain* chain);
+/* MeiosisSampler::step(dg, meiosis): whole-chromosome Gibbs update of one meiosis indicator.  The
+   indicator draw of locus l is uniform(seed, chain, iteration, l, SLK_SLOT_MEIOSIS + meiosis). */
+int slk_msampler_step(slk_chain* chain, uint64_t iteration, int meiosis);
+/* One M-sweep (markov_chain.cc:342-349): Philox Fisher-Yates shuffle of the ordering, reset, one step
+   per meiosis -- every launch asynchronous on the chain's stream. */
+int slk_msampler_sweep(slk_chain* chain, uint64_t iteration);
+/* DescentGraph::get_likelihood (descent_graph.cc:150-156): ln of transmission x recombination x
+   founder-allele-graph prior; -DBL_MAX (LOG_ILLEGAL) if some locus has likelihood 0.  Synchronises. */
+int slk_dg_likelihood(slk_chain* chain, double* log_likelihood);
+/* which kind of sweep iteration `iteration` of this chain is: 1 = L-sweep, 0 = M-sweep
+   (get_random() < lsampler_prob, markov_chain.cc:332, drawn from the Philox stream) */
+int slk_sweep_is_lsampler(const slk_chain* chain, uint64_t iteration, double lsampler_prob);
+
 /* ---- LOD scoring: replaces run_gpu_lodscoreinit_kernel / run_gpu_lodscore_kernel /
         run_gpu_lodscorenormalise_kernel (cuda_common.h:249-252, cuda_lodscore.cu:389-541) ---- */
 
@@ -196,6 +226,14 @@ int slk_debug_lsampler_step(slk_chain* chain, uint64_t iteration, int locus, int
    and, if matrices != NULL, the dense peel matrices of position dump_k */
 int slk_debug_lod_interval(slk_chain* chain, int interval, double* result, double* prob,
                            int dump_k, double* matrices);
+/* founder allele graph of every locus on the chain's graph, optionally with one meiosis flipped
+   (meiosis < 0: none): lik[M] and, if edges != NULL, the edge lists [M][2N]
+   (FounderAlleleGraph4::reset / flip / likelihood) */
+int slk_debug_fag(slk_chain* chain, int meiosis, double* lik, int32_t* edges);
+/* after slk_msampler_step: raw_matrix [M][2] as the step saw it is not kept; this returns the
+   forward matrix fb[M][2] (meiosis_sampler.cc:134-153, before the backward pass) and the carried
+   per-locus likelihood cur[M] of the graph the step left */
+int slk_debug_msampler_state(slk_chain* chain, double* fb, double* cur);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward
    level, after every backward level, after the indicators.  Returns the number of stamps. */

@@ -26,6 +26,8 @@ SYMBOLS = [
     "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood",
+    "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
+    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
     "slk_debug_philox", "slk_debug_uniform", "slk_measure_fp64_peak",
 ]
@@ -48,7 +50,8 @@ class Problem(C.Structure):
                 ("marker_prob", C.POINTER(C.c_double)), ("marker_xprob", C.POINTER(C.c_double)),
                 ("theta", C.POINTER(C.c_double)), ("partial_theta", C.POINTER(C.c_double)),
                 ("elimination", C.POINTER(C.c_uint8)),
-                ("n_ops", C.c_int32), ("ops", C.POINTER(PeelOp))]
+                ("n_ops", C.c_int32), ("ops", C.POINTER(PeelOp)),
+                ("minor_freq", C.POINTER(C.c_double))]
 
 
 class SlkError(RuntimeError):
@@ -117,6 +120,7 @@ def make_problem(d):
             for j, v in enumerate(vals):
                 getattr(arr[i], name)[j] = v
     keep["ops"] = arr
+    keep["minor"] = None if d.get("minor") is None else np.ascontiguousarray(d["minor"], np.float64)
     p = Problem(N, int(d["F"]), M, int(d["nlod"]), int(d["sex_linked"]),
                 _ptr(keep["mother"], C.c_int32), _ptr(keep["father"], C.c_int32),
                 _ptr(keep["sex"], C.c_int32), _ptr(keep["typed"], C.c_int32),
@@ -124,7 +128,8 @@ def make_problem(d):
                 _ptr(keep["genotypes"], C.c_uint8), _ptr(keep["disease_prob"], C.c_double),
                 _ptr(keep["mapprob"], C.c_double), _ptr(keep["mapxprob"], C.c_double),
                 _ptr(keep["theta"], C.c_double), _ptr(keep["partial"], C.c_double),
-                _ptr(keep["elim"], C.c_uint8), len(ops), arr)
+                _ptr(keep["elim"], C.c_uint8), len(ops), arr,
+                _ptr(keep["minor"], C.c_double) if keep["minor"] is not None else None)
     return p, keep
 
 
@@ -163,6 +168,11 @@ class Plan(object):
         v = C.c_double(0)
         _check(self.L.slk_trait_likelihood(self.h, C.byref(v)))
         return v.value
+
+    def msampler_ordering(self):
+        out = np.zeros(2 * self.N + 1, np.int32)
+        n = int(self.L.slk_msampler_ordering(self.h, _ptr(out, C.c_int32), len(out)))
+        return out[:n].copy()
 
     def close(self):
         if self.h:
@@ -243,6 +253,36 @@ class Chain(object):
         out = np.zeros((self.plan.M - 1) * self.plan.nlod)
         _check(self.L.slk_lodscore_normalise(self.h, C.c_double(trait_prob), _ptr(out, C.c_double)))
         return out.reshape(self.plan.M - 1, self.plan.nlod)
+
+    # ---- M-sampler ------------------------------------------------------------------------
+    def msampler_reset(self):
+        _check(self.L.slk_msampler_reset(self.h))
+
+    def msampler_step(self, iteration, meiosis):
+        _check(self.L.slk_msampler_step(self.h, C.c_uint64(iteration), int(meiosis)))
+
+    def msampler_sweep(self, iteration):
+        _check(self.L.slk_msampler_sweep(self.h, C.c_uint64(iteration)))
+
+    def dg_likelihood(self):
+        v = C.c_double(0)
+        _check(self.L.slk_dg_likelihood(self.h, C.byref(v)))
+        return v.value
+
+    def sweep_is_lsampler(self, iteration, lsampler_prob):
+        return bool(self.L.slk_sweep_is_lsampler(self.h, C.c_uint64(iteration), C.c_double(lsampler_prob)))
+
+    def debug_fag(self, meiosis=-1, edges=False):
+        lik = np.zeros(self.plan.M)
+        e = np.zeros((self.plan.M, 2 * self.plan.N), np.int32) if edges else None
+        _check(self.L.slk_debug_fag(self.h, int(meiosis), _ptr(lik, C.c_double),
+                                    _ptr(e, C.c_int32) if edges else None))
+        return lik, e
+
+    def debug_msampler_state(self):
+        fb = np.zeros((self.plan.M, 2)); cur = np.zeros(self.plan.M)
+        _check(self.L.slk_debug_msampler_state(self.h, _ptr(fb, C.c_double), _ptr(cur, C.c_double)))
+        return fb, cur
 
     # ---- parity hooks ---------------------------------------------------------------------
     def debug_forward(self, locus, ignore_left=False, ignore_right=False):

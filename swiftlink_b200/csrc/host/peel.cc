@@ -548,7 +548,9 @@ void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg,
     }
     out.marker_prob.resize((size_t) M * 4); out.marker_xprob.resize((size_t) M * 4);
     out.theta.resize(M - 1); out.partial_theta.resize(M - 1);
+    out.minor_freq.resize(M);
     for(int l = 0; l < M; ++l) {
+        out.minor_freq[l] = map.get_minor(l);
         for(int g = 0; g < 4; ++g) {
             out.marker_prob[(size_t) l * 4 + g] = map.get_prob(l, (enum phased_trait) g, false);
             out.marker_xprob[(size_t) l * 4 + g] = map.get_prob(l, (enum phased_trait) g, true);
@@ -591,6 +593,7 @@ void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg,
     d.theta = out.theta.data(); d.partial_theta = out.partial_theta.data();
     d.elimination = out.elimination.data();
     d.n_ops = (int) out.ops.size(); d.ops = out.ops.data();
+    d.minor_freq = out.minor_freq.data();
 }
 
 }  // namespace swiftlink

@@ -14,6 +14,7 @@
 #include "swiftlink_b200.h"
 #include "slk_plan.h"
 #include "slk_kernels.cuh"
+#include "slk_msampler.cuh"
 
 namespace {
 
@@ -57,6 +58,8 @@ struct slk_plan {
     std::vector<void*> owned;
     int ls_blocks_per_sm, lod_blocks_per_sm;
     int ls_cta_smem, lod_cta_smem;
+    // M-sampler likelihood kernel geometry
+    int ms_grid, ms_threads, ms_smem;
 };
 
 struct slk_chain {
@@ -72,6 +75,9 @@ struct slk_chain {
     size_t gscratch_doubles;
     int* err;                     // device [4]
     int32_t count;                // scoring passes (LODscores::count)
+    // M-sampler state (allocated on first use)
+    double* ms_cur; double* ms_flipped; double* ms_fb; double* ms_out;
+    bool ms_cur_valid;            // ms_cur describes the graph now in dgp
     // debug buffers (allocated on first use)
     double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
 };
@@ -181,6 +187,8 @@ int check_device_error(slk_chain* c) {
         cudaMemsetAsync(c->err, 0, 4 * sizeof(int), c->stream);
         if(h[0] == SLK_ERR_ZERO_LIKELIHOOD)
             return fail(h[0], "likelihood is zero at locus %d (check penetrance function?)", h[1]);
+        if(h[0] == SLK_ERR_ILLEGAL_GRAPH)
+            return fail(h[0], "illegal descent graph given to m-sampler (locus %d)", h[1]);
         return fail(h[0], "intermediate state had a likelihood of 0.0 or less (lod score unit %d)", h[1]);
     }
     return SLK_OK;
@@ -265,11 +273,29 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         dp.team_smem_bytes = hp.team_smem_bytes;
         dp.table_doubles_per_child = hp.table_doubles_per_child;
     }
+    UP(ms.seq, h.ms_seq); UP(ms.typed, h.ms_typed); UP(ms.obsT, h.ms_obsT); UP(ms.minor, h.ms_minor);
+    d.ms.n_typed = (int) h.ms_typed.size();
+    d.ms.available = h.ms_available ? 1 : 0;
 #undef UP
     if(e != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
         slk_plan_destroy(p);
         return fail(SLK_ERR_CUDA, "plan upload failed: %s", msg.c_str());
+    }
+    {
+        // M-sampler likelihood kernel: one thread per locus, loci dealt evenly over at most one CTA per
+        // SM; as many threads as the per-thread tables leave room for in shared memory
+        const MsLayout lay = slk_ms_layout(h.N, h.F, d.ms.n_typed);
+        int tmax = ((slk::kSmemPerBlockMax - (int) lay.cta_tables) / (int) lay.per_thread) / 32 * 32;
+        if(tmax > 256) tmax = 256;
+        p->ms_threads = 0;
+        if(tmax >= 32) {
+            int grid = std::min(p->sm_count, (h.M + 31) / 32);
+            int per = (h.M + grid - 1) / grid;
+            int t = std::min(tmax, (per + 31) / 32 * 32);
+            p->ms_grid = grid; p->ms_threads = t;
+            p->ms_smem = (int) lay.cta_tables + t * (int) lay.per_thread;
+        }
     }
 
     p->ls_cta_smem = d.ls.prog_smem_bytes + (d.ls.cta_threads / d.ls.team_threads) * d.ls.team_smem_bytes;
@@ -284,6 +310,8 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         e = prep_by_team(d.lod.team_threads, 0, p->lod_cta_smem, 0, d.lod.cta_threads, 0, &p->lod_blocks_per_sm, false, true);
     if(e == cudaSuccess)
         e = prep_debug(d.ls.prog_smem_bytes + d.ls.team_smem_bytes, d.lod.prog_smem_bytes + d.lod.team_smem_bytes);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
     if(e != cudaSuccess || p->ls_blocks_per_sm < 1 || p->lod_blocks_per_sm < 1) {
         std::string msg = cudaGetErrorString(e);
         slk_plan_destroy(p);
@@ -371,6 +399,7 @@ void slk_chain_destroy(slk_chain* c) {
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
     cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
+    cudaFree(c->ms_cur); cudaFree(c->ms_flipped); cudaFree(c->ms_fb); cudaFree(c->ms_out);
     delete c;
 }
 
@@ -394,6 +423,7 @@ int slk_dg_upload(slk_chain* c, const int32_t* dg) {
     CU(cudaMemcpyAsync(c->dg_staging, dg, cells * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     slk_dg_pack_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(c->dg_staging, c->dgp, cells);
     CU(cudaGetLastError());
+    c->ms_cur_valid = false;
     // the caller may reuse its buffer as soon as we return (GPULodscores::calculate uses a
     // synchronous copy for the same reason, gpu_lodscores.cc:598-607)
     CU(cudaStreamSynchronize(c->stream));
@@ -423,6 +453,7 @@ int slk_lsampler_window(slk_chain* c, uint64_t iteration, int window_length, int
     L.offset = offset;
     L.nunits = (d.M - offset + window_length - 1) / window_length;
     if(L.nunits <= 0) return SLK_OK;
+    c->ms_cur_valid = false;
     const int tpc = d.ls.cta_threads / d.ls.team_threads;
     const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
     launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
@@ -441,6 +472,7 @@ int slk_lsampler_locus_by_locus(slk_chain* c, uint64_t iteration) {
     L.offset = 0;
     L.nunits = d.M;
     L.ignore_left = L.ignore_right = 1;
+    c->ms_cur_valid = false;
     const int tpc = d.ls.cta_threads / d.ls.team_threads;
     const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
     launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
@@ -463,6 +495,7 @@ int slk_sequential_imputation(slk_chain* c, uint64_t run, int start_locus, doubl
     L.nunits = d.M;
     L.si_start = start_locus;
     L.dump_result = c->dbg_res;
+    c->ms_cur_valid = false;
     // one team walks the loci in sequence: a single CTA whose team 0 owns every unit
     launch_ls_by_team(d.ls.team_threads, L, 1, d.ls.team_threads, d.ls.prog_smem_bytes + d.ls.team_smem_bytes, c->stream);
     CU(cudaGetLastError());
@@ -550,6 +583,161 @@ int slk_trait_likelihood(slk_plan* plan, double* log_prob) {
     }
     slk_chain_destroy(c);
     return rc;
+}
+
+// ---- M-sampler ---------------------------------------------------------------------------
+
+static int ms_ready(slk_chain* c) {
+    if(!c) return fail(SLK_ERR_INVALID, "null chain");
+    slk_plan* p = c->plan;
+    if(!p->dev.ms.available) return fail(SLK_ERR_UNSUPPORTED, "slk_problem.minor_freq was NULL: the M-sampler tables were not built");
+    if(p->ms_threads < 32)
+        return fail(SLK_ERR_UNSUPPORTED, "pedigree too large for the M-sampler's shared-memory tables (N=%d, F=%d)", p->dev.N, p->dev.F);
+    CU(cudaSetDevice(p->device));
+    if(!c->ms_cur) {
+        const size_t M = (size_t) p->dev.M;
+        CU(cudaMalloc((void**) &c->ms_cur, sizeof(double) * M));
+        CU(cudaMalloc((void**) &c->ms_flipped, sizeof(double) * M));
+        CU(cudaMalloc((void**) &c->ms_fb, sizeof(double) * 2 * M));
+        CU(cudaMalloc((void**) &c->ms_out, sizeof(double) * 4));
+        CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
+        c->ms_cur_valid = false;
+    }
+    return SLK_OK;
+}
+
+static SlkMsLaunch ms_launch(slk_chain* c) {
+    const SlkDevPlan& d = c->plan->dev;
+    SlkMsLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.ms = d.ms;
+    L.N = d.N; L.F = d.F; L.M = d.M; L.sex_linked = d.sex_linked;
+    L.mother = d.mother; L.father = d.father; L.male = d.male; L.theta = d.theta;
+    L.log_theta = d.log_theta; L.log_1mtheta = d.log_1mtheta;
+    L.dgp = c->dgp; L.cur = c->ms_cur; L.flipped = c->ms_flipped; L.fb = c->ms_fb; L.err = c->err;
+    L.out = c->ms_out;
+    L.person = -1; L.parent = 0;
+    L.seed = c->seed; L.chain = c->chain_id;
+    return L;
+}
+
+static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
+    slk_plan* p = c->plan;
+    if(2 * p->dev.F > 256) slk_ms_likelihood_kernel<true><<<p->ms_grid, p->ms_threads, p->ms_smem, c->stream>>>(L);
+    else slk_ms_likelihood_kernel<false><<<p->ms_grid, p->ms_threads, p->ms_smem, c->stream>>>(L);
+}
+
+int slk_msampler_ordering(const slk_plan* plan, int32_t* out, int cap) {
+    if(!plan) return 0;
+    const std::vector<int32_t>& o = plan->host.ms_ordering;
+    for(int i = 0; i < (int) o.size() && i < cap; ++i) out[i] = o[i];
+    return (int) o.size();
+}
+
+int slk_msampler_reset(slk_chain* c) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    SlkMsLaunch L = ms_launch(c);
+    ms_launch_likelihood(c, L);
+    CU(cudaGetLastError());
+    c->ms_cur_valid = true;
+    return SLK_OK;
+}
+
+int slk_msampler_step(slk_chain* c, uint64_t iteration, int meiosis) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const SlkDevPlan& d = c->plan->dev;
+    if(meiosis < 0 || meiosis >= 2 * (d.N - d.F)) return fail(SLK_ERR_INVALID, "meiosis %d out of range", meiosis);
+    if(!c->ms_cur_valid) {
+        rc = slk_msampler_reset(c);
+        if(rc != SLK_OK) return rc;
+    }
+    SlkMsLaunch L = ms_launch(c);
+    L.person = d.F + meiosis / 2;
+    L.parent = meiosis % 2;
+    L.iteration = iteration;
+    L.slot = SLK_SLOT_MEIOSIS + (uint32_t) meiosis;
+    ms_launch_likelihood(c, L);
+    CU(cudaGetLastError());
+    slk_ms_chain_kernel<<<1, SLK_MS_CHAIN_THREADS, 0, c->stream>>>(L);
+    CU(cudaGetLastError());
+    return SLK_OK;
+}
+
+int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    std::vector<int32_t> order = c->plan->host.ms_ordering;
+    const int n = (int) order.size();
+    if(n == 0) return SLK_OK;
+    // Fisher-Yates on the chain's Philox stream (the oracle's orc_ms_shuffle)
+    for(int i = n - 1; i > 0; --i) {
+        int j = (int)(slk_uniform(c->seed, c->chain_id, iteration, (uint32_t) i, SLK_SLOT_MSHUFFLE) * (double)(i + 1));
+        if(j > i) j = i;
+        std::swap(order[i], order[j]);
+    }
+    // MeiosisSampler::reset at the start of every sweep (markov_chain.cc:345)
+    rc = slk_msampler_reset(c);
+    for(int j = 0; j < n && rc == SLK_OK; ++j) rc = slk_msampler_step(c, iteration, order[j]);
+    return rc;
+}
+
+int slk_dg_likelihood(slk_chain* c, double* log_likelihood) {
+    if(!log_likelihood) return fail(SLK_ERR_INVALID, "null argument");
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    if(!c->ms_cur_valid) {
+        rc = slk_msampler_reset(c);
+        if(rc != SLK_OK) return rc;
+    }
+    SlkMsLaunch L = ms_launch(c);
+    slk_ms_dg_likelihood_kernel<<<1, 1024, 0, c->stream>>>(L);
+    CU(cudaGetLastError());
+    double h[2] = {0.0, 0.0};
+    CU(cudaMemcpyAsync(h, c->ms_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_error(c);
+    if(rc != SLK_OK) return rc;
+    // descent_graph.cc:150-169: log_product(marker_transmission + recombination, sum prior)
+    *log_likelihood = (h[0] == -DBL_MAX) ? -DBL_MAX : (c->plan->dev.marker_transmission + h[1]) + h[0];
+    return SLK_OK;
+}
+
+int slk_sweep_is_lsampler(const slk_chain* c, uint64_t iteration, double lsampler_prob) {
+    if(!c) return 1;
+    return slk_uniform(c->seed, c->chain_id, iteration, 0u, SLK_SLOT_KIND) < lsampler_prob ? 1 : 0;
+}
+
+int slk_debug_fag(slk_chain* c, int meiosis, double* lik, int32_t* edges) {
+    if(!lik) return fail(SLK_ERR_INVALID, "null argument");
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const SlkDevPlan& d = c->plan->dev;
+    if(meiosis >= 2 * (d.N - d.F)) return fail(SLK_ERR_INVALID, "meiosis %d out of range", meiosis);
+    SlkMsLaunch L = ms_launch(c);
+    int32_t* dev_edges = 0;
+    if(edges) {
+        CU(cudaMalloc((void**) &dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N));
+        L.dump_edges = dev_edges;
+    }
+    if(meiosis >= 0) { L.person = d.F + meiosis / 2; L.parent = meiosis % 2; }
+    else c->ms_cur_valid = true;              // the no-flip launch refreshes ms_cur
+    ms_launch_likelihood(c, L);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(lik, meiosis >= 0 ? c->ms_flipped : c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
+    if(edges) CU(cudaMemcpyAsync(edges, dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_error(c);
+    cudaFree(dev_edges);
+    return rc;
+}
+
+int slk_debug_msampler_state(slk_chain* c, double* fb, double* cur) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const SlkDevPlan& d = c->plan->dev;
+    if(fb)  CU(cudaMemcpyAsync(fb, c->ms_fb, sizeof(double) * 2 * d.M, cudaMemcpyDeviceToHost, c->stream));
+    if(cur) CU(cudaMemcpyAsync(cur, c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
+    return check_device_error(c);
 }
 
 // ---- parity hooks ----------------------------------------------------------------------

@@ -489,6 +489,42 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
     }
     hp.marker_transmission = pb.sex_linked ? log(0.5) * (N - F) : log(0.5) * (2 * (N - F));   // descent_graph.cc:22,35
 
+    // ---- M-sampler tables ----
+    hp.ms_available = pb.minor_freq != 0;
+    hp.ms_seq.clear(); hp.ms_typed.clear(); hp.ms_ordering.clear();
+    {
+        // meiosis_sampler.cc:41-72: founders, then repeated passes picking people whose parents are placed
+        std::vector<char> visited(N, 0);
+        for(int i = 0; i < F; ++i) visited[i] = 1;
+        int total = N - F;
+        while(total > 0) {
+            int placed = 0;
+            for(int i = F; i < N; ++i) {
+                if(visited[i]) continue;
+                if(visited[pb.mother[i]] && visited[pb.father[i]]) { hp.ms_seq.push_back((uint16_t) i); visited[i] = 1; --total; ++placed; }
+            }
+            if(!placed) { err = "pedigree has a person who is their own ancestor"; return false; }
+        }
+        for(int i = 0; i < N; ++i) if(pb.typed[i]) hp.ms_typed.push_back((uint16_t) i);
+        const int nt = (int) hp.ms_typed.size();
+        hp.ms_obsT.resize((size_t) std::max(nt, 1) * M);
+        for(int k = 0; k < nt; ++k)
+            for(int l = 0; l < M; ++l) hp.ms_obsT[(size_t) k * M + l] = pb.genotypes[(size_t) hp.ms_typed[k] * M + l];
+        hp.ms_minor.assign(M, 0.0);
+        if(pb.minor_freq) hp.ms_minor.assign(pb.minor_freq, pb.minor_freq + M);
+        // markov_chain.cc:68-80 with Person::safe_to_ignore_meiosis (person.cc:208-222)
+        std::vector<int> nchild(N, 0);
+        for(int i = F; i < N; ++i) { nchild[pb.mother[i]]++; nchild[pb.father[i]]++; }
+        for(int i = 0; i < 2 * (N - F); ++i) {
+            const int person = F + i / 2, par = i % 2;
+            const int parent = par == 0 ? pb.mother[person] : pb.father[person];
+            bool ignore;
+            if(parent >= F) ignore = pb.sex_linked ? (par == 1) : false;
+            else ignore = nchild[parent] == 1;
+            if(!ignore) hp.ms_ordering.push_back(i);
+        }
+    }
+
     hp.ls = HostProgram(); hp.lod = HostProgram();
     hp.ls.arena_doubles = hp.lod.arena_doubles = 0;
     emit_program(pb, hp, false, hp.ls);

@@ -45,6 +45,12 @@ struct HostPlan {
     double flops_ls, flops_lod;          // SURVEY.md section 8(d) F_L and F_T
     int max_cutset;
     HostProgram ls, lod;
+    // M-sampler
+    bool ms_available;
+    std::vector<uint16_t> ms_seq, ms_typed;
+    std::vector<uint8_t> ms_obsT;        // [n_typed][M]
+    std::vector<double> ms_minor;        // [M]
+    std::vector<int32_t> ms_ordering;    // meioses an M-sweep visits (markov_chain.cc:68-80)
 };
 
 // shared-memory budget per SM the layout may assume (bytes); 227 KB on sm_100

@@ -71,6 +71,16 @@ struct SlkProgram {
     int table_doubles_per_child;    // 16 (sampler) or 4 (trait)
 };
 
+// M-sampler tables (slk_msampler.cuh)
+struct SlkMsPlan {
+    const uint16_t* seq;            // [N-F] non-founders, parents before children (meiosis_sampler.cc:41-72)
+    const uint16_t* typed;          // [n_typed] Person::istyped(), pedigree order
+    const uint8_t* obsT;            // [n_typed][M] observed genotype (SLK_UNTYPED..SLK_HOMOZ_B)
+    const double* minor;            // [M] Snp::minor()
+    int n_typed;
+    int available;                  // slk_problem.minor_freq was given
+};
+
 struct SlkDevPlan {
     int N, F, M, nlod, sex_linked, nops;
     int last_op;                    // op whose 1-cell matrix is the likelihood
@@ -87,6 +97,7 @@ struct SlkDevPlan {
     double marker_transmission;     // descent_graph.cc:22,35
     SlkProgram ls;                  // sampler program
     SlkProgram lod;                 // trait program
+    SlkMsPlan ms;                   // M-sampler tables
 };
 
 // Per-team shared-memory layout (byte offsets from the team's base), used by the host to size

@@ -1,0 +1,158 @@
+"""M-sampler and descent-graph likelihood on the device, through the C ABI, against the C oracle
+(oracle/msampler_oracle.c, pinned bit-exact to the compiled reference) and the golden vectors.
+
+Bar: founder-allele-graph edge lists and likelihoods bit-exact (integer labels; same floating-point
+operation order), sampled descent graphs identical under the shared Philox draws, the forward matrix
+within 1e-12 relative (the device evaluates the two-state recurrence as a blocked scan; north_star
+allows 1e-9), ln-likelihoods within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from common import CASES, golden, problem, oracle_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from swiftlink_b200 import capi
+    assert capi.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    made = {}
+
+    def get(name, seed=77, chain_id=3):
+        key = (name, seed, chain_id)
+        if key not in made:
+            plan = made.get(("plan", name))
+            if plan is None:
+                plan = capi.Plan(problem(name))
+                made[("plan", name)] = plan
+            made[key] = capi.Chain(plan, seed=seed, chain_id=chain_id)
+        return made[key]
+    yield get
+    for k, v in made.items():
+        if k[0] != "plan":
+            v.close()
+    for k, v in made.items():
+        if k[0] == "plan":
+            v.close()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    d = np.abs(a - b)
+    s = np.maximum(np.abs(a), np.abs(b))
+    return float(np.max(np.where(s > 0, d / np.where(s > 0, s, 1), 0.0)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ordering(gpu, name):
+    ch, ms = gpu(name), golden(name + "_ms")
+    assert (ch.plan.msampler_ordering() == ms["ms_ordering"]).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_founder_allele_graph_bit_exact(gpu, name):
+    """edge lists and likelihoods of every locus == reference (golden), plain and with a meiosis flipped"""
+    fx, ms, ch = golden(name), golden(name + "_ms"), gpu(name)
+    for gi in range(fx["dgs"].shape[0]):
+        ch.dg_upload(fx["dgs"][gi])
+        lik, edges = ch.debug_fag(-1, edges=True)
+        assert (edges == ms["fag_edges_%d" % gi]).all()
+        assert (lik == ms["fag_lik_%d" % gi]).all()
+        for k, m in enumerate(ms["flip_meioses"]):
+            fl, _ = ch.debug_fag(int(m))
+            assert (fl == ms["fag_flip_lik_%d" % gi][:, k]).all(), (name, gi, m)
+        assert (ch.dg_download() == fx["dgs"][gi]).all()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_flipped_edges_match_oracle(gpu, name):
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    dg = np.ascontiguousarray(fx["dgs"][3])
+    ch.dg_upload(dg)
+    for m in orc.ms_ordering():
+        lik, edges = ch.debug_fag(int(m), edges=True)
+        for l in range(orc.M):
+            e, v = orc.fag(dg, l, (orc.F + int(m) // 2, int(m) % 2))
+            assert (e == edges[l]).all() and v == lik[l]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dg_likelihood(gpu, name):
+    fx, ch = golden(name), gpu(name)
+    for gi in range(fx["dgs"].shape[0]):
+        ch.dg_upload(fx["dgs"][gi])
+        got, want = ch.dg_likelihood(), float(fx["dg_likelihood"][gi])
+        assert abs(got - want) <= TOL * abs(want)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_steps_match_oracle(gpu, name):
+    """reset + one step per meiosis, forwards then backwards through the ordering: forward matrix,
+    carried likelihoods and the sampled graph after every step"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name, seed=4242, chain_id=1)
+    for gi in (1, 2):
+        dg = np.ascontiguousarray(fx["dgs"][gi]).copy()
+        ch.dg_upload(dg)
+        order = orc.ms_ordering()
+        s = orc.msampler()
+        assert s.reset(dg, int(order[0])) == 0
+        ch.msampler_reset()
+        flips = 0
+        for it, m in enumerate(list(order) + list(order[::-1])):
+            before = dg.copy()
+            assert s.step(dg, int(m), 4242, 1, 100 + it) == 0
+            ch.msampler_step(100 + it, int(m))
+            fb, cur = ch.debug_msampler_state()
+            st = s.state()
+            assert rel(fb, st["fwd"]) <= TOL, (name, gi, m, rel(fb, st["fwd"]))
+            got = ch.dg_download()
+            assert (got == dg).all(), (name, gi, it, m)
+            person, par = orc.F + int(m) // 2, int(m) % 2
+            assert (cur == st["raw"][np.arange(orc.M), dg[:, person, par]]).all()
+            flips += int((before != dg).sum())
+        if name != "loop":
+            assert flips > 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sweeps_match_oracle(gpu, name):
+    """whole M-sweeps (shuffle, reset, every meiosis), interleaved with L-sweeps as MarkovChain::run
+    mixes them: identical graphs"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name, seed=99, chain_id=0)
+    dg = np.ascontiguousarray(fx["dgs"][2]).copy()
+    ch.dg_upload(dg)
+    kinds = []
+    for it in range(12):
+        is_l = ch.sweep_is_lsampler(it, 0.5)
+        kinds.append(is_l)
+        if is_l:
+            assert orc.ls_sweep(dg, 99, 0, it) == 0
+            ch.lsampler_sweep(it)
+        else:
+            assert orc.ms_sweep(dg, 99, 0, it) == 0
+            ch.msampler_sweep(it)
+        assert (ch.dg_download() == dg).all(), (name, it, is_l)
+    assert any(kinds) and not all(kinds)
+    want = orc.dg_likelihood(dg)
+    assert abs(ch.dg_likelihood() - want) <= TOL * abs(want)
+
+
+def test_illegal_graph_is_reported(gpu):
+    """a graph whose founder allele graph has likelihood 0 -> SLK_ERR_ILLEGAL_GRAPH, as the reference
+    aborts with "illegal descent graph given to m-sampler" (meiosis_sampler.cc:31-34)"""
+    from swiftlink_b200 import capi
+    fx, orc, ch = golden("east"), oracle_problem("east"), gpu("east", seed=5, chain_id=9)
+    dg = np.zeros_like(fx["dgs"][2])
+    if orc.dg_sum_prior_prob(dg) > -1e300:
+        pytest.skip("all-zero graph happens to be legal here")
+    ch.dg_upload(dg)
+    assert ch.dg_likelihood() == -np.finfo(float).max
+    with pytest.raises(capi.SlkError) as e:
+        ch.msampler_step(0, int(orc.ms_ordering()[0]))
+        ch.sync()
+    assert e.value.code == -7
+    ch.dg_upload(fx["dgs"][2])
+    ch.sync()
