@@ -60,6 +60,7 @@ struct slk_plan {
     int ls_cta_smem, lod_cta_smem;
     // M-sampler likelihood kernel geometry
     int ms_grid, ms_threads, ms_smem;
+    int ms_chain_loci, ms_chain_smem;
 };
 
 struct slk_chain {
@@ -76,7 +77,7 @@ struct slk_chain {
     int* err;                     // device [4]
     int32_t count;                // scoring passes (LODscores::count)
     // M-sampler state (allocated on first use)
-    double* ms_cur; double* ms_flipped; double* ms_fb; double* ms_out;
+    double* ms_cur; double2* ms_raw; uint8_t* ms_bits; double* ms_u; double* ms_fb; double* ms_out;
     bool ms_cur_valid;            // ms_cur describes the graph now in dgp
     // debug buffers (allocated on first use)
     double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
@@ -286,15 +287,20 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         // M-sampler likelihood kernel: one thread per locus, loci dealt evenly over at most one CTA per
         // SM; as many threads as the per-thread tables leave room for in shared memory
         const MsLayout lay = slk_ms_layout(h.N, h.F, d.ms.n_typed);
-        int tmax = ((slk::kSmemPerBlockMax - (int) lay.cta_tables) / (int) lay.per_thread) / 32 * 32;
-        if(tmax > 256) tmax = 256;
+        // one warp per CTA (the warps are independent): small CTAs let several chains' launches share
+        // an SM, and every locus of a 10k-marker map is resident at once (3 CTAs per SM)
         p->ms_threads = 0;
-        if(tmax >= 32) {
-            int grid = std::min(p->sm_count, (h.M + 31) / 32);
-            int per = (h.M + grid - 1) / grid;
-            int t = std::min(tmax, (per + 31) / 32 * 32);
-            p->ms_grid = grid; p->ms_threads = t;
-            p->ms_smem = (int) lay.cta_tables + t * (int) lay.per_thread;
+        if((int) lay.cta_tables + 32 * (int) lay.per_thread <= slk::kSmemPerBlockMax) {
+            p->ms_grid = (h.M + 31) / 32; p->ms_threads = 32;
+            p->ms_smem = (int) lay.cta_tables + 32 * (int) lay.per_thread;
+        }
+        if(lay.G > SLK_MS_MAXGROUPS) p->ms_threads = 0;
+        // chain kernel: raw pair (16 B) + one map byte per locus of the CTA's share of the chromosome
+        {
+            const int per_thread = (h.M + SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS - 1) / (SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS);
+            p->ms_chain_loci = per_thread * SLK_MS_CHAIN_THREADS;
+            p->ms_chain_smem = (p->ms_chain_loci * 17 + 15) & ~15;
+            if(p->ms_chain_smem > slk::kSmemPerBlockMax - 4096) p->ms_threads = 0;     // > 100k markers: unsupported for now
         }
     }
 
@@ -312,6 +318,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         e = prep_debug(d.ls.prog_smem_bytes + d.ls.team_smem_bytes, d.lod.prog_smem_bytes + d.lod.team_smem_bytes);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax - 4096);
     if(e != cudaSuccess || p->ls_blocks_per_sm < 1 || p->lod_blocks_per_sm < 1) {
         std::string msg = cudaGetErrorString(e);
         slk_plan_destroy(p);
@@ -399,7 +406,7 @@ void slk_chain_destroy(slk_chain* c) {
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
     cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
-    cudaFree(c->ms_cur); cudaFree(c->ms_flipped); cudaFree(c->ms_fb); cudaFree(c->ms_out);
+    cudaFree(c->ms_cur); cudaFree(c->ms_raw); cudaFree(c->ms_bits); cudaFree(c->ms_u); cudaFree(c->ms_fb); cudaFree(c->ms_out);
     delete c;
 }
 
@@ -597,7 +604,9 @@ static int ms_ready(slk_chain* c) {
     if(!c->ms_cur) {
         const size_t M = (size_t) p->dev.M;
         CU(cudaMalloc((void**) &c->ms_cur, sizeof(double) * M));
-        CU(cudaMalloc((void**) &c->ms_flipped, sizeof(double) * M));
+        CU(cudaMalloc((void**) &c->ms_raw, sizeof(double2) * M));
+        CU(cudaMalloc((void**) &c->ms_bits, M));
+        CU(cudaMalloc((void**) &c->ms_u, sizeof(double) * M));
         CU(cudaMalloc((void**) &c->ms_fb, sizeof(double) * 2 * M));
         CU(cudaMalloc((void**) &c->ms_out, sizeof(double) * 4));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
@@ -614,7 +623,7 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.N = d.N; L.F = d.F; L.M = d.M; L.sex_linked = d.sex_linked;
     L.mother = d.mother; L.father = d.father; L.male = d.male; L.theta = d.theta;
     L.log_theta = d.log_theta; L.log_1mtheta = d.log_1mtheta;
-    L.dgp = c->dgp; L.cur = c->ms_cur; L.flipped = c->ms_flipped; L.fb = c->ms_fb; L.err = c->err;
+    L.dgp = c->dgp; L.cur = c->ms_cur; L.raw = c->ms_raw; L.bits = c->ms_bits; L.u = c->ms_u; L.fb = c->ms_fb; L.err = c->err;
     L.out = c->ms_out;
     L.person = -1; L.parent = 0;
     L.seed = c->seed; L.chain = c->chain_id;
@@ -660,7 +669,7 @@ int slk_msampler_step(slk_chain* c, uint64_t iteration, int meiosis) {
     L.slot = SLK_SLOT_MEIOSIS + (uint32_t) meiosis;
     ms_launch_likelihood(c, L);
     CU(cudaGetLastError());
-    slk_ms_chain_kernel<<<1, SLK_MS_CHAIN_THREADS, 0, c->stream>>>(L);
+    slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
     CU(cudaGetLastError());
     return SLK_OK;
 }
@@ -724,10 +733,18 @@ int slk_debug_fag(slk_chain* c, int meiosis, double* lik, int32_t* edges) {
     else c->ms_cur_valid = true;              // the no-flip launch refreshes ms_cur
     ms_launch_likelihood(c, L);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(lik, meiosis >= 0 ? c->ms_flipped : c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> pairs;
+    std::vector<uint8_t> bits;
+    if(meiosis >= 0) {
+        pairs.resize(2 * (size_t) d.M); bits.resize(d.M);
+        CU(cudaMemcpyAsync(pairs.data(), c->ms_raw, sizeof(double) * 2 * d.M, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(bits.data(), c->ms_bits, d.M, cudaMemcpyDeviceToHost, c->stream));
+    }
+    else CU(cudaMemcpyAsync(lik, c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
     if(edges) CU(cudaMemcpyAsync(edges, dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_error(c);
     cudaFree(dev_edges);
+    if(meiosis >= 0) for(int l = 0; l < d.M; ++l) lik[l] = pairs[2 * l + ((bits[l] & 1) ? 0 : 1)];   // the flipped value
     return rc;
 }
 

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--markers", type=int, default=bench.N_MARKERS)
     ap.add_argument("--sweeps", type=int, default=5)
     ap.add_argument("--lod", type=int, default=1)
+    ap.add_argument("--msweeps", type=int, default=0)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--trace", action="store_true")
     args = ap.parse_args()
@@ -39,6 +40,18 @@ def main():
         chain.lodscore_accumulate()
     chain.sync()
     t2 = time.time()
+    if args.msweeps:
+        chain.msampler_sweep(1000); chain.sync()
+        t3 = time.time()
+        for it in range(args.msweeps):
+            chain.msampler_sweep(2000 + it)
+        t_enq = time.time()
+        chain.sync()
+        t4 = time.time()
+        n = len(plan.msampler_ordering())
+        print("M-sweep ms %.3f (%d meioses, %.2f us per step; host enqueue %.3f ms per sweep); ln L = %.3f" %
+              (1e3 * (t4 - t3) / args.msweeps, n, 1e6 * (t4 - t3) / args.msweeps / n, 1e3 * (t_enq - t3) / args.msweeps,
+               chain.dg_likelihood()))
     if args.trace:
         import numpy as np
         st = plan.stats()
