@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the peeling hot path (L-sampler + LOD scoring) on B200.
+"""bench.py -- throughput of the MCMC hot path (L-sampler + M-sampler + LOD scoring) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -7,19 +7,21 @@ Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 
 200-member consanguineous pedigree with 10 000 SNPs (swiftlink_b200/synth.py, seed 20261017),
 scored at 5 positions per interval every 100th iteration.
 
-One MCMC iteration of the hot path = one L-sampler sweep over all M loci (both parity classes);
-every `scoring period` (100) iterations the descent graph is LOD-scored at all (M-1)*5 positions.
-One bench STEP = 100 iterations = 100 sweeps + 1 scoring pass.  The reference's M-sampler sweeps
-(the other half of its default mix) are outside the path and are run by
-neither arm.  metric = MCMC iterations / second, whole job.
+One MCMC iteration = MarkovChain::run's loop body (markov_chain.cc:330-361) with the reference's
+default sampler mix: with probability 0.5 one L-sampler sweep over all M loci (both parity classes),
+otherwise one M-sampler sweep over every meiosis (shuffled; 281 whole-chromosome updates here); every
+`scoring period` (100) iterations the descent graph is LOD-scored at all (M-1)*5 positions.
+One bench STEP = 100 iterations (the kind of each drawn from the chain's Philox stream, as
+GPUMarkovChain::run does) + 1 scoring pass.  metric = MCMC iterations / second, whole job.
 
 With N > 1 GPUs every rank runs an independent replicate chain (the reference's -R, one chain
 group per GPU, weak scaling); the LOD accumulators are merged at the end by small NCCL
 all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the counts).
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libswiftref.so, built by
-oracle/Makefile) on the host cores with all OpenMP threads: its own LocusSampler sweeps and
-Peeler::process passes (markov_chain.cc:209-266, :375-383) on a bounded sample of the same
+oracle/Makefile) on the host cores with all OpenMP threads: its own LocusSampler sweeps,
+MeiosisSampler sweeps and Peeler::process passes (markov_chain.cc:209-266, :342-349, :375-383),
+combined with the same 0.5 / 0.5 mix, on a bounded sample of the same
 workload -- the first 1000 of the 10 000 SNPs of the same pedigree (the per-locus cost does not
 depend on M; the reference's per-locus index tables make M = 10 000 take minutes to set up) --
 extrapolated linearly in M and stated as such in `cpu_baseline.sample`.
@@ -40,10 +42,13 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 N_MEMBERS, N_MARKERS, N_LOD, SCORING_PERIOD = 200, 10000, 5, 100
+LSAMPLER_PROB = 0.5                       # defaults.h: the reference's default -l
 REF_SAMPLE_MARKERS = 1000
 METRIC = "mcmc_iterations_per_sec_incl_lod_scoring"
 UNIT = "iterations/s"
-WORKLOAD = "synthetic 200-member consanguineous pedigree, 10k SNPs, LOD scoring (5 positions/interval) every 100th iteration"
+WORKLOAD = ("synthetic 200-member consanguineous pedigree, 10k SNPs, default sampler mix (-l 0.5), LOD scoring "
+            "(5 positions/interval) every 100th iteration")
+STEP_DESC = "100 iterations (each an L-sweep w.p. 0.5, else an M-sweep over all meioses) + 1 LOD scoring pass"
 
 
 def load_order():
@@ -87,16 +92,19 @@ def reference_measure(steps, warmup, quiet=True):
         t_grp = r.bench_lsweeps(1, 4) if threads > 1 else t_old
         t_sweep = min(t_old, t_grp)       # the reference picks the faster scheduler itself (markov_chain.cc:269-311)
         t_lod = r.bench_lodpasses(1)
+        t_ms = r.bench_msweeps(1)
         if s >= warmup:
-            times.append((t_sweep, t_lod))
+            times.append((t_sweep, t_lod, t_ms))
     t_sweep = float(np.mean([t[0] for t in times])) * scale
     t_lod = float(np.mean([t[1] for t in times])) * float(N_MARKERS - 1) / (REF_SAMPLE_MARKERS - 1)
-    t_iter = t_sweep + t_lod / SCORING_PERIOD
-    info = dict(cores=threads, host_cores=cores, sweep_s_at_10k=t_sweep, lod_pass_s_at_10k=t_lod,
+    t_msweep = float(np.mean([t[2] for t in times])) * scale
+    t_iter = LSAMPLER_PROB * t_sweep + (1.0 - LSAMPLER_PROB) * t_msweep + t_lod / SCORING_PERIOD
+    info = dict(cores=threads, host_cores=cores, sweep_s_at_10k=t_sweep, msweep_s_at_10k=t_msweep, lod_pass_s_at_10k=t_lod,
                 locus_updates_per_s=N_MARKERS / t_sweep,
                 trait_positions_per_s=(N_MARKERS - 1) * N_LOD / t_lod,
-                sample="reference LocusSampler sweep + Peeler::process pass over the first %d of %d SNPs of the same "
-                       "pedigree, %d OpenMP threads, x%d linear extrapolation in M" %
+                sample="reference LocusSampler sweep, MeiosisSampler sweep and Peeler::process pass over the first %d of "
+                       "%d SNPs of the same pedigree, %d OpenMP threads, x%d linear extrapolation in M, iteration = "
+                       "0.5 L-sweep + 0.5 M-sweep + 1/100 scoring pass" %
                        (REF_SAMPLE_MARKERS, N_MARKERS, threads, int(scale)))
     r.close()
     return 1.0 / t_iter, info
@@ -115,12 +123,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_iter * SCORING_PERIOD, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "100 iterations = 100 L-sampler sweeps + 1 LOD scoring pass",
+        "config": {"workload": WORKLOAD, "step": STEP_DESC,
                    "n_members": N_MEMBERS, "n_markers": N_MARKERS, "n_lod": N_LOD},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "reference", "sample": info["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "detail": {k: info[k] for k in ("sweep_s_at_10k", "lod_pass_s_at_10k", "locus_updates_per_s",
+        "detail": {k: info[k] for k in ("sweep_s_at_10k", "msweep_s_at_10k", "lod_pass_s_at_10k", "locus_updates_per_s",
                                         "trait_positions_per_s", "host_cores")},
         "wall_s": time.time() - t0,
     }
@@ -215,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
     it = 1
     for _ in range(10):
         chain.lsampler_sweep(it); it += 1
+    chain.msampler_sweep(it); it += 1
     chain.sync()
     trait_prob = plan.trait_likelihood()
     t_setup = time.time() - t_setup
@@ -230,10 +239,22 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    n_meioses = len(plan.msampler_ordering())
+    launches = [0]
+    kinds = [0, 0]
+
     def hot_step(start_it):
         for k in range(SCORING_PERIOD):
-            chain.lsampler_sweep(start_it + k)
+            if chain.sweep_is_lsampler(start_it + k, LSAMPLER_PROB):
+                chain.lsampler_sweep(start_it + k)
+                launches[0] += 2
+                kinds[0] += 1
+            else:
+                chain.msampler_sweep(start_it + k)
+                launches[0] += 1 + 2 * n_meioses
+                kinds[1] += 1
         chain.lodscore_accumulate()
+        launches[0] += 1
         return start_it + SCORING_PERIOD
 
     def timed(step_fn, k_steps, it0):
@@ -259,7 +280,10 @@ def run_ours(args, rank, world, local_rank):
     chain.sync()
     clocks = ClockSampler(local_rank)
     clocks.start()
+    launches[0] = 0
+    kinds[0] = kinds[1] = 0
     secs, it = timed(hot_step, args.steps, it)
+    timed_launches, timed_kinds = launches[0], list(kinds)
     chain.sync()
     clock_info = clocks.stop()
     if dist is not None:
@@ -318,6 +342,12 @@ def run_ours(args, rank, world, local_rank):
         ctr[0] += 1
     ls_ms = kernel_ms(one_window, 40)                              # one launch = M/2 loci
     lod_ms = kernel_ms(chain.lodscore_accumulate, 5)               # one launch = (M-1)*5 positions
+    mctr = [it + 100000]
+
+    def one_msweep():
+        chain.msampler_sweep(mctr[0])
+        mctr[0] += 1
+    msweep_ms = kernel_ms(one_msweep, 3)                           # 1 + 2 * n_meioses launches
     chain.sync()
     fp64_peak = capi.measure_fp64_peak(local_rank)
 
@@ -359,26 +389,32 @@ def run_ours(args, rank, world, local_rank):
         "lodscore_kernel": {"achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
                             "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops,
                             "trait_positions_per_s": (M - 1) * N_LOD / (lod_ms * 1e-3)},
-        "share_of_step": {"slk_lsampler_kernel": 2 * SCORING_PERIOD * ls_ms / (2 * SCORING_PERIOD * ls_ms + lod_ms),
-                          "slk_lodscore_kernel": lod_ms / (2 * SCORING_PERIOD * ls_ms + lod_ms)},
+        "msampler": {"sweep_ms": msweep_ms, "meioses_per_sweep": n_meioses, "us_per_meiosis_step": 1e3 * msweep_ms / max(n_meioses, 1),
+                     "locus_likelihoods_per_s": n_meioses * M / (msweep_ms * 1e-3)},
     }
+    n_l, n_m = timed_kinds
+    t_l, t_m, t_s = n_l * 2 * ls_ms, n_m * msweep_ms, args.steps * lod_ms
+    roofline["share_of_step"] = {"slk_lsampler_kernel": t_l / (t_l + t_m + t_s), "slk_ms_kernels": t_m / (t_l + t_m + t_s),
+                                 "slk_lodscore_kernel": t_s / (t_l + t_m + t_s)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "100 iterations = 100 L-sampler sweeps + 1 LOD scoring pass",
+        "config": {"workload": WORKLOAD, "step": STEP_DESC, "lsampler_prob": LSAMPLER_PROB,
+                   "l_sweeps_timed": n_l, "m_sweeps_timed": n_m, "meioses_per_m_sweep": n_meioses,
                    "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU",
                    "l2": "256 MiB buffer written between timed steps (working set is L2-resident by design)",
                    "peel_cost_sum4c": stats["sum_cells"], "max_cutset": stats["max_cutset"],
                    "ls_team_threads": stats["ls_team_threads"], "lod_team_threads": stats["lod_team_threads"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_secs / args.steps},
-        "gpu_launches": args.steps * (2 * SCORING_PERIOD + 1),
+        "gpu_launches": timed_launches,
         "clocks": clock_info,
         "roofline": roofline,
-        "derived": {"locus_updates_per_s": world * M * SCORING_PERIOD * args.steps / secs,
+        "derived": {"locus_updates_per_s": world * M * n_l / secs,
                     "trait_positions_per_s_kernel": (M - 1) * N_LOD / (lod_ms * 1e-3),
+                    "l_sweep_ms": 2 * ls_ms, "m_sweep_ms": msweep_ms, "lod_pass_ms": lod_ms,
                     "lod_max": lod_max, "lod_argmax_interval": lod_argmax, "scoring_passes_merged": merged_count,
                     "setup_s": t_setup, "si_log10_weight": si_weight / np.log(10.0)},
     }
@@ -389,7 +425,9 @@ def run_ours(args, rank, world, local_rank):
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "reference",
                                         "sample": info["sample"],
                                         "trait_positions_per_s": info["trait_positions_per_s"],
-                                        "locus_updates_per_s": info["locus_updates_per_s"]}
+                                        "locus_updates_per_s": info["locus_updates_per_s"],
+                                        "l_sweep_s": info["sweep_s_at_10k"], "m_sweep_s": info["msweep_s_at_10k"],
+                                        "lod_pass_s": info["lod_pass_s_at_10k"]}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": info["error"]}
         except Exception as e:                                       # the baseline must not take the bench line down

@@ -56,12 +56,12 @@ const slk_problem* slk_host_problem(slk_host* h);
 /* LinkageWriter::write for one pedigree: lod[(M-1)*n_lod] already normalised */
 int slk_host_write_results(slk_host* h, const char* filename, const double* lod);
 
-/* GPUMarkovChain::run on the device with the L-sampler only (M-sampler sweeps are the reference's
-   CPU code and are not part of this library): burnin + iterations sweeps, scoring every
+/* GPUMarkovChain::run on the device: burnin + iterations sweeps, each an L-sweep with probability
+   lsampler_prob and an M-sweep otherwise (markov_chain.cc:332-349), scoring every
    scoring_period-th iteration after burn-in (markov_chain.cc:357-361), dg int32[M][N][2] updated
    in place; lod_out[(M-1)*n_lod] receives the normalised LOD scores.  Returns 0 or an slk_status. */
 int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int burnin, int iterations,
-                       int scoring_period, int32_t* dg, double* lod_out, double* trait_prob_out);
+                       int scoring_period, double lsampler_prob, int32_t* dg, double* lod_out, double* trait_prob_out);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cfloat>
 #include <cstring>
 
 namespace swiftlink {
@@ -91,25 +92,63 @@ double GPUMarkovChain::sequential_imputation(DescentGraph& dg, int iterations) {
     return best;
 }
 
-// markov_chain.cc:314-404 with both batches on the device.  The M-sampler (meiosis_sampler.cc,
-// founder_allele_graph4.cc) is outside this library: a chain that asks for M-sweeps
-// (lsampler_prob < 1) is refused rather than silently run with a different mix.
+// DescentGraph::get_likelihood (descent_graph.cc:150-156) of a host graph, on the device
+double GPUMarkovChain::get_likelihood(DescentGraph& dg) {
+    double v = 0.0;
+    die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::get_likelihood (upload)");
+    die_on(slk_dg_likelihood(chain, &v), "GPUMarkovChain::get_likelihood");
+    return v;
+}
+
+// markov_chain.cc:314-404 with every sampler and the scoring on the device: each iteration is an
+// L-sweep with probability lsampler_prob, otherwise an M-sweep over the shuffled meioses
+// (markov_chain.cc:332-349); scoring on iterations i >= burnin with i % scoring_period == 0
+// (:351-361); optional CODA trace of the graph likelihood at the scored iterations (:362-370).
+// The graph never leaves the device between sweeps (the reference's GPU chain copies it back and
+// forth for every M-sweep, gpu_markov_chain.cc:1199-1210).
 LODscores* GPUMarkovChain::run(DescentGraph& dg) {
-    if(options.lsampler_prob < 1.0) {
-        fprintf(stderr, "error: this build runs L-sampler sweeps only; use -l 1.0 (the M-sampler is not part of the device path)\n");
-        abort();
-    }
     LODscores* lod = new LODscores(map);
     const double trait_prob = calc_trait_prob();
     printf("P(T) = %.5f\n", trait_prob / log(10.0));
     die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (upload)");
+    const bool need_fag = options.lsampler_prob < 1.0 || options.coda_logging;
+    if(need_fag) {
+        double lik = 0.0;
+        die_on(slk_dg_likelihood(chain, &lik), "GPUMarkovChain::run (likelihood)");
+        if(lik == LOG_ILLEGAL) {
+            fprintf(stderr, "error: descent graph illegal pre-markov chain...\n");
+            abort();
+        }
+    }
+    FILE* coda = 0;
+    if(options.coda_logging) {
+        char buf[16];
+        snprintf(buf, sizeof(buf), "%d", seq_num);
+        std::string fname = options.coda_prefix + ".ped" + ped->get_id() + ".run" + std::string(buf);   // markov_chain.cc:84-91
+        coda = fopen(fname.c_str(), "w");
+        if(!coda) { fprintf(stderr, "error: could not open trace file '%s'\n", fname.c_str()); abort(); }
+        fprintf(coda, "iteration likelihood\n");
+        printf("opened trace file (%s)\n", fname.c_str());
+    }
     die_on(slk_lodscore_init(chain), "GPUMarkovChain::run (init)");
     const int total = options.iterations + options.burnin;
     for(int i = 0; i < total; ++i) {
-        die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (L-sampler)");
+        if(slk_sweep_is_lsampler(chain, (uint64_t) i, options.lsampler_prob))
+            die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (L-sampler)");
+        else
+            die_on(slk_msampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (M-sampler)");
         if(i < options.burnin) continue;
-        if((i % options.scoring_period) == 0) die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::run (scoring)");
+        if((i % options.scoring_period) == 0) {
+            if(coda) {
+                double lik = 0.0;
+                die_on(slk_dg_likelihood(chain, &lik), "GPUMarkovChain::run (trace)");
+                if(lik == LOG_ILLEGAL) { fprintf(stderr, "error: descent graph illegal...\n"); abort(); }
+                fprintf(coda, "%d\t%f\n", i + 1, lik);
+            }
+            die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::run (scoring)");
+        }
     }
+    if(coda) fclose(coda);
     die_on(slk_dg_download(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (download)");
     std::vector<double> raw(lod->num_lodscores());
     int32_t count = 0;

@@ -173,11 +173,11 @@ int slk_host_write_results(slk_host* h, const char* filename, const double* lod)
 }
 
 int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int burnin, int iterations,
-                       int scoring_period, int32_t* dg, double* lod_out, double* trait_prob_out) {
+                       int scoring_period, double lsampler_prob, int32_t* dg, double* lod_out, double* trait_prob_out) {
     if(!h->psg) return SLK_ERR_INVALID;
     struct mcmc_options o;
     o.burnin = burnin; o.iterations = iterations; o.scoring_period = scoring_period;
-    o.lsampler_prob = 1.0; o.sex_linked = h->dm.is_sexlinked(); o.seed = seed; o.device = device;
+    o.lsampler_prob = lsampler_prob; o.sex_linked = h->dm.is_sexlinked(); o.seed = seed; o.device = device;
     DescentGraph d(h->ped, &h->map, h->dm.is_sexlinked());
     memcpy(d.get_internal_ptr(), dg, d.get_internal_size());
     GPUMarkovChain chain(h->ped, &h->map, h->psg, o, (int) chain_id);

@@ -1,8 +1,8 @@
 // swift_main.cc -- the `swift` command line on top of the device path.  Same flags, input order,
 // messages and output file as the reference's main.cc:185-557 / linkage_program.cc:26-171 for
 // the linkage mode; every chain runs on the GPU (-g is implied, -X is allowed with it, which the
-// reference refuses at main.cc:534-537).  Not supported by this build, and refused explicitly:
-// M-sampler sweeps (-l < 1), --elod, --trace (both need the founder-allele-graph likelihood).
+// reference refuses at main.cc:534-537): L-sampler and M-sampler sweeps, LOD scoring, the CODA trace.
+// Not supported by this build, and refused explicitly: --elod.
 #include <getopt.h>
 
 #include <cmath>
@@ -20,7 +20,6 @@ static void usage(const char* prog) {
     struct mcmc_options d;
     fprintf(stderr,
 "Usage: %s [OPTIONS] -p pedfile -m mapfile -d datfile\n"
-"       %s [OPTIONS] -p pedfile -m mapfile -d datfile -l 1.0\n"
 "\n"
 "Input files:\n"
 "  -p pedfile, --pedigree=pedfile\n"
@@ -35,7 +34,7 @@ static void usage(const char* prog) {
 "  -b NUM,     --burnin=NUM                (default = %d)\n"
 "  -s NUM,     --sequentialimputation=NUM  (default = %d)\n"
 "  -x NUM,     --scoringperiod=NUM         (default = %d)\n"
-"  -l FLOAT,   --lsamplerprobability=FLOAT (default = %.1f; this build runs L-sampler sweeps only: pass 1.0)\n"
+"  -l FLOAT,   --lsamplerprobability=FLOAT (default = %.1f)\n"
 "  -n NUM,     --lodscores=NUM             (default = %d)\n"
 "  -R NUM,     --runs=NUM                  (default = %d)\n"
 "\n"
@@ -49,11 +48,13 @@ static void usage(const char* prog) {
 "  -a,         --affectedonly\n"
 "  -q NUM,     --peelseqiter=NUM           (default = %d)\n"
 "  -S NUM,     --seed=NUM                  Philox seed (default = %llu)\n"
+"  -T,         --trace\n"
+"  -P PREFIX,  --traceprefix=PREFIX        (default = '%s')\n"
 "  -v,         --verbose\n"
 "  -h,         --help\n"
 "\n",
-    prog, prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
-    d.peelopt_iterations, (unsigned long long) d.seed);
+    prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
+    d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
 }
 
 static bool str2int(int& out, const char* s) {
@@ -77,9 +78,9 @@ int main(int argc, char** argv) {
         {"sequentialimputation", required_argument, 0, 's'}, {"verbose", no_argument, 0, 'v'},
         {"scoringperiod", required_argument, 0, 'x'}, {"sexlinked", no_argument, 0, 'X'},
         {"runs", required_argument, 0, 'R'}, {"trace", no_argument, 0, 'T'}, {"device", required_argument, 0, 'D'},
-        {"seed", required_argument, 0, 'S'}, {0, 0, 0, 0}};
+        {"seed", required_argument, 0, 'S'}, {"traceprefix", required_argument, 0, 'P'}, {0, 0, 0, 0}};
     int ch, tmp;
-    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:", longopts, 0)) != -1) {
+    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:P:", longopts, 0)) != -1) {
         switch(ch) {
             case 'p': pedfile = optarg; break;
             case 'm': mapfile = optarg; break;
@@ -91,7 +92,8 @@ int main(int argc, char** argv) {
             case 'X': o.sex_linked = true; break;
             case 'h': usage(argv[0]); return EXIT_SUCCESS;
             case 'e': fprintf(stderr, "error: --elod is not part of this build\n"); return EXIT_FAILURE;
-            case 'T': fprintf(stderr, "error: --trace needs the founder-allele-graph likelihood, which is not part of this build\n"); return EXIT_FAILURE;
+            case 'T': o.coda_logging = true; break;
+            case 'P': o.coda_prefix = optarg; break;
             case 'l': o.lsampler_prob = atof(optarg);
                       if(o.lsampler_prob < 0.0 || o.lsampler_prob > 1.0) { fprintf(stderr, "%s: option '-l' requires a floating point argument between 0.0 and 1.0\n", argv[0]); return EXIT_FAILURE; }
                       break;
@@ -113,10 +115,6 @@ int main(int argc, char** argv) {
         return EXIT_FAILURE;
     }
     if(o.scoring_period < 1 || o.lodscores < 1 || o.mcmc_runs < 1) { fprintf(stderr, "%s: -x, -n and -R must be at least 1\n", argv[0]); return EXIT_FAILURE; }
-    if(o.lsampler_prob < 1.0) {
-        fprintf(stderr, "error: this build runs L-sampler sweeps only (the M-sampler is not part of the device path); pass -l 1.0\n");
-        return EXIT_FAILURE;
-    }
 
     GeneticMap map(o.lodscores);
     DiseaseModel dm;

@@ -339,6 +339,8 @@ class LODscores {
     void set(unsigned int index, double prob) { scores[index] = prob; initialised[index] = 1; }
 };
 
+const double LOG_ILLEGAL = -1.7976931348623157e308;           // logarithms.h:10-11 (-DBL_MAX)
+const double LOG_ZERO = LOG_ILLEGAL;
 double log_sum(double a, double b);                           // logarithms.cc:14-23
 
 // linkage_writer.cc:14-92
@@ -393,6 +395,7 @@ class GPUMarkovChain {
     // `iterations` runs of LocusSampler::start_from, or locus_by_locus when iterations == 0
     double sequential_imputation(DescentGraph& dg, int iterations);
     double calc_trait_prob();                   // Peeler::calc_trait_prob on the device
+    double get_likelihood(DescentGraph& dg);    // DescentGraph::get_likelihood on the device
     slk_chain* get_chain() { return chain; }
 };
 

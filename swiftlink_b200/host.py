@@ -144,11 +144,12 @@ class Host(object):
         lod = np.ascontiguousarray(lod, np.float64)
         return bool(self.L.slk_host_write_results(self.h, filename.encode(), _dp(lod)))
 
-    def run_chain(self, dg, burnin, iterations, scoring_period=10, seed=1, chain_id=0, device=0):
+    def run_chain(self, dg, burnin, iterations, scoring_period=10, seed=1, chain_id=0, device=0, lsampler_prob=1.0):
         dg = np.ascontiguousarray(dg, np.int32).copy()
         lod = np.zeros((self.M - 1) * self.nlod); tp = C.c_double(0)
         rc = self.L.slk_host_run_chain(self.h, int(device), C.c_uint64(seed), C.c_uint32(chain_id), int(burnin),
-                                       int(iterations), int(scoring_period), _ip(dg), _dp(lod), C.byref(tp))
+                                       int(iterations), int(scoring_period), C.c_double(lsampler_prob), _ip(dg), _dp(lod),
+                                       C.byref(tp))
         if rc != 0:
             raise capi.SlkError(rc, self.L.slk_last_error().decode())
         return dict(lod=lod.reshape(self.M - 1, self.nlod), dg=dg, trait_prob=tp.value)

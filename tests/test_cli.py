@@ -25,24 +25,25 @@ def test_cli_builds_and_prints_usage():
 def test_cli_refuses_what_it_cannot_do():
     from oracle import refapi
     ped, mapf, dat = refapi.example("loop")
-    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat], capture_output=True, text=True)
-    assert out.returncode != 0 and "-l 1.0" in out.stderr            # default mix needs the M-sampler
     out = subprocess.run([SWIFT, "-p", ped, "-m", mapf], capture_output=True, text=True)
     assert out.returncode != 0 and "required" in out.stderr
-    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.0", "-e"], capture_output=True, text=True)
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-e"], capture_output=True, text=True)
     assert out.returncode != 0
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.5"], capture_output=True, text=True)
+    assert out.returncode != 0 and "between 0.0 and 1.0" in out.stderr
 
 
 @pytest.mark.gpu
 @needs_ref
 def test_cli_end_to_end_east(tmp_path):
-    """swift -p east.ped -m east.map -d east.dat -l 1.0 (short run) writes the reference's
-    marker / position / lod table and the reference's P(T)"""
+    """swift -p east.ped -m east.map -d east.dat (default sampler mix, short run, with the CODA trace) writes the
+    reference's marker / position / lod table, the reference's P(T) and the trace files"""
     from oracle import refapi
     ped, mapf, dat = refapi.example("east")
     out_file = tmp_path / "swiftlink.out"
-    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.0", "-b", "300", "-i", "600", "-s", "5",
-                          "-q", "20000", "-R", "2", "-o", str(out_file)], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-b", "300", "-i", "600", "-s", "5",
+                          "-q", "20000", "-R", "2", "-T", "-P", str(tmp_path / "tr"), "-o", str(out_file)],
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "P(T) = -9.31939" in out.stdout                          # BASELINE.md known-answer scalar
     rows = out_file.read_text().splitlines()
@@ -54,3 +55,9 @@ def test_cli_end_to_end_east(tmp_path):
     lods = np.array([float(r.split("\t")[2]) for r in rows[1:] if r.startswith("-")])
     assert lods.shape == ((M - 1) * n,) and np.isfinite(lods).all()
     assert -5.0 < lods.mean() < 8.0
+    for run in (0, 1):
+        tr = [p for p in tmp_path.iterdir() if p.name.startswith("tr.ped") and p.name.endswith(".run%d" % run)]
+        assert len(tr) == 1
+        lines = tr[0].read_text().splitlines()
+        assert lines[0] == "iteration likelihood" and len(lines) == 1 + 60          # iterations 300..899 every 10th
+        assert all(float(ln.split("\t")[1]) < 0.0 for ln in lines[1:])

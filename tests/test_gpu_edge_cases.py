@@ -45,6 +45,14 @@ def _check_everything(d, orc, plan, sweeps=3, seed=11):
         scale = np.abs(np.log(a[0])).max() + abs(orc.marker_transmission())
         assert np.abs(a[1] - b[1]).max() <= 1e-12 * scale
     assert abs(plan.trait_likelihood() - orc.trait_prob()) <= 1e-12 * abs(orc.trait_prob())
+    # M-sampler: ordering, whole sweeps and the graph likelihood
+    assert (plan.msampler_ordering() == orc.ms_ordering()).all()
+    for it in range(100, 100 + sweeps):
+        assert orc.ms_sweep(ref, seed, 1, it) == 0
+        ch.msampler_sweep(it)
+        assert (ch.dg_download() == ref).all()
+    want = orc.dg_likelihood(ref)
+    assert abs(ch.dg_likelihood() - want) <= 1e-12 * abs(want)
     ch.close()
 
 

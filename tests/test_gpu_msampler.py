@@ -145,13 +145,25 @@ def test_illegal_graph_is_reported(gpu):
     aborts with "illegal descent graph given to m-sampler" (meiosis_sampler.cc:31-34)"""
     from swiftlink_b200 import capi
     fx, orc, ch = golden("east"), oracle_problem("east"), gpu("east", seed=5, chain_id=9)
-    dg = np.zeros_like(fx["dgs"][2])
-    if orc.dg_sum_prior_prob(dg) > -1e300:
-        pytest.skip("all-zero graph happens to be legal here")
+    dg = np.ascontiguousarray(fx["dgs"][2]).copy()
+    # flip indicator bits until some locus becomes impossible (two flips: the first step only sees one of them)
+    bad = []
+    for m in orc.ms_ordering():
+        person, par = orc.F + int(m) // 2, int(m) % 2
+        for l in range(orc.M):
+            if orc.fag(dg, l, (person, par))[1] == 0.0:
+                bad.append((l, person, par))
+        if len(bad) >= 2:
+            break
+    assert len(bad) >= 2
+    for l, person, par in bad[:2]:
+        dg[l, person, par] ^= 1
+    assert orc.dg_sum_prior_prob(dg) < -1e300
     ch.dg_upload(dg)
     assert ch.dg_likelihood() == -np.finfo(float).max
+    other = [int(m) for m in orc.ms_ordering() if (orc.F + int(m) // 2, int(m) % 2) not in [(b[1], b[2]) for b in bad[:2]]]
     with pytest.raises(capi.SlkError) as e:
-        ch.msampler_step(0, int(orc.ms_ordering()[0]))
+        ch.msampler_step(0, other[0])
         ch.sync()
     assert e.value.code == -7
     ch.dg_upload(fx["dgs"][2])

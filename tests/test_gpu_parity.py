@@ -224,10 +224,10 @@ def test_locus_by_locus_matches_oracle(gpu, name):
     assert (ch.dg_download() == dg).all()
 
 
-def _gpu_chain_lod(plan, fx, seed, burnin=2000, iterations=4000, period=10, si_runs=100):
-    """the reference's run_pedigree flow on the device, L-sampler only: best of `si_runs`
-    sequential-imputation runs as the start state (sequential_imputation.cc:67-115), then
-    MarkovChain::run with scoring every `period`-th iteration after burn-in"""
+def _gpu_chain_lod(plan, fx, seed, burnin=2000, iterations=4000, period=10, si_runs=100, lsampler_prob=1.0):
+    """the reference's run_pedigree flow on the device: best of `si_runs` sequential-imputation
+    runs as the start state (sequential_imputation.cc:67-115), then MarkovChain::run (L-sweep with
+    probability lsampler_prob, else M-sweep) with scoring every `period`-th iteration after burn-in"""
     from swiftlink_b200 import capi
     rng = np.random.default_rng(seed)
     ch = capi.Chain(plan, seed=seed, chain_id=0)
@@ -239,7 +239,10 @@ def _gpu_chain_lod(plan, fx, seed, burnin=2000, iterations=4000, period=10, si_r
     ch.dg_upload(best_dg)
     ch.lodscore_init()
     for i in range(burnin + iterations):
-        ch.lsampler_sweep(1000 + i)
+        if lsampler_prob >= 1.0 or ch.sweep_is_lsampler(1000 + i, lsampler_prob):
+            ch.lsampler_sweep(1000 + i)
+        else:
+            ch.msampler_sweep(1000 + i)
         if i >= burnin and i % period == 0:
             ch.lodscore_accumulate()
     lod = ch.lodscore_normalise(float(fx["trait_prob"]))
@@ -274,6 +277,28 @@ def test_lod_curves_agree_with_reference_within_mc_error(gpu, name):
     sep = np.sqrt(mine.var(axis=0, ddof=1) / n_mine + ref.var(axis=0, ddof=1) / ref.shape[0]) + 1e-3
     z_pos = np.abs(mine.mean(axis=0) - ref.mean(axis=0)) / sep
     print("%s: mean LOD device %.3f reference %.3f (se %.3f, z %.2f); max per-position z %.2f" %
+          (name, a.mean(), b.mean(), se, z_mean, z_pos.max()))
+    assert z_mean < 4.0
+    assert z_pos.max() < 6.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_default_mix_lod_curves_agree_with_reference_within_mc_error(gpu, name):
+    """End to end with the reference's default sampler mix (-l 0.5: L-sweeps and M-sweeps, markov_chain.cc:332-349):
+    independent device chains against independent chains of the compiled reference (golden fixture, same burn-in,
+    iterations and scoring period); replicate means agree within Monte Carlo error."""
+    fx = golden(name)
+    ref = fx["lod_curves_default_mix"]                         # [replicates, M-1, n_lod]
+    plan = gpu(name).plan
+    n_mine = 8
+    mine = np.stack([_gpu_chain_lod(plan, fx, 7000 + s, lsampler_prob=0.5) for s in range(n_mine)])
+    assert np.isfinite(mine).all()
+    a, b = mine.mean(axis=(1, 2)), ref.mean(axis=(1, 2))
+    se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b)) + 1e-3
+    z_mean = abs(a.mean() - b.mean()) / se
+    sep = np.sqrt(mine.var(axis=0, ddof=1) / n_mine + ref.var(axis=0, ddof=1) / ref.shape[0]) + 1e-3
+    z_pos = np.abs(mine.mean(axis=0) - ref.mean(axis=0)) / sep
+    print("%s (default mix): mean LOD device %.3f reference %.3f (se %.3f, z %.2f); max per-position z %.2f" %
           (name, a.mean(), b.mean(), se, z_mean, z_pos.max()))
     assert z_mean < 4.0
     assert z_pos.max() < 6.0
