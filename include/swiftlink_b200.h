@@ -188,7 +188,9 @@ int slk_msampler_reset(slk_chain* chain);
    indicator draw of locus l is uniform(seed, chain, iteration, l, SLK_SLOT_MEIOSIS + meiosis). */
 int slk_msampler_step(slk_chain* chain, uint64_t iteration, int meiosis);
 /* One M-sweep (markov_chain.cc:342-349): Philox Fisher-Yates shuffle of the ordering, reset, one step
-   per meiosis -- every launch asynchronous on the chain's stream. */
+   per meiosis -- every launch asynchronous on the chain's stream.  Steps are issued in pairs: the
+   second meiosis's likelihoods are evaluated under both outcomes of the first, which changes the
+   launch count, not the result. */
 int slk_msampler_sweep(slk_chain* chain, uint64_t iteration);
 /* DescentGraph::get_likelihood (descent_graph.cc:150-156): ln of transmission x recombination x
    founder-allele-graph prior; -DBL_MAX (LOG_ILLEGAL) if some locus has likelihood 0.  Synchronises. */
@@ -227,13 +229,12 @@ int slk_debug_lsampler_step(slk_chain* chain, uint64_t iteration, int locus, int
 int slk_debug_lod_interval(slk_chain* chain, int interval, double* result, double* prob,
                            int dump_k, double* matrices);
 /* founder allele graph of every locus on the chain's graph, optionally with one meiosis flipped
-   (meiosis < 0: none): lik[M] and, if edges != NULL, the edge lists [M][2N]
-   (FounderAlleleGraph4::reset / flip / likelihood) */
-int slk_debug_fag(slk_chain* chain, int meiosis, double* lik, int32_t* edges);
-/* after slk_msampler_step: raw_matrix [M][2] as the step saw it is not kept; this returns the
-   forward matrix fb[M][2] (meiosis_sampler.cc:134-153, before the backward pass) and the carried
-   per-locus likelihood cur[M] of the graph the step left */
-int slk_debug_msampler_state(slk_chain* chain, double* fb, double* cur);
+   (meiosis < 0: none): ln likelihood [M] (-inf where the reference returns 0) and, if edges != NULL,
+   the edge lists [M][2N] (FounderAlleleGraph4::reset / flip / likelihood) */
+int slk_debug_fag(slk_chain* chain, int meiosis, double* ln_lik, int32_t* edges);
+/* after slk_msampler_step: the forward matrix fb[M][2] (meiosis_sampler.cc:134-153, before the
+   backward pass) and the carried per-locus ln likelihood [M] of the graph the step left */
+int slk_debug_msampler_state(slk_chain* chain, double* fb, double* ln_cur);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward
    level, after every backward level, after the indicators.  Returns the number of stamps. */

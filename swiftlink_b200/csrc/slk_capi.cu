@@ -77,7 +77,7 @@ struct slk_chain {
     int* err;                     // device [4]
     int32_t count;                // scoring passes (LODscores::count)
     // M-sampler state (allocated on first use)
-    double* ms_cur; double2* ms_raw; uint8_t* ms_bits; double* ms_u; double* ms_fb; double* ms_out;
+    double* ms_lncur; double* ms_lnl; uint8_t* ms_bits; double* ms_fb; double* ms_out;
     bool ms_cur_valid;            // ms_cur describes the graph now in dgp
     // debug buffers (allocated on first use)
     double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
@@ -275,6 +275,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         dp.table_doubles_per_child = hp.table_doubles_per_child;
     }
     UP(ms.seq, h.ms_seq); UP(ms.typed, h.ms_typed); UP(ms.obsT, h.ms_obsT); UP(ms.minor, h.ms_minor);
+    UP(ms.lnmajor, h.ms_lnmajor); UP(ms.lnminor, h.ms_lnminor);
     d.ms.n_typed = (int) h.ms_typed.size();
     d.ms.available = h.ms_available ? 1 : 0;
 #undef UP
@@ -299,7 +300,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         {
             const int per_thread = (h.M + SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS - 1) / (SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS);
             p->ms_chain_loci = per_thread * SLK_MS_CHAIN_THREADS;
-            p->ms_chain_smem = (p->ms_chain_loci * 17 + 15) & ~15;
+            p->ms_chain_smem = (p->ms_chain_loci * SLK_MS_CHAIN_BYTES_PER_LOCUS + 15) & ~15;
             if(p->ms_chain_smem > slk::kSmemPerBlockMax - 4096) p->ms_threads = 0;     // > 100k markers: unsupported for now
         }
     }
@@ -406,7 +407,7 @@ void slk_chain_destroy(slk_chain* c) {
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
     cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
-    cudaFree(c->ms_cur); cudaFree(c->ms_raw); cudaFree(c->ms_bits); cudaFree(c->ms_u); cudaFree(c->ms_fb); cudaFree(c->ms_out);
+    cudaFree(c->ms_lncur); cudaFree(c->ms_lnl); cudaFree(c->ms_bits); cudaFree(c->ms_fb); cudaFree(c->ms_out);
     delete c;
 }
 
@@ -599,14 +600,13 @@ static int ms_ready(slk_chain* c) {
     slk_plan* p = c->plan;
     if(!p->dev.ms.available) return fail(SLK_ERR_UNSUPPORTED, "slk_problem.minor_freq was NULL: the M-sampler tables were not built");
     if(p->ms_threads < 32)
-        return fail(SLK_ERR_UNSUPPORTED, "pedigree too large for the M-sampler's shared-memory tables (N=%d, F=%d)", p->dev.N, p->dev.F);
+        return fail(SLK_ERR_UNSUPPORTED, "pedigree or map too large for the M-sampler's shared-memory tables (N=%d, F=%d, M=%d)", p->dev.N, p->dev.F, p->dev.M);
     CU(cudaSetDevice(p->device));
-    if(!c->ms_cur) {
+    if(!c->ms_lncur) {
         const size_t M = (size_t) p->dev.M;
-        CU(cudaMalloc((void**) &c->ms_cur, sizeof(double) * M));
-        CU(cudaMalloc((void**) &c->ms_raw, sizeof(double2) * M));
-        CU(cudaMalloc((void**) &c->ms_bits, M));
-        CU(cudaMalloc((void**) &c->ms_u, sizeof(double) * M));
+        CU(cudaMalloc((void**) &c->ms_lncur, sizeof(double) * M));
+        CU(cudaMalloc((void**) &c->ms_lnl, sizeof(double) * SLK_MS_MAXSETS * M));
+        CU(cudaMalloc((void**) &c->ms_bits, 2 * M));
         CU(cudaMalloc((void**) &c->ms_fb, sizeof(double) * 2 * M));
         CU(cudaMalloc((void**) &c->ms_out, sizeof(double) * 4));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
@@ -623,17 +623,42 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.N = d.N; L.F = d.F; L.M = d.M; L.sex_linked = d.sex_linked;
     L.mother = d.mother; L.father = d.father; L.male = d.male; L.theta = d.theta;
     L.log_theta = d.log_theta; L.log_1mtheta = d.log_1mtheta;
-    L.dgp = c->dgp; L.cur = c->ms_cur; L.raw = c->ms_raw; L.bits = c->ms_bits; L.u = c->ms_u; L.fb = c->ms_fb; L.err = c->err;
+    L.dgp = c->dgp; L.lncur = c->ms_lncur; L.lnl = c->ms_lnl; L.bits = c->ms_bits; L.fb = c->ms_fb; L.err = c->err;
     L.out = c->ms_out;
-    L.person = -1; L.parent = 0;
+    L.nsets = 1;
     L.seed = c->seed; L.chain = c->chain_id;
     return L;
 }
 
 static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
     slk_plan* p = c->plan;
-    if(2 * p->dev.F > 256) slk_ms_likelihood_kernel<true><<<p->ms_grid, p->ms_threads, p->ms_smem, c->stream>>>(L);
-    else slk_ms_likelihood_kernel<false><<<p->ms_grid, p->ms_threads, p->ms_smem, c->stream>>>(L);
+    const int grid = p->ms_grid * L.nsets;
+    if(2 * p->dev.F > 255) slk_ms_likelihood_kernel<true><<<grid, 32, p->ms_smem, c->stream>>>(L);
+    else slk_ms_likelihood_kernel<false><<<grid, 32, p->ms_smem, c->stream>>>(L);
+}
+
+// one or two consecutive steps of a sweep: the second meiosis's likelihood is evaluated under both
+// outcomes of the first, so the pair costs one likelihood launch and one chain launch
+static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1) {
+    const SlkDevPlan& d = c->plan->dev;
+    SlkMsLaunch L = ms_launch(c);
+    L.iteration = iteration;
+    const int p0 = d.F + m0 / 2, a0 = m0 % 2;
+    L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
+    L.nsteps = 1;
+    L.step_person[0] = p0; L.step_parent[0] = a0; L.step_slot[0] = SLK_SLOT_MEIOSIS + (uint32_t) m0;
+    if(m1 >= 0) {
+        const int p1 = d.F + m1 / 2, a1 = m1 % 2;
+        L.nsets = 3; L.nsteps = 2;
+        L.set_n[1] = 1; L.set_person[1][0] = p1; L.set_parent[1][0] = a1;
+        L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
+        L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) m1;
+    }
+    ms_launch_likelihood(c, L);
+    CU(cudaGetLastError());
+    slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
+    CU(cudaGetLastError());
+    return SLK_OK;
 }
 
 int slk_msampler_ordering(const slk_plan* plan, int32_t* out, int cap) {
@@ -647,6 +672,7 @@ int slk_msampler_reset(slk_chain* c) {
     int rc = ms_ready(c);
     if(rc != SLK_OK) return rc;
     SlkMsLaunch L = ms_launch(c);
+    L.nsets = 1; L.set_n[0] = 0;
     ms_launch_likelihood(c, L);
     CU(cudaGetLastError());
     c->ms_cur_valid = true;
@@ -662,16 +688,7 @@ int slk_msampler_step(slk_chain* c, uint64_t iteration, int meiosis) {
         rc = slk_msampler_reset(c);
         if(rc != SLK_OK) return rc;
     }
-    SlkMsLaunch L = ms_launch(c);
-    L.person = d.F + meiosis / 2;
-    L.parent = meiosis % 2;
-    L.iteration = iteration;
-    L.slot = SLK_SLOT_MEIOSIS + (uint32_t) meiosis;
-    ms_launch_likelihood(c, L);
-    CU(cudaGetLastError());
-    slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
-    CU(cudaGetLastError());
-    return SLK_OK;
+    return ms_steps(c, iteration, meiosis, -1);
 }
 
 int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
@@ -688,7 +705,7 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     }
     // MeiosisSampler::reset at the start of every sweep (markov_chain.cc:345)
     rc = slk_msampler_reset(c);
-    for(int j = 0; j < n && rc == SLK_OK; ++j) rc = slk_msampler_step(c, iteration, order[j]);
+    for(int j = 0; j < n && rc == SLK_OK; j += 2) rc = ms_steps(c, iteration, order[j], j + 1 < n ? order[j + 1] : -1);
     return rc;
 }
 
@@ -717,8 +734,8 @@ int slk_sweep_is_lsampler(const slk_chain* c, uint64_t iteration, double lsample
     return slk_uniform(c->seed, c->chain_id, iteration, 0u, SLK_SLOT_KIND) < lsampler_prob ? 1 : 0;
 }
 
-int slk_debug_fag(slk_chain* c, int meiosis, double* lik, int32_t* edges) {
-    if(!lik) return fail(SLK_ERR_INVALID, "null argument");
+int slk_debug_fag(slk_chain* c, int meiosis, double* lnlik, int32_t* edges) {
+    if(!lnlik) return fail(SLK_ERR_INVALID, "null argument");
     int rc = ms_ready(c);
     if(rc != SLK_OK) return rc;
     const SlkDevPlan& d = c->plan->dev;
@@ -729,31 +746,24 @@ int slk_debug_fag(slk_chain* c, int meiosis, double* lik, int32_t* edges) {
         CU(cudaMalloc((void**) &dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N));
         L.dump_edges = dev_edges;
     }
-    if(meiosis >= 0) { L.person = d.F + meiosis / 2; L.parent = meiosis % 2; }
-    else c->ms_cur_valid = true;              // the no-flip launch refreshes ms_cur
+    L.nsets = 1;
+    if(meiosis >= 0) { L.set_n[0] = 1; L.set_person[0][0] = d.F + meiosis / 2; L.set_parent[0][0] = meiosis % 2; }
+    else { L.set_n[0] = 0; c->ms_cur_valid = true; }         // the no-flip launch refreshes ms_lncur
     ms_launch_likelihood(c, L);
     CU(cudaGetLastError());
-    std::vector<double> pairs;
-    std::vector<uint8_t> bits;
-    if(meiosis >= 0) {
-        pairs.resize(2 * (size_t) d.M); bits.resize(d.M);
-        CU(cudaMemcpyAsync(pairs.data(), c->ms_raw, sizeof(double) * 2 * d.M, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(bits.data(), c->ms_bits, d.M, cudaMemcpyDeviceToHost, c->stream));
-    }
-    else CU(cudaMemcpyAsync(lik, c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(lnlik, meiosis >= 0 ? c->ms_lnl : c->ms_lncur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
     if(edges) CU(cudaMemcpyAsync(edges, dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_error(c);
     cudaFree(dev_edges);
-    if(meiosis >= 0) for(int l = 0; l < d.M; ++l) lik[l] = pairs[2 * l + ((bits[l] & 1) ? 0 : 1)];   // the flipped value
     return rc;
 }
 
-int slk_debug_msampler_state(slk_chain* c, double* fb, double* cur) {
+int slk_debug_msampler_state(slk_chain* c, double* fb, double* lncur) {
     int rc = ms_ready(c);
     if(rc != SLK_OK) return rc;
     const SlkDevPlan& d = c->plan->dev;
-    if(fb)  CU(cudaMemcpyAsync(fb, c->ms_fb, sizeof(double) * 2 * d.M, cudaMemcpyDeviceToHost, c->stream));
-    if(cur) CU(cudaMemcpyAsync(cur, c->ms_cur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
+    if(fb)    CU(cudaMemcpyAsync(fb, c->ms_fb, sizeof(double) * 2 * d.M, cudaMemcpyDeviceToHost, c->stream));
+    if(lncur) CU(cudaMemcpyAsync(lncur, c->ms_lncur, sizeof(double) * d.M, cudaMemcpyDeviceToHost, c->stream));
     return check_device_error(c);
 }
 

@@ -512,6 +512,12 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
             for(int l = 0; l < M; ++l) hp.ms_obsT[(size_t) k * M + l] = pb.genotypes[(size_t) hp.ms_typed[k] * M + l];
         hp.ms_minor.assign(M, 0.0);
         if(pb.minor_freq) hp.ms_minor.assign(pb.minor_freq, pb.minor_freq + M);
+        hp.ms_lnmajor.resize(M); hp.ms_lnminor.resize(M);
+        for(int l = 0; l < M; ++l) {
+            const double mn = hp.ms_minor[l], mj = 1.0 - mn;                    // genetic_map.h:42-47
+            hp.ms_lnmajor[l] = mj > 0.0 ? log(mj) : -1e300;
+            hp.ms_lnminor[l] = mn > 0.0 ? log(mn) : -1e300;
+        }
         // markov_chain.cc:68-80 with Person::safe_to_ignore_meiosis (person.cc:208-222)
         std::vector<int> nchild(N, 0);
         for(int i = F; i < N; ++i) { nchild[pb.mother[i]]++; nchild[pb.father[i]]++; }

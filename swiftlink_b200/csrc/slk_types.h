@@ -77,6 +77,8 @@ struct SlkMsPlan {
     const uint16_t* typed;          // [n_typed] Person::istyped(), pedigree order
     const uint8_t* obsT;            // [n_typed][M] observed genotype (SLK_UNTYPED..SLK_HOMOZ_B)
     const double* minor;            // [M] Snp::minor()
+    const double* lnmajor;          // [M] ln(1 - minor) (-1e300 if the frequency is 0)
+    const double* lnminor;          // [M] ln(minor)
     int n_typed;
     int available;                  // slk_problem.minor_freq was given
 };

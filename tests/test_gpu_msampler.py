@@ -1,10 +1,11 @@
 """M-sampler and descent-graph likelihood on the device, through the C ABI, against the C oracle
 (oracle/msampler_oracle.c, pinned bit-exact to the compiled reference) and the golden vectors.
 
-Bar: founder-allele-graph edge lists and likelihoods bit-exact (integer labels; same floating-point
-operation order), sampled descent graphs identical under the shared Philox draws, the forward matrix
-within 1e-12 relative (the device evaluates the two-state recurrence as a blocked scan; north_star
-allows 1e-9), ln-likelihoods within 1e-12 relative."""
+Bar: founder-allele-graph edge lists bit-exact (integer labels); per-locus likelihoods within 1e-12 on
+ln L (the device counts the exponents of the two allele frequencies exactly and rounds once, the
+reference multiplies as it walks the graph); sampled descent graphs identical under the shared Philox
+draws; the forward matrix within 1e-10 relative (blocked scan instead of a sequential pass; north_star
+allows 1e-9); ln-likelihoods of whole graphs within 1e-12 relative."""
 import numpy as np
 import pytest
 
@@ -13,6 +14,17 @@ from common import CASES, golden, problem, oracle_problem
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
+TOL_FB = 1e-10
+
+
+def ln_close(ln_got, lik_want):
+    """device ln L against a reference likelihood (0 <-> -inf)"""
+    ln_got, lik_want = np.asarray(ln_got, float), np.asarray(lik_want, float)
+    zero = lik_want == 0.0
+    if not (np.isneginf(ln_got) == zero).all():
+        return False
+    want = np.log(lik_want[~zero])
+    return bool((np.abs(ln_got[~zero] - want) <= TOL * np.maximum(1.0, np.abs(want))).all())
 
 
 @pytest.fixture(scope="module")
@@ -58,12 +70,12 @@ def test_founder_allele_graph_bit_exact(gpu, name):
     fx, ms, ch = golden(name), golden(name + "_ms"), gpu(name)
     for gi in range(fx["dgs"].shape[0]):
         ch.dg_upload(fx["dgs"][gi])
-        lik, edges = ch.debug_fag(-1, edges=True)
+        lnl, edges = ch.debug_fag(-1, edges=True)
         assert (edges == ms["fag_edges_%d" % gi]).all()
-        assert (lik == ms["fag_lik_%d" % gi]).all()
+        assert ln_close(lnl, ms["fag_lik_%d" % gi])
         for k, m in enumerate(ms["flip_meioses"]):
             fl, _ = ch.debug_fag(int(m))
-            assert (fl == ms["fag_flip_lik_%d" % gi][:, k]).all(), (name, gi, m)
+            assert ln_close(fl, ms["fag_flip_lik_%d" % gi][:, k]), (name, gi, m)
         assert (ch.dg_download() == fx["dgs"][gi]).all()
 
 
@@ -73,10 +85,13 @@ def test_flipped_edges_match_oracle(gpu, name):
     dg = np.ascontiguousarray(fx["dgs"][3])
     ch.dg_upload(dg)
     for m in orc.ms_ordering():
-        lik, edges = ch.debug_fag(int(m), edges=True)
+        lnl, edges = ch.debug_fag(int(m), edges=True)
+        want = []
         for l in range(orc.M):
             e, v = orc.fag(dg, l, (orc.F + int(m) // 2, int(m) % 2))
-            assert (e == edges[l]).all() and v == lik[l]
+            assert (e == edges[l]).all()
+            want.append(v)
+        assert ln_close(lnl, want), (name, m)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -107,11 +122,11 @@ def test_steps_match_oracle(gpu, name):
             ch.msampler_step(100 + it, int(m))
             fb, cur = ch.debug_msampler_state()
             st = s.state()
-            assert rel(fb, st["fwd"]) <= TOL, (name, gi, m, rel(fb, st["fwd"]))
+            assert rel(fb, st["fwd"]) <= TOL_FB, (name, gi, m, rel(fb, st["fwd"]))
             got = ch.dg_download()
             assert (got == dg).all(), (name, gi, it, m)
             person, par = orc.F + int(m) // 2, int(m) % 2
-            assert (cur == st["raw"][np.arange(orc.M), dg[:, person, par]]).all()
+            assert ln_close(cur, st["raw"][np.arange(orc.M), dg[:, person, par]])
             flips += int((before != dg).sum())
         if name != "loop":
             assert flips > 0
