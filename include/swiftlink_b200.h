@@ -146,6 +146,10 @@ int slk_chain_sync(slk_chain* chain);         /* replaces GPULodscores::block_un
    (gpu_lodscores.cc:602) / copy_to_gpu / copy_from_gpu */
 int slk_dg_upload(slk_chain* chain, const int32_t* dg);
 int slk_dg_download(slk_chain* chain, int32_t* dg);
+/* exchange the descent graphs of two chains of the same device and dimensions in O(1) (the
+   Metropolis-coupled swap of Mc3::run, mc3.cc:155-159, `swap(graphs[rand], graphs[rand+1])`); the
+   plans may differ (heated maps).  Both streams are synchronised first. */
+int slk_dg_swap(slk_chain* a, slk_chain* b);
 
 /* ---- L-sampler: replaces run_gpu_lsampler_kernel(numblocks, numthreads, state, window_length,
         offset) (cuda_common.h:236, cuda_lsampler.cu:403-449) ------------------------------- */
@@ -235,6 +239,10 @@ int slk_debug_fag(slk_chain* chain, int meiosis, double* ln_lik, int32_t* edges)
 /* after slk_msampler_step: the forward matrix fb[M][2] (meiosis_sampler.cc:134-153, before the
    backward pass) and the carried per-locus ln likelihood [M] of the graph the step left */
 int slk_debug_msampler_state(slk_chain* chain, double* fb, double* ln_cur);
+/* tuning aid: one three-hypothesis likelihood launch for the pair (meiosis0, meiosis1) that records
+   clock64() stamps of lane 0 of every 64th CTA: stamps[16][8] = start, tables built, genotypes staged,
+   labels done, typed labels kept, graph walked, result written */
+int slk_debug_msampler_trace(slk_chain* chain, int meiosis0, int meiosis1, long long* stamps);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward
    level, after every backward level, after the indicators.  Returns the number of stamps. */

@@ -63,6 +63,15 @@ int slk_host_write_results(slk_host* h, const char* filename, const double* lod)
 int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int burnin, int iterations,
                        int scoring_period, double lsampler_prob, int32_t* dg, double* lod_out, double* trait_prob_out);
 
+/* Mc3::run (mc3.cc:81-200, see swiftlink_b200/csrc/host/mc3.cc for the specified behaviour): a ladder
+   of n_chains heated chains on one device, temperatures NULL = the reference's ladder
+   1 / (1 + 0.001 * 2^i); swap_success / swap_failure [n_chains] receive the exchange counts of each
+   adjacent pair; lod_out the cold chain's normalised LOD scores. */
+int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int n_chains, int exchange_period,
+                     const double* temperatures, int burnin, int iterations, int scoring_period, double lsampler_prob,
+                     int si_iterations, double* lod_out, int32_t* swap_success, int32_t* swap_failure);
+double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures);
+
 #ifdef __cplusplus
 }
 #endif

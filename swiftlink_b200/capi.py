@@ -22,12 +22,12 @@ SYMBOLS = [
     "slk_abi_version", "slk_last_error", "slk_device_count",
     "slk_plan_create", "slk_plan_destroy", "slk_plan_stats", "slk_plan_validate",
     "slk_chain_create", "slk_chain_destroy", "slk_chain_set_stream", "slk_chain_sync",
-    "slk_dg_upload", "slk_dg_download",
+    "slk_dg_upload", "slk_dg_download", "slk_dg_swap",
     "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood",
     "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
-    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state",
+    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
     "slk_debug_philox", "slk_debug_uniform", "slk_measure_fp64_peak",
 ]
@@ -215,6 +215,9 @@ class Chain(object):
     def dg_download_ptr(self, ptr):
         _check(self.L.slk_dg_download(self.h, C.c_void_p(ptr)))
 
+    def dg_swap(self, other):
+        _check(self.L.slk_dg_swap(self.h, other.h))
+
     def lsampler_window(self, iteration, window, offset):
         _check(self.L.slk_lsampler_window(self.h, C.c_uint64(iteration), int(window), int(offset)))
 
@@ -278,6 +281,11 @@ class Chain(object):
         _check(self.L.slk_debug_fag(self.h, int(meiosis), _ptr(lik, C.c_double),
                                     _ptr(e, C.c_int32) if edges else None))
         return lik, e
+
+    def debug_msampler_trace(self, m0, m1):
+        buf = np.zeros((16, 8), np.int64)
+        _check(self.L.slk_debug_msampler_trace(self.h, int(m0), int(m1), _ptr(buf, C.c_longlong)))
+        return buf
 
     def debug_msampler_state(self):
         fb = np.zeros((self.plan.M, 2)); cur = np.zeros(self.plan.M)

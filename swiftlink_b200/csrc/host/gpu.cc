@@ -51,9 +51,15 @@ void GPULodscores::get_results(LODscores* lod) {
     for(unsigned int i = 0; i < raw.size(); ++i) lod->set(i, raw[i]);
 }
 
-GPUMarkovChain::GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num) :
-    ped(ped), map(map), psg(psg), options(options), plan(0), chain(0), seq_num(sequence_num) {
-    flatten_problem(*ped, *map, *psg, options.sex_linked, flat);
+GPUMarkovChain::GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options,
+                               int sequence_num, double temperature) :
+    ped(ped), map(map), psg(psg), options(options), heated(*map), temperature(temperature), plan(0), chain(0),
+    seq_num(sequence_num), trait_prob(0.0), scoring_started(false) {
+    // MarkovChain::_init: "heat up the map" (markov_chain.cc:33-34).  Thetas and allele frequencies move
+    // towards 0.5; the genotype priors cached per person stay cold, as in the reference (Snp::prob is
+    // not recomputed by set_minor_freq, genetic_map.h:43-47)
+    if(temperature != 1.0) heated.set_temperature(temperature);
+    flatten_problem(*ped, heated, *psg, options.sex_linked, flat);
     die_on(slk_plan_create(&flat.desc, options.device, &plan), "GPUMarkovChain: plan");
     die_on(slk_chain_create(plan, options.seed, (uint32_t) sequence_num, &chain), "GPUMarkovChain: chain");
 }
@@ -98,6 +104,53 @@ double GPUMarkovChain::get_likelihood(DescentGraph& dg) {
     die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::get_likelihood (upload)");
     die_on(slk_dg_likelihood(chain, &v), "GPUMarkovChain::get_likelihood");
     return v;
+}
+
+void GPUMarkovChain::upload(DescentGraph& dg) {
+    die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::upload");
+}
+
+void GPUMarkovChain::download(DescentGraph& dg) {
+    die_on(slk_dg_download(chain, dg.get_internal_ptr()), "GPUMarkovChain::download");
+}
+
+double GPUMarkovChain::get_likelihood() {
+    double v = 0.0;
+    die_on(slk_dg_likelihood(chain, &v), "GPUMarkovChain::get_likelihood");
+    return v;
+}
+
+// MarkovChain::step (markov_chain.cc:107-207): no progress bar, no trace; "only score the coldest chain"
+void GPUMarkovChain::step(int start_iteration, int step_size) {
+    if(!scoring_started) {
+        trait_prob = calc_trait_prob();
+        die_on(slk_lodscore_init(chain), "GPUMarkovChain::step (init)");
+        scoring_started = true;
+    }
+    for(int i = start_iteration; i < start_iteration + step_size; ++i) {
+        if(slk_sweep_is_lsampler(chain, (uint64_t) i, options.lsampler_prob))
+            die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::step (L-sampler)");
+        else
+            die_on(slk_msampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::step (M-sampler)");
+        if(i < options.burnin) continue;
+        if(temperature != 1.0) continue;
+        if((i % options.scoring_period) == 0) die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::step (scoring)");
+    }
+}
+
+LODscores* GPUMarkovChain::get_result() {
+    if(temperature != 1.0) {
+        fprintf(stderr, "error: only the coldest chain can be used!\n");
+        abort();
+    }
+    LODscores* lod = new LODscores(map);
+    std::vector<double> raw(lod->num_lodscores());
+    int32_t count = 0;
+    die_on(slk_lodscore_read(chain, raw.data(), &count), "GPUMarkovChain::get_result");
+    lod->set_trait_prob(trait_prob);
+    lod->set_count((unsigned int) count);
+    if(count > 0) for(unsigned int i = 0; i < raw.size(); ++i) lod->set(i, raw[i]);
+    return lod;
 }
 
 // markov_chain.cc:314-404 with every sampler and the scoring on the device: each iteration is an

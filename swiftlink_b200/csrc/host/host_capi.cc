@@ -190,4 +190,32 @@ int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id
     return SLK_OK;
 }
 
+int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int n_chains, int exchange_period,
+                     const double* temperatures, int burnin, int iterations, int scoring_period, double lsampler_prob,
+                     int si_iterations, double* lod_out, int32_t* swap_success, int32_t* swap_failure) {
+    if(!h->psg) return SLK_ERR_INVALID;
+    struct mcmc_options o;
+    o.burnin = burnin; o.iterations = iterations; o.scoring_period = scoring_period; o.si_iterations = si_iterations;
+    o.lsampler_prob = lsampler_prob; o.sex_linked = h->dm.is_sexlinked(); o.seed = seed; o.device = device;
+    o.mc3 = true; o.mc3_number_of_chains = n_chains; o.mc3_exchange_period = exchange_period;
+    if(temperatures) o.mc3_temperatures.assign(temperatures, temperatures + n_chains);
+    Mc3 mc3(h->ped, &h->map, h->psg, o, (int) chain_id);
+    LODscores* lod = mc3.run();
+    const unsigned n = h->map.get_lodscore_count();
+    for(unsigned l = 0; l + 1 < h->map.num_markers(); ++l) for(unsigned k = 0; k < n; ++k) lod_out[l * n + k] = lod->get(l, k);
+    for(int i = 0; i < n_chains; ++i) {
+        if(swap_success) swap_success[i] = mc3.get_swap_success()[i];
+        if(swap_failure) swap_failure[i] = mc3.get_swap_failure()[i];
+    }
+    delete lod;
+    return SLK_OK;
+}
+
+double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures) {
+    struct mcmc_options o;
+    o.mc3 = true; o.mc3_number_of_chains = n_chains;
+    if(temperatures) o.mc3_temperatures.assign(temperatures, temperatures + n_chains);
+    return mc3_temperature(chain_index, o);
+}
+
 }  // extern "C"

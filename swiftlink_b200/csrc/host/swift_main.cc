@@ -38,6 +38,13 @@ static void usage(const char* prog) {
 "  -n NUM,     --lodscores=NUM             (default = %d)\n"
 "  -R NUM,     --runs=NUM                  (default = %d)\n"
 "\n"
+"Metropolis-coupled MCMC options (commented out in the reference's main.cc:70-75):\n"
+"  -M,         --mcmcmc\n"
+"  -z NUM,     --chains=NUM                (default = %d)\n"
+"  -y NUM,     --exchangeperiod=NUM        (default = %d)\n"
+"  -t FLOAT,FLOAT,... --temperatures=FLOAT,FLOAT,...\n"
+"  -j FILE,    --exchangefile=FILE\n"
+"\n"
 "Runtime options:\n"
 "  -c NUM,     --cores=NUM                 (accepted, ignored: the samplers run on the GPU)\n"
 "  -g,         --gpu                       (always on)\n"
@@ -54,7 +61,7 @@ static void usage(const char* prog) {
 "  -h,         --help\n"
 "\n",
     prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
-    d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
+    d.mc3_number_of_chains, d.mc3_exchange_period, d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
 }
 
 static bool str2int(int& out, const char* s) {
@@ -78,9 +85,11 @@ int main(int argc, char** argv) {
         {"sequentialimputation", required_argument, 0, 's'}, {"verbose", no_argument, 0, 'v'},
         {"scoringperiod", required_argument, 0, 'x'}, {"sexlinked", no_argument, 0, 'X'},
         {"runs", required_argument, 0, 'R'}, {"trace", no_argument, 0, 'T'}, {"device", required_argument, 0, 'D'},
-        {"seed", required_argument, 0, 'S'}, {"traceprefix", required_argument, 0, 'P'}, {0, 0, 0, 0}};
+        {"seed", required_argument, 0, 'S'}, {"traceprefix", required_argument, 0, 'P'}, {"mcmcmc", no_argument, 0, 'M'},
+        {"chains", required_argument, 0, 'z'}, {"exchangeperiod", required_argument, 0, 'y'},
+        {"temperatures", required_argument, 0, 't'}, {"exchangefile", required_argument, 0, 'j'}, {0, 0, 0, 0}};
     int ch, tmp;
-    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:P:", longopts, 0)) != -1) {
+    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:P:Mz:y:t:j:", longopts, 0)) != -1) {
         switch(ch) {
             case 'p': pedfile = optarg; break;
             case 'm': mapfile = optarg; break;
@@ -94,15 +103,36 @@ int main(int argc, char** argv) {
             case 'e': fprintf(stderr, "error: --elod is not part of this build\n"); return EXIT_FAILURE;
             case 'T': o.coda_logging = true; break;
             case 'P': o.coda_prefix = optarg; break;
+            case 'M': o.mc3 = true; break;
+            case 'j': o.exchange_filename = optarg; break;
+            case 't': {
+                o.mc3_temperatures.clear();
+                std::string str(optarg);
+                size_t pos = 0;
+                bool ok = !str.empty();
+                while(ok && pos <= str.size()) {
+                    size_t c = str.find(',', pos);
+                    std::string tok = str.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+                    char* end;
+                    double v = strtod(tok.c_str(), &end);
+                    if(tok.empty() || *end != '\0' || v < 0.0 || v > 1.0) ok = false;
+                    else o.mc3_temperatures.push_back(v);
+                    if(c == std::string::npos) break;
+                    pos = c + 1;
+                }
+                if(!ok) { fprintf(stderr, "%s: temperatures must be comma delimited floats from 0.0 - 1.0 inclusive, e.g.: 1.0,0.9,0.8,0.7 ('%s' given)\n", argv[0], optarg); return EXIT_FAILURE; }
+                break;
+            }
             case 'l': o.lsampler_prob = atof(optarg);
                       if(o.lsampler_prob < 0.0 || o.lsampler_prob > 1.0) { fprintf(stderr, "%s: option '-l' requires a floating point argument between 0.0 and 1.0\n", argv[0]); return EXIT_FAILURE; }
                       break;
             case 'S': o.seed = strtoull(optarg, 0, 10); break;
-            case 'i': case 'b': case 's': case 'x': case 'q': case 'n': case 'R': case 'c': case 'D':
+            case 'i': case 'b': case 's': case 'x': case 'q': case 'n': case 'R': case 'c': case 'D': case 'z': case 'y':
                 if(!str2int(tmp, optarg) || tmp < 0) { fprintf(stderr, "%s: option '-%c' requires a non-negative integer argument ('%s' given)\n", argv[0], ch, optarg); return EXIT_FAILURE; }
                 if(ch == 'i') o.iterations = tmp; else if(ch == 'b') o.burnin = tmp; else if(ch == 's') o.si_iterations = tmp;
                 else if(ch == 'x') o.scoring_period = tmp; else if(ch == 'q') o.peelopt_iterations = tmp;
                 else if(ch == 'n') o.lodscores = tmp; else if(ch == 'R') o.mcmc_runs = tmp; else if(ch == 'c') o.thread_count = tmp;
+                else if(ch == 'z') o.mc3_number_of_chains = tmp; else if(ch == 'y') o.mc3_exchange_period = tmp;
                 else o.device = tmp;
                 break;
             case ':': fprintf(stderr, "%s: option '-%c' requires an argument\n", argv[0], optopt); return EXIT_FAILURE;
@@ -112,6 +142,12 @@ int main(int argc, char** argv) {
     if(pedfile.empty() || mapfile.empty() || datfile.empty()) {
         fprintf(stderr, "%s: the pedigree, map and dat files are all required\n", argv[0]);
         usage(argv[0]);
+        return EXIT_FAILURE;
+    }
+    if(o.mc3_number_of_chains < 1 || o.mc3_exchange_period < 1) { fprintf(stderr, "%s: -z and -y must be at least 1\n", argv[0]); return EXIT_FAILURE; }
+    if(!o.mc3_temperatures.empty() && (int) o.mc3_temperatures.size() != o.mc3_number_of_chains) {
+        fprintf(stderr, "%s: %d temperature%s specified, but there are %d chain%s\n", argv[0], (int) o.mc3_temperatures.size(),
+                o.mc3_temperatures.size() == 1 ? " was" : "s were", o.mc3_number_of_chains, o.mc3_number_of_chains == 1 ? "" : "s");   // main.cc:539-546
         return EXIT_FAILURE;
     }
     if(o.scoring_period < 1 || o.lodscores < 1 || o.mcmc_runs < 1) { fprintf(stderr, "%s: -x, -n and -R must be at least 1\n", argv[0]); return EXIT_FAILURE; }
@@ -146,10 +182,17 @@ int main(int argc, char** argv) {
 
         LODscores* total = 0;
         for(int r = 0; r < o.mcmc_runs; ++r) {
-            DescentGraph dg(&p, &map, dm.is_sexlinked());
-            GPUMarkovChain chain(&p, &map, &psg, o, r);
-            chain.sequential_imputation(dg, o.si_iterations);
-            LODscores* lod = chain.run(dg);
+            LODscores* lod;
+            if(o.mc3 && o.mc3_number_of_chains > 1) {
+                Mc3 ladder(&p, &map, &psg, o, r);                 // linkage_program.cc:169-170 (commented out upstream)
+                lod = ladder.run();
+            }
+            else {
+                DescentGraph dg(&p, &map, dm.is_sexlinked());
+                GPUMarkovChain chain(&p, &map, &psg, o, r);
+                chain.sequential_imputation(dg, o.si_iterations);
+                lod = chain.run(dg);
+            }
             if(!total) total = lod;
             else { total->merge_results(lod); delete lod; }
         }

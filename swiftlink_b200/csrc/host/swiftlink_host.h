@@ -45,6 +45,11 @@ struct mcmc_options {
     bool affected_only, sex_linked;
     uint64_t seed;              // Philox seed (replaces the per-thread mt19937 seed file)
     int device;                 // CUDA device of this chain group
+    // Metropolis-coupled MCMC (types.h:94-98)
+    bool mc3;
+    int mc3_number_of_chains, mc3_exchange_period;
+    std::vector<double> mc3_temperatures;
+    std::string exchange_filename;
     mcmc_options();
 };
 
@@ -383,20 +388,58 @@ class GPUMarkovChain {
     GeneticMap* map;
     PeelSequenceGenerator* psg;
     struct mcmc_options options;
+    GeneticMap heated;          // the chain's own copy of the map (MarkovChain::map is a value member, heated in _init)
+    double temperature;
     FlatProblem flat;
     slk_plan* plan;
     slk_chain* chain;
     int seq_num;
+    double trait_prob;
+    bool scoring_started;
  public:
-    GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num = 0);
+    // temperature as in MarkovChain(ped, map, psg, options, temp) (markov_chain.h:44-70): 1.0 = cold
+    GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options,
+                   int sequence_num = 0, double temperature = 1.0);
     ~GPUMarkovChain();
     LODscores* run(DescentGraph& dg);           // gpu_markov_chain.cc:991 / markov_chain.cc:314
+    // MarkovChain::step (markov_chain.cc:107-207) on the chain's device-resident graph: step_size
+    // iterations numbered from start_iteration; only the cold chain scores
+    void step(int start_iteration, int step_size);
+    void upload(DescentGraph& dg);
+    void download(DescentGraph& dg);
+    double get_likelihood();                    // MarkovChain::get_likelihood of the device-resident graph
+    LODscores* get_result();                    // markov_chain.h:113-119
+    double get_temperature() const { return temperature; }
     // SequentialImputation::parallel_run (sequential_imputation.cc:47-115) on the device: best of
     // `iterations` runs of LocusSampler::start_from, or locus_by_locus when iterations == 0
     double sequential_imputation(DescentGraph& dg, int iterations);
     double calc_trait_prob();                   // Peeler::calc_trait_prob on the device
     double get_likelihood(DescentGraph& dg);    // DescentGraph::get_likelihood on the device
     slk_chain* get_chain() { return chain; }
+};
+
+// ---- Metropolis-coupled MCMC (mc3.h/.cc) ----------------------------------------------------------------
+// The reference's Mc3 is compiled but unreachable (linkage_program.cc:169-170 is commented out, the
+// -M/-z/-y/-t flags too, main.cc:70-75,382-428) and its driver numbers iterations i * spurts instead
+// of i * exchange_period (mc3.cc:117).  This class specifies the intended behaviour: same ladder
+// (mc3.cc:36-42), same heating (genetic_map.cc:95-117), same swap rule (mc3.cc:138-162), iterations
+// numbered consecutively; every chain of the ladder lives on one device and a swap exchanges two
+// device pointers.
+double mc3_temperature(int chain_index, const struct mcmc_options& options);      // mc3.cc:31-42
+class Mc3 {
+    Pedigree* ped;
+    GeneticMap* map;
+    PeelSequenceGenerator* psg;
+    struct mcmc_options options;
+    std::vector<GPUMarkovChain*> chains;
+    std::vector<int> swap_success, swap_failure;
+    int seq_num;
+ public:
+    Mc3(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num = 0);
+    ~Mc3();
+    LODscores* run();                           // mc3.cc:81-200; the caller deletes the result
+    const std::vector<int>& get_swap_success() const { return swap_success; }
+    const std::vector<int>& get_swap_failure() const { return swap_failure; }
 };
 
 }  // namespace swiftlink

@@ -295,7 +295,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
             p->ms_grid = (h.M + 31) / 32; p->ms_threads = 32;
             p->ms_smem = (int) lay.cta_tables + 32 * (int) lay.per_thread;
         }
-        if(lay.G > SLK_MS_MAXGROUPS) p->ms_threads = 0;
+        if(lay.G > SLK_MS_MAXGROUPS || h.N >= 2048) p->ms_threads = 0;      // 12-bit component ids, 16-bit row offsets
         // chain kernel: raw pair (16 B) + one map byte per locus of the CTA's share of the chromosome
         {
             const int per_thread = (h.M + SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS - 1) / (SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS);
@@ -446,6 +446,20 @@ int slk_dg_download(slk_chain* c, int32_t* dg) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(dg, c->dg_staging, cells * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     return check_device_error(c);
+}
+
+int slk_dg_swap(slk_chain* a, slk_chain* b) {
+    if(!a || !b) return fail(SLK_ERR_INVALID, "null chain");
+    const SlkDevPlan& da = a->plan->dev;
+    const SlkDevPlan& db = b->plan->dev;
+    if(a->plan->device != b->plan->device || da.M != db.M || da.N != db.N)
+        return fail(SLK_ERR_INVALID, "slk_dg_swap: chains must live on one device and have the same dimensions");
+    CU(cudaSetDevice(a->plan->device));
+    CU(cudaStreamSynchronize(a->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    std::swap(a->dgp, b->dgp);
+    a->ms_cur_valid = b->ms_cur_valid = false;     // the carried likelihoods belong to the other plan's frequencies
+    return SLK_OK;
 }
 
 int slk_lsampler_window(slk_chain* c, uint64_t iteration, int window_length, int offset) {
@@ -755,6 +769,29 @@ int slk_debug_fag(slk_chain* c, int meiosis, double* lnlik, int32_t* edges) {
     if(edges) CU(cudaMemcpyAsync(edges, dev_edges, sizeof(int32_t) * (size_t) d.M * 2 * d.N, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_error(c);
     cudaFree(dev_edges);
+    return rc;
+}
+
+int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long* stamps) {
+    if(!stamps) return fail(SLK_ERR_INVALID, "null argument");
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const SlkDevPlan& d = c->plan->dev;
+    long long* dev = 0;
+    CU(cudaMalloc((void**) &dev, sizeof(long long) * 128));
+    CU(cudaMemsetAsync(dev, 0, sizeof(long long) * 128, c->stream));
+    SlkMsLaunch L = ms_launch(c);
+    L.trace = dev;
+    L.nsets = 3;
+    const int p0 = d.F + meiosis0 / 2, a0 = meiosis0 % 2, p1 = d.F + meiosis1 / 2, a1 = meiosis1 % 2;
+    L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
+    L.set_n[1] = 1; L.set_person[1][0] = p1; L.set_parent[1][0] = a1;
+    L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
+    ms_launch_likelihood(c, L);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(stamps, dev, sizeof(long long) * 128, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_error(c);
+    cudaFree(dev);
     return rc;
 }
 

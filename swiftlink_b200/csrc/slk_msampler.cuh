@@ -83,6 +83,7 @@ struct SlkMsLaunch {
     uint64_t seed, iteration;
     uint32_t chain;
     int32_t* dump_edges;         // optional [M][2N] (set 0)
+    long long* trace;            // optional: clock64() stamps of lane 0 of every 64th CTA (tuning aid) [16][8]
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
     const double* log_1mtheta;
@@ -106,7 +107,7 @@ __device__ __forceinline__ void ms_st16(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void ms_st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 // Host and device agree on the carve-up through this function.  Per thread, in bytes:
-//   keep     te (labels of typed people, 2*nt entries of E bytes)
+//   keep     te (labels of typed people, 2*nt entries of E bytes) | obs (their genotypes, 2 bits each)
 //   overlay  phase A: labels (2(N-F) entries of E bytes, founders are implicit) | graph row (N bytes)
 //            phase C: grp (G words, 2 words if wide) | fa (2F x u16)
 // E = 1 if 2F <= 256 else 2 ("wide"); G = min(nt, 2F) components at most (each one is created by a
@@ -114,11 +115,11 @@ __device__ __forceinline__ void ms_st32(uint32_t a, uint32_t v) { asm volatile("
 struct MsLayout {
     int wide;
     int G;
-    uint32_t te, ov;             // region offsets for one thread (multiply by 32 lanes)
+    uint32_t te, obs, ov;        // region offsets for one thread (multiply by 32 lanes)
     uint32_t lab, row;           // phase A inside the overlay
     uint32_t grp, cnt, fa;       // phase C inside the overlay (cnt: second word per component, wide only)
     uint32_t per_thread;         // bytes per thread
-    uint32_t cta_tables;         // bytes of CTA-shared tables (seq, mother, father, typed list, x-male flags)
+    uint32_t cta_tables;         // bytes of CTA-shared tables (per-person records, typed list, x-male flags)
 };
 
 #if defined(__CUDACC__)
@@ -133,7 +134,8 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
 #define r4(x) ((((uint32_t)(x)) + 3u) & ~3u)
 #define r8(x) ((((uint32_t)(x)) + 7u) & ~7u)
     L.te = 0;
-    L.ov = r4(2u * nt * E);
+    L.obs = r4(2u * nt * E);
+    L.ov = L.obs + 4u * ((nt + 15u) / 16u);
     L.lab = 0;
     L.row = L.lab + r4(2u * (N - F) * E);
     const uint32_t a_bytes = L.row + r4((uint32_t) N);
@@ -142,7 +144,7 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
     const uint32_t c_bytes = L.fa + r4(4u * F);
     L.per_thread = L.ov + r4(a_bytes > c_bytes ? a_bytes : c_bytes);
-    L.cta_tables = r8((uint32_t)(2 * (N - F) + 4 * N + 2 * nt + nt + 8));
+    L.cta_tables = r8((uint32_t)(16 * (N - F) + 4 * nt + nt + 8));
 #undef r4
 #undef r8
     return L;
@@ -175,27 +177,44 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     const int N = L.N, F = L.F, M = L.M, nt = L.ms.n_typed;
     const MsLayout lay = slk_ms_layout(N, F, nt);
     const uint32_t t = threadIdx.x;
+    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 16) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
+    if(tr) tr[0] = clock64();
 
-    // CTA-shared tables
-    uint16_t* s_seq = (uint16_t*) ms_smem;                 // [N-F]
-    int16_t* s_mo = (int16_t*)(s_seq + (N - F));          // [N]
-    int16_t* s_fa = s_mo + N;                             // [N]
-    uint16_t* s_typed = (uint16_t*)(s_fa + N);            // [nt]
-    uint8_t* s_auto = (uint8_t*)(s_typed + nt);           // [nt] x-linked male: maternal allele only
-    for(int i = t; i < N - F; i += 32) s_seq[i] = L.ms.seq[i];
-    for(int i = t; i < N; i += 32) { s_mo[i] = L.mother[i]; s_fa[i] = L.father[i]; }
-    for(int i = t; i < nt; i += 32) {
-        int p = L.ms.typed[i];
-        s_typed[i] = (uint16_t) p;
-        s_auto[i] = (L.sex_linked && L.male[p]) ? 1 : 0;
-    }
     // the phase A and phase C tables overlay each other ACROSS the lanes of the warp, so the phases are
     // separated by __syncwarp()
     MsLane ln;
     ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
-    const uint32_t o_te = lay.te * 32u, o_ov = lay.ov * 32u;
+    const uint32_t o_te = lay.te * 32u, o_obs = lay.obs * 32u, o_ov = lay.ov * 32u;
     const uint32_t o_lab = o_ov + lay.lab * 32u, o_row = o_ov + lay.row * 32u;
     const uint32_t o_grp = o_ov + lay.grp * 32u, o_cnt = o_ov + lay.cnt * 32u, o_fa = o_ov + lay.fa * 32u;
+
+    // byte offset (inside the lane-interleaved label array) of the label PAIR of non-founder p: the two
+    // labels are adjacent (narrow: two bytes of one 16-bit half-word; wide: one 32-bit word)
+#define PAIR_OFF(p) (WIDE ? ln_a16_off(2u * (uint32_t)((p) - F)) : ln_a8_off(2u * (uint32_t)((p) - F)))
+    auto ln_a8_off = [](uint32_t k) -> uint32_t { return ((k & ~3u) << 5) | (k & 3u); };
+    auto ln_a16_off = [](uint32_t k) -> uint32_t { return ((k & ~1u) << 6) | ((k & 1u) << 1); };
+
+    // CTA-shared tables, built once per warp: for the k-th non-founder in topological order
+    //   x = person << 16 | offset of its graph-row byte, y = offset of its label pair,
+    //   z / w = mother's / father's label-pair offset, or 0x80000000 | 2 * parent for a founder parent;
+    // for the k-th typed person its label-pair offset or 0x80000000 | 2 * person
+    uint4* s_rec = (uint4*) ms_smem;                       // [N-F]
+    uint32_t* s_trec = (uint32_t*)(s_rec + (N - F));       // [nt]
+    uint8_t* s_auto = (uint8_t*)(s_trec + nt);             // [nt] x-linked male: maternal allele only
+    for(int k = t; k < N - F; k += 32) {
+        const int i = L.ms.seq[k], mo = L.mother[i], fa = L.father[i];
+        uint4 r;
+        r.x = ((uint32_t) i << 16) | ln_a8_off((uint32_t) i);
+        r.y = PAIR_OFF(i);
+        r.z = mo < F ? (0x80000000u | (uint32_t)(2 * mo)) : PAIR_OFF(mo);
+        r.w = fa < F ? (0x80000000u | (uint32_t)(2 * fa)) : PAIR_OFF(fa);
+        s_rec[k] = r;
+    }
+    for(int k = t; k < nt; k += 32) {
+        const int p = L.ms.typed[k];
+        s_trec[k] = p < F ? (0x80000000u | (uint32_t)(2 * p)) : PAIR_OFF(p);
+        s_auto[k] = (L.sex_linked && L.male[p]) ? 1 : 0;
+    }
     __syncwarp();
 
     const int nblk = (M + 31) >> 5;
@@ -206,15 +225,10 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     const int p0 = nflip > 0 ? L.set_person[set][0] : -1, a0 = L.set_parent[set][0];
     const int p1 = nflip > 1 ? L.set_person[set][1] : -1, a1 = L.set_parent[set][1];
 
-#define LAB_LD(k)     (WIDE ? ms_ld16(ln.a16(o_lab, (k))) : ms_ld8(ln.a8(o_lab, (k))))
-#define LAB_ST(k, v)  do { if(WIDE) ms_st16(ln.a16(o_lab, (k)), (v)); else ms_st8(ln.a8(o_lab, (k)), (v)); } while(0)
-#define TE_LD(k)      (WIDE ? ms_ld16(ln.a16(o_te, (k))) : ms_ld8(ln.a8(o_te, (k))))
-#define TE_ST(k, v)   do { if(WIDE) ms_st16(ln.a16(o_te, (k)), (v)); else ms_st8(ln.a8(o_te, (k)), (v)); } while(0)
 #define FA_LD(k)      ms_ld16(ln.a16(o_fa, (k)))
 #define FA_ST(k, v)   ms_st16(ln.a16(o_fa, (k)), (v))
-// founder labels are implicit: person p < F carries alleles 2p, 2p + 1
-#define LABEL_OF(p, b) ((p) < F ? (uint32_t)(2 * (p) + (b)) : LAB_LD(2 * ((p) - F) + (b)))
 
+    if(tr) tr[1] = clock64();
     // ---- phase A: labels -----------------------------------------------------------------------
     if(live) {
         const uint8_t* row = L.dgp + (size_t) l * N;
@@ -225,33 +239,66 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
         else {
             for(int i = F; i < N; ++i) ms_st8(ln.a8(o_row, i), row[i]);
         }
+        // observed genotypes of the typed people ([nt][M] in global memory: coalesced over the lanes),
+        // sixteen independent loads in flight, packed two bits each
+        {
+            const uint8_t* obs = L.ms.obsT + l;
+            for(int w = 0; w * 16 < nt; ++w) {
+                uint32_t acc = 0;
+#pragma unroll
+                for(int j = 0; j < 16; ++j) {
+                    const int k = w * 16 + j;
+                    if(k < nt) acc |= (uint32_t) __ldg(obs + (size_t) k * M) << (2 * j);
+                }
+                ms_st32(ln.a32(o_obs, w), acc);
+            }
+        }
+        if(tr) tr[2] = clock64();
+        const uint32_t lab_base = ln.base + o_lab, row_base = ln.base + o_row;
         for(int k = 0; k < N - F; ++k) {
-            const int i = s_seq[k];
-            uint32_t b = ms_ld8(ln.a8(o_row, i));
+            const uint4 r = s_rec[k];
+            const int i = (int)(r.x >> 16);
+            uint32_t b = ms_ld8(row_base + (r.x & 0xffffu));
             if(i == p0) {
                 if(set < 2) L.bits[(size_t) set * M + l] = (uint8_t)((b >> a0) & 1u);
                 b ^= (1u << a0);
             }
             if(i == p1) b ^= (1u << a1);
-            const int mo = s_mo[i], fa = s_fa[i];
-            const uint32_t m = LABEL_OF(mo, b & 1u);
-            const uint32_t f = LABEL_OF(fa, (b >> 1) & 1u);
-            LAB_ST(2 * (i - F), m);
-            LAB_ST(2 * (i - F) + 1, f);
+            const uint32_t bm = b & 1u, bf = (b >> 1) & 1u;
+            uint32_t m, f;
+            if(WIDE) {
+                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld16(lab_base + r.z + 2u * bm);
+                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld16(lab_base + r.w + 2u * bf);
+                ms_st32(lab_base + r.y, m | (f << 16));
+            }
+            else {
+                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld8(lab_base + r.z + bm);
+                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld8(lab_base + r.w + bf);
+                ms_st16(lab_base + r.y, m | (f << 8));
+            }
         }
         if(L.dump_edges && set == 0) {
             int32_t* e = L.dump_edges + (size_t) l * 2 * N;
-            for(int i = 0; i < 2 * N; ++i) e[i] = (int32_t) LABEL_OF(i >> 1, i & 1);
+            for(int i = 0; i < 2 * F; ++i) e[i] = i;
+            for(int i = 2 * F; i < 2 * N; ++i)
+                e[i] = (int32_t)(WIDE ? ms_ld16(ln.a16(o_lab, i - 2 * F)) : ms_ld8(ln.a8(o_lab, i - 2 * F)));
         }
-        // ---- phase B: keep the typed people's labels ---------------------------------------------
+        if(tr) tr[3] = clock64();
+        // ---- phase B: keep the typed people's label pairs ------------------------------------------
         for(int k = 0; k < nt; ++k) {
-            const int i = s_typed[k];
-            const uint32_t a = LABEL_OF(i, 0), b = LABEL_OF(i, 1);
-            TE_ST(2 * k, a);
-            TE_ST(2 * k + 1, b);
+            const uint32_t c = s_trec[k];
+            if(WIDE) {
+                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffffu) | (((c & 0xffffu) + 1u) << 16)) : ms_ld32(lab_base + c);
+                ms_st32(ln.a16(o_te, 2 * k), v);
+            }
+            else {
+                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffu) | (((c & 0xffu) + 1u) << 8)) : ms_ld16(lab_base + c);
+                ms_st16(ln.a8(o_te, 2 * k), v);
+            }
         }
     }
     __syncwarp();                                      // every lane is done with its labels
+    if(tr) tr[4] = clock64();
     if(!live) return;
     for(int i = 0; i < F; ++i) ms_st32(ln.a32(o_fa, i), 0u);           // two u16 entries per word
 
@@ -291,15 +338,14 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
 
     int ngroups = 0;
     bool dead = false;
-    // observed genotypes come straight from global memory ([nt][M]: coalesced over the lanes), one
-    // person ahead of their use
-    const uint8_t* obs = L.ms.obsT + l;
-    uint32_t g_next = nt > 0 ? __ldg(obs) : 0u;
+    uint32_t gw = 0;
     for(int k = 0; k < nt && !dead; ++k) {
-        const uint32_t g = g_next;
-        if(k + 1 < nt) g_next = __ldg(obs + (size_t)(k + 1) * M);
+        if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
+        const uint32_t g = (gw >> (2 * (k & 15))) & 3u;
         if(g == SLK_UNTYPED) continue;
-        const uint32_t mat = TE_LD(2 * k), pat = TE_LD(2 * k + 1);
+        uint32_t mat, pat;
+        if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
+        else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
         const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
         const bool het = g == SLK_HETERO;
         const uint32_t em = FA_LD(mat);
@@ -446,6 +492,7 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
         ++ngroups;
     }
 
+    if(tr) tr[5] = clock64();
     double ret = -INFINITY;
     if(!dead) {
         const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
@@ -466,13 +513,10 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     }
     if(nflip == 0) L.lncur[l] = ret;
     else L.lnl[(size_t) set * M + l] = ret;
-#undef LAB_LD
-#undef LAB_ST
-#undef TE_LD
-#undef TE_ST
+    if(tr) tr[6] = clock64();
 #undef FA_LD
 #undef FA_ST
-#undef LABEL_OF
+#undef PAIR_OFF
 }
 
 // ---- (2) + (3): forward pass and backward sampling along the chromosome ------------------------------

@@ -31,6 +31,17 @@ def merge_lod(raw, count, group=None):
     return merged, int(c.item())
 
 
+def merge_swap_stats(success, failure, group=None, device=None):
+    """MC3 exchange statistics of every rank's ladder (mc3.cc:107-108,164-181): two small integer
+    all-reduces over 2 x (chains - 1) counters.  Returns (success, failure) summed over ranks."""
+    s = torch.as_tensor(success, dtype=torch.int64, device=device).clone()
+    f = torch.as_tensor(failure, dtype=torch.int64, device=device).clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
+    return s, f
+
+
 def normalise(raw, count, trait_prob):
     """LODscores::get (lod_score.h:86-88)"""
     return (raw - math.log(max(int(count), 1)) - trait_prob) / math.log(10.0)

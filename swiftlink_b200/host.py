@@ -11,7 +11,7 @@ SYMBOLS = [
     "slk_host_marker_name", "slk_host_genotypes", "slk_host_marker_trait_prob", "slk_host_map_table",
     "slk_host_disease_model", "slk_host_elim_masks", "slk_host_build_peel", "slk_host_set_peel",
     "slk_host_num_ops", "slk_host_peel_cost", "slk_host_op_info", "slk_host_random_descentgraph",
-    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain",
+    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_mc3", "slk_host_mc3_temperature",
 ]
 
 
@@ -153,6 +153,28 @@ class Host(object):
         if rc != 0:
             raise capi.SlkError(rc, self.L.slk_last_error().decode())
         return dict(lod=lod.reshape(self.M - 1, self.nlod), dg=dg, trait_prob=tp.value)
+
+
+    def run_mc3(self, n_chains, burnin, iterations, exchange_period=10, temperatures=None, scoring_period=10,
+                seed=1, chain_id=0, device=0, lsampler_prob=0.5, si_iterations=10):
+        """Mc3::run: a ladder of heated chains on one device; returns the cold chain's LOD table and the swap counts"""
+        lod = np.zeros((self.M - 1) * self.nlod)
+        ok = np.zeros(n_chains, np.int32); bad = np.zeros(n_chains, np.int32)
+        t = None if temperatures is None else np.ascontiguousarray(temperatures, np.float64)
+        rc = self.L.slk_host_run_mc3(self.h, int(device), C.c_uint64(seed), C.c_uint32(chain_id), int(n_chains),
+                                     int(exchange_period), _dp(t) if t is not None else None, int(burnin), int(iterations),
+                                     int(scoring_period), C.c_double(lsampler_prob), int(si_iterations), _dp(lod),
+                                     _ip(ok), _ip(bad))
+        if rc != 0:
+            raise capi.SlkError(rc, self.L.slk_last_error().decode())
+        return dict(lod=lod.reshape(self.M - 1, self.nlod), swap_success=ok[:n_chains - 1], swap_failure=bad[:n_chains - 1])
+
+
+def mc3_temperature(i, n_chains, temperatures=None):
+    L = capi.lib()
+    L.slk_host_mc3_temperature.restype = C.c_double
+    t = None if temperatures is None else np.ascontiguousarray(temperatures, np.float64)
+    return float(L.slk_host_mc3_temperature(int(i), int(n_chains), _dp(t) if t is not None else None))
 
 
 class PlanFromHost(capi.Plan):

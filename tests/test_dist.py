@@ -28,7 +28,8 @@ def _worker(rank, world, port, raws, counts, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     merged, count = sdist.merge_lod(torch.from_numpy(raws[rank].copy()), counts[rank])
-    out[rank] = (merged.numpy().copy(), count)
+    ok, bad = sdist.merge_swap_stats([3 + rank, 5], [1, 2 * rank])
+    out[rank] = (merged.numpy().copy(), count, ok.tolist(), bad.tolist())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,8 +47,9 @@ def test_merge_lod_two_ranks_gloo():
     mp.spawn(_worker, args=(2, _free_port(), raws, counts, out), nprocs=2, join=True)
     want = np.array([orcapi.log_sum(a, b) for a, b in zip(raws[0], raws[1])])   # logarithms.cc:14-23
     for r in (0, 1):
-        merged, count = out[r]
+        merged, count, ok, bad = out[r]
         assert count == 38
+        assert ok == [7, 10] and bad == [2, 2]          # MC3 swap counters summed over the two ladders
         assert merged[7] == big and merged[5] == raws[1][5]
         assert np.abs(merged - want).max() <= 1e-12 * np.abs(want[want > big]).max()
 
@@ -66,3 +68,12 @@ def test_chain_placement():
     assert sdist.chain_placement(8, 8) == [[i] for i in range(8)]
     assert sdist.chain_placement(8, 2) == [[0, 2, 4, 6], [1, 3, 5, 7]]
     assert sum(len(x) for x in sdist.chain_placement(10, 4)) == 10
+
+
+def test_mc3_ladder():
+    """mc3.cc:31-42: T_0 = 1, T_i = 1 / (1 + 0.001 * 2^i), or the user's temperatures"""
+    from swiftlink_b200 import host as H
+    assert H.mc3_temperature(0, 4) == 1.0
+    for i in range(1, 8):
+        assert H.mc3_temperature(i, 8) == 1.0 / (1.0 + 0.001 * 2.0 ** i)
+    assert H.mc3_temperature(2, 3, [1.0, 0.9, 0.5]) == 0.5

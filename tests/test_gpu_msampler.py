@@ -183,3 +183,38 @@ def test_illegal_graph_is_reported(gpu):
     assert e.value.code == -7
     ch.dg_upload(fx["dgs"][2])
     ch.sync()
+
+
+def test_dg_swap(gpu):
+    """slk_dg_swap exchanges two chains' graphs in O(1) and invalidates the carried likelihoods"""
+    fx = golden("east")
+    a, b = gpu("east", seed=1, chain_id=0), gpu("east", seed=1, chain_id=1)
+    a.dg_upload(fx["dgs"][1]); b.dg_upload(fx["dgs"][3])
+    la, lb = a.dg_likelihood(), b.dg_likelihood()
+    a.dg_swap(b)
+    assert (a.dg_download() == fx["dgs"][3]).all() and (b.dg_download() == fx["dgs"][1]).all()
+    assert a.dg_likelihood() == lb and b.dg_likelihood() == la
+    a.dg_swap(b)
+    assert (a.dg_download() == fx["dgs"][1]).all()
+
+
+@pytest.mark.parametrize("name", ["east", "xlinked"])
+def test_mc3_ladder_runs_and_scores(name, tmp_path):
+    """Mc3::run on the device (three heated chains, default sampler mix): swap bookkeeping and a cold-chain
+    LOD curve in the band of the reference's own default-mix replicates"""
+    from common import case_files, FORCE_X, ref_available
+    if not ref_available():
+        pytest.skip("example inputs live in oracle/_ref/examples")
+    from swiftlink_b200 import host as H
+    fx = golden(name)
+    h = H.Host(*case_files(name, tmp_path), sex_linked=bool(FORCE_X[name]))
+    assert h.set_peel([o["peelnode"] for o in problem(name)["ops"]])
+    out = h.run_mc3(3, burnin=300, iterations=900, exchange_period=10, seed=31, si_iterations=20)
+    tries = out["swap_success"] + out["swap_failure"]
+    assert tries.sum() == 120 and (tries > 0).all()
+    assert out["swap_success"].sum() > 0                      # temperatures 0.998 / 0.996: swaps are nearly free
+    lod = out["lod"]
+    assert np.isfinite(lod).all()
+    ref = fx["lod_curves_default_mix"].mean(axis=(1, 2))
+    assert abs(lod.mean() - ref.mean()) < 6.0 * ref.std(ddof=1) + 0.75
+    h.close()

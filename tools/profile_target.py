@@ -52,7 +52,18 @@ def main():
         print("M-sweep ms %.3f (%d meioses, %.2f us per step; host enqueue %.3f ms per sweep); ln L = %.3f" %
               (1e3 * (t4 - t3) / args.msweeps, n, 1e6 * (t4 - t3) / args.msweeps / n, 1e3 * (t_enq - t3) / args.msweeps,
                chain.dg_likelihood()))
-    if args.trace:
+    if args.msweeps and args.trace:
+        import numpy as np
+        order = plan.msampler_ordering()
+        tr = chain.debug_msampler_trace(int(order[0]), int(order[1]))
+        tr = chain.debug_msampler_trace(int(order[2]), int(order[3]))
+        d = np.diff(tr[:, :7], axis=1)
+        print("likelihood kernel cycles per phase [tables, genotypes, labels, keep, (sync), walk, finish] for sampled warps:")
+        for row in d:
+            if row.min() >= 0 and row.sum() > 0:
+                print("   ", row.tolist(), "total", int(row.sum()))
+        print("    start spread (cycles):", int(tr[:, 0][tr[:, 0] > 0].max() - tr[:, 0][tr[:, 0] > 0].min()))
+    if args.trace and args.sweeps:
         import numpy as np
         st = plan.stats()
         t = chain.debug_trace(99, 0)
