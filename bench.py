@@ -251,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
                 kinds[0] += 1
             else:
                 chain.msampler_sweep(start_it + k)
-                launches[0] += 1 + 2 * n_meioses
+                launches[0] += 1 + 2 * ((n_meioses + 1) // 2)
                 kinds[1] += 1
         chain.lodscore_accumulate()
         launches[0] += 1
@@ -347,7 +347,10 @@ def run_ours(args, rank, world, local_rank):
     def one_msweep():
         chain.msampler_sweep(mctr[0])
         mctr[0] += 1
-    msweep_ms = kernel_ms(one_msweep, 3)                           # 1 + 2 * n_meioses launches
+    msweep_ms = kernel_ms(one_msweep, 3)                           # 1 + 2 * ceil(n_meioses / 2) launches
+    order = plan.msampler_ordering()
+    ms_lik_ms = kernel_ms(lambda: chain.debug_msampler_launch(order[0], order[1], 0, 20), 1) / 20.0
+    ms_chain_ms = kernel_ms(lambda: chain.debug_msampler_launch(order[2], order[3], 1, 20), 1) / 20.0
     chain.sync()
     fp64_peak = capi.measure_fp64_peak(local_rank)
 
@@ -377,20 +380,33 @@ def run_ours(args, rank, world, local_rank):
     # algorithmic bytes (minimal encodings): per locus update read 2x2(N-F) bits of
     # neighbouring meioses + 2N bits of genotypes + 16 B theta, write 2(N-F) bits
     ls_bytes = loci_per_launch * ((4 * nf + 2 * N + 2 * nf) / 8.0 + 16)
+    # The dominant kernel of the default mix is the M-sampler's likelihood kernel: integer / byte work, one
+    # thread per (locus, hypothesis).  Algorithmic bytes per evaluation (minimal encodings): the graph row
+    # 2(N-F) bits, the typed people's genotypes 2 nt bits, two allele-frequency logs 16 B, ln L out 8 B.
+    n_typed = int(np.asarray(hst.person_table()["typed"]).sum())
+    ms_bytes_per_eval = (2 * nf + 2 * n_typed) / 8.0 + 24.0
+    ms_evals = 3 * M                                               # three hypotheses per locus per launch
+    ms_bytes = ms_bytes_per_eval * ms_evals
     roofline = {
-        "kernel": "slk_lsampler_kernel", "bound": "fp64", "achieved": ls_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": ls_tflops / fp64_peak if fp64_peak else None, "traffic": None,
-        "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
-        "algorithmic_flops_per_launch": ls_flops, "launch_ms": ls_ms, "units_per_launch": loci_per_launch,
-        "hbm": {"achieved": ls_bytes / (ls_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ls_bytes / (ls_ms * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": ls_bytes},
-        "lodscore_kernel": {"achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
+        "kernel": "slk_ms_likelihood_kernel", "bound": "hbm", "achieved": ms_bytes / (ms_lik_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+        "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": ms_lik_ms, "units_per_launch": ms_evals,
+        "note": "latency-bound integer walk (one dependent chain per thread, 939 warps resident): neither HBM nor a math "
+                "pipe is the limiter; see DESIGN.md section 4",
+        "ms_chain_kernel": {"launch_ms": ms_chain_ms, "steps_per_launch": 2},
+        "lsampler_kernel": {
+            "bound": "fp64", "achieved": ls_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": ls_tflops / fp64_peak if fp64_peak else None,
+            "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+            "algorithmic_flops_per_launch": ls_flops, "launch_ms": ls_ms, "units_per_launch": loci_per_launch,
+            "hbm": {"achieved": ls_bytes / (ls_ms * 1e-3) / 1e9, "frac": ls_bytes / (ls_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_launch": ls_bytes}},
+        "lodscore_kernel": {"bound": "fp64", "achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
                             "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops,
                             "trait_positions_per_s": (M - 1) * N_LOD / (lod_ms * 1e-3)},
         "msampler": {"sweep_ms": msweep_ms, "meioses_per_sweep": n_meioses, "us_per_meiosis_step": 1e3 * msweep_ms / max(n_meioses, 1),
-                     "locus_likelihoods_per_s": n_meioses * M / (msweep_ms * 1e-3)},
+                     "locus_likelihoods_per_s": 1.5 * n_meioses * M / (msweep_ms * 1e-3)},
     }
     n_l, n_m = timed_kinds
     t_l, t_m, t_s = n_l * 2 * ls_ms, n_m * msweep_ms, args.steps * lod_ms

@@ -243,6 +243,9 @@ int slk_debug_msampler_state(slk_chain* chain, double* fb, double* ln_cur);
    clock64() stamps of lane 0 of every 64th CTA: stamps[16][8] = start, tables built, genotypes staged,
    labels done, typed labels kept, graph walked, result written */
 int slk_debug_msampler_trace(slk_chain* chain, int meiosis0, int meiosis1, long long* stamps);
+/* measurement aid for bench.py: enqueue `reps` launches of one M-sampler kernel for the pair
+   (meiosis0, meiosis1): which = 0 the three-hypothesis likelihood kernel, 1 the two-step chain kernel */
+int slk_debug_msampler_launch(slk_chain* chain, int meiosis0, int meiosis1, int which, int reps);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward
    level, after every backward level, after the indicators.  Returns the number of stamps. */

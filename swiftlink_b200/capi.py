@@ -27,7 +27,7 @@ SYMBOLS = [
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood",
     "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
-    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace",
+    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace", "slk_debug_msampler_launch",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
     "slk_debug_philox", "slk_debug_uniform", "slk_measure_fp64_peak",
 ]
@@ -286,6 +286,9 @@ class Chain(object):
         buf = np.zeros((16, 8), np.int64)
         _check(self.L.slk_debug_msampler_trace(self.h, int(m0), int(m1), _ptr(buf, C.c_longlong)))
         return buf
+
+    def debug_msampler_launch(self, m0, m1, which, reps):
+        _check(self.L.slk_debug_msampler_launch(self.h, int(m0), int(m1), int(which), int(reps)))
 
     def debug_msampler_state(self):
         fb = np.zeros((self.plan.M, 2)); cur = np.zeros(self.plan.M)

@@ -795,6 +795,38 @@ int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long
     return rc;
 }
 
+int slk_debug_msampler_launch(slk_chain* c, int meiosis0, int meiosis1, int which, int reps) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const SlkDevPlan& d = c->plan->dev;
+    if(meiosis0 < 0 || meiosis1 < 0 || meiosis0 >= 2 * (d.N - d.F) || meiosis1 >= 2 * (d.N - d.F)) return fail(SLK_ERR_INVALID, "meiosis out of range");
+    if(!c->ms_cur_valid) {
+        rc = slk_msampler_reset(c);
+        if(rc != SLK_OK) return rc;
+    }
+    SlkMsLaunch L = ms_launch(c);
+    const int p0 = d.F + meiosis0 / 2, a0 = meiosis0 % 2, p1 = d.F + meiosis1 / 2, a1 = meiosis1 % 2;
+    L.nsets = 3; L.nsteps = 2;
+    L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
+    L.set_n[1] = 1; L.set_person[1][0] = p1; L.set_parent[1][0] = a1;
+    L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
+    L.step_person[0] = p0; L.step_parent[0] = a0; L.step_slot[0] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis0;
+    L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis1;
+    if(which == 0) {
+        for(int r = 0; r < reps; ++r) ms_launch_likelihood(c, L);
+    }
+    else {
+        ms_launch_likelihood(c, L);                    // the chain kernel needs this pair's likelihoods
+        for(int r = 0; r < reps; ++r) {
+            L.iteration = (uint64_t) r;
+            slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
+        }
+        c->ms_cur_valid = false;                       // repeated sampling of one pair: the graph is still legal, ln cur is stale
+    }
+    CU(cudaGetLastError());
+    return SLK_OK;
+}
+
 int slk_debug_msampler_state(slk_chain* c, double* fb, double* lncur) {
     int rc = ms_ready(c);
     if(rc != SLK_OK) return rc;
