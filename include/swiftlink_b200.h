@@ -240,8 +240,11 @@ int slk_debug_fag(slk_chain* chain, int meiosis, double* ln_lik, int32_t* edges)
    backward pass) and the carried per-locus ln likelihood [M] of the graph the step left */
 int slk_debug_msampler_state(slk_chain* chain, double* fb, double* ln_cur);
 /* tuning aid: one three-hypothesis likelihood launch for the pair (meiosis0, meiosis1) that records
-   clock64() stamps of lane 0 of every 64th CTA: stamps[16][8] = start, tables built, genotypes staged,
-   labels done, typed labels kept, graph walked, result written */
+   clock64() stamps of lane 0 of every 64th CTA: stamps[0..11][8] = start, tables built, genotypes staged,
+   labels done, typed labels kept, graph walked, result written (only the first 12 sampled CTAs are kept);
+   followed by the two-step chain kernel of the same pair: stamps[12..14] = CTA 0, stamps[15..17] = last CTA
+   (start, then per step: staged, chunk product, CTA scan, cluster sync, recurrence, map scans, applied, synced).
+   stamps must hold 160 values. */
 int slk_debug_msampler_trace(slk_chain* chain, int meiosis0, int meiosis1, long long* stamps);
 /* measurement aid for bench.py: enqueue `reps` launches of one M-sampler kernel for the pair
    (meiosis0, meiosis1): which = 0 the three-hypothesis likelihood kernel, 1 the two-step chain kernel */

@@ -283,7 +283,7 @@ class Chain(object):
         return lik, e
 
     def debug_msampler_trace(self, m0, m1):
-        buf = np.zeros((16, 8), np.int64)
+        buf = np.zeros((20, 8), np.int64)
         _check(self.L.slk_debug_msampler_trace(self.h, int(m0), int(m1), _ptr(buf, C.c_longlong)))
         return buf
 

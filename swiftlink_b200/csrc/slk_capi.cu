@@ -778,8 +778,8 @@ int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long
     if(rc != SLK_OK) return rc;
     const SlkDevPlan& d = c->plan->dev;
     long long* dev = 0;
-    CU(cudaMalloc((void**) &dev, sizeof(long long) * 128));
-    CU(cudaMemsetAsync(dev, 0, sizeof(long long) * 128, c->stream));
+    CU(cudaMalloc((void**) &dev, sizeof(long long) * 160));
+    CU(cudaMemsetAsync(dev, 0, sizeof(long long) * 160, c->stream));
     SlkMsLaunch L = ms_launch(c);
     L.trace = dev;
     L.nsets = 3;
@@ -787,9 +787,23 @@ int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long
     L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
     L.set_n[1] = 1; L.set_person[1][0] = p1; L.set_parent[1][0] = a1;
     L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
+    L.nsteps = 2;
+    L.step_person[0] = p0; L.step_parent[0] = a0; L.step_slot[0] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis0;
+    L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis1;
+    if(!c->ms_cur_valid) {
+        rc = slk_msampler_reset(c);
+        if(rc != SLK_OK) return rc;
+    }
     ms_launch_likelihood(c, L);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(stamps, dev, sizeof(long long) * 128, cudaMemcpyDeviceToHost, c->stream));
+    if(meiosis0 != meiosis1) {
+        // the chain kernel's stamps go to rows 12.. (CTA 0) and 15.. (last CTA) of the same buffer
+        SlkMsLaunch L2 = L;
+        L2.trace = dev + 96;
+        slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L2);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(stamps, dev, sizeof(long long) * 160, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_error(c);
     cudaFree(dev);
     return rc;

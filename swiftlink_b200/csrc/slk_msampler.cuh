@@ -83,7 +83,7 @@ struct SlkMsLaunch {
     uint64_t seed, iteration;
     uint32_t chain;
     int32_t* dump_edges;         // optional [M][2N] (set 0)
-    long long* trace;            // optional: clock64() stamps of lane 0 of every 64th CTA (tuning aid) [16][8]
+    long long* trace;            // optional: clock64() stamps (tuning aid), see slk_debug_msampler_trace
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
     const double* log_1mtheta;
@@ -177,7 +177,7 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     const int N = L.N, F = L.F, M = L.M, nt = L.ms.n_typed;
     const MsLayout lay = slk_ms_layout(N, F, nt);
     const uint32_t t = threadIdx.x;
-    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 16) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
+    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
     if(tr) tr[0] = clock64();
 
     // the phase A and phase C tables overlay each other ACROSS the lanes of the warp, so the phases are
@@ -545,7 +545,7 @@ __device__ __forceinline__ Mat2 mat2_mul_rescale(const Mat2& x, const Mat2& y) {
 __device__ __forceinline__ int ms_pick(double w0, double w1, double u) {
     if(w0 == 0.0) return 1;
     if(w1 == 0.0) return 0;
-    return (u < (w0 / (w0 + w1))) ? 0 : 1;
+    return (u * (w0 + w1) < w0) ? 0 : 1;           // u < w0 / (w0 + w1) without the division
 }
 
 __device__ __forceinline__ Mat2 mat2_shfl_up(const Mat2& v, int d) {
@@ -557,11 +557,11 @@ __device__ __forceinline__ Mat2 mat2_shfl_up(const Mat2& v, int d) {
 
 // One thread-block CLUSTER of SLK_MS_CLUSTER CTAs (the chromosome is cut into contiguous chunks, one
 // per thread of the cluster); the two scans cross CTAs through distributed shared memory.  Dynamic
-// shared memory of a CTA, per locus of its share: raw pair (16 B), ln cur (8 B), ln flipped (8 B), map
-// byte, changed-in-step-0 byte.
+// shared memory of a CTA, per locus of its share: raw pair (16 B), ln cur (8 B), ln flipped (8 B), theta of
+// the interval to its left (8 B), the step's uniform draw (8 B), map byte, changed-in-step-0 byte.
 #define SLK_MS_CLUSTER 8
-#define SLK_MS_CHAIN_THREADS 512
-#define SLK_MS_CHAIN_BYTES_PER_LOCUS 34
+#define SLK_MS_CHAIN_THREADS 640
+#define SLK_MS_CHAIN_BYTES_PER_LOCUS 50
 
 __global__ void __cluster_dims__(SLK_MS_CLUSTER, 1, 1) __launch_bounds__(SLK_MS_CHAIN_THREADS)
 slk_ms_chain_kernel(const SlkMsLaunch L) {
@@ -571,6 +571,9 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     __shared__ Mat2 s_cmat[SLK_MS_CLUSTER];        // the product of each CTA of the cluster
     __shared__ uint8_t s_wmap[32];
     __shared__ uint8_t s_cmap[SLK_MS_CLUSTER];
+    __shared__ double2 s_r0;                       // raw pair of locus 0 (published by CTA 0)
+    __shared__ Mat2 s_cpre;                        // product of the CTAs before this one
+    __shared__ uint32_t s_cpost;                   // composition of the CTAs after this one
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int) cluster.block_rank();
     const int M = L.M, N = L.N, T = blockDim.x, t = threadIdx.x;
@@ -582,13 +585,21 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     double2* s_raw = (double2*) ch_smem;                                    // [cap]
     double* s_lncur = (double*)(s_raw + cap);                               // [cap]
     double* s_lnflip = s_lncur + cap;                                       // [cap]
-    uint8_t* s_map = (uint8_t*)(s_lnflip + cap);                            // [cap]
+    double* s_theta = s_lnflip + cap;                                       // [cap] theta[i - 1]
+    double* s_u = s_theta + cap;                                            // [cap]
+    uint8_t* s_map = (uint8_t*)(s_u + cap);                                 // [cap]
     uint8_t* s_changed = s_map + cap;                                       // [cap]
 
     auto apply = [](uint32_t f, uint32_t x) -> uint32_t { return (f >> x) & 1u; };
     auto compose = [&](uint32_t f, uint32_t g) -> uint32_t { return apply(f, apply(g, 0)) | (apply(f, apply(g, 1)) << 1); };
 
-    for(int i = cta_lo + t; i < cta_hi; i += T) { s_lncur[i - cta_lo] = L.lncur[i]; s_changed[i - cta_lo] = 0; }
+    long long* tr = (L.trace && t == 0 && (rank == 0 || rank == SLK_MS_CLUSTER - 1)) ? L.trace + (rank ? 24 : 0) : 0;
+    if(tr) tr[0] = clock64();
+    for(int i = cta_lo + t; i < cta_hi; i += T) {
+        s_lncur[i - cta_lo] = L.lncur[i]; s_changed[i - cta_lo] = 0;
+        s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
+    }
+    const double theta_hi = cta_hi < M && cta_hi > 0 ? L.theta[cta_hi - 1] : 0.5;   // interval right of the CTA's last locus
 
     for(int step = 0; step < L.nsteps; ++step) {
         const uint8_t* bits = L.bits + (size_t) step * M;
@@ -601,20 +612,23 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             const double lc = s_lncur[k];
             const double r = exp(lf - lc);                 // -inf -> 0
             s_lnflip[k] = lf;
+            s_u[k] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) i, L.step_slot[step]);
             s_raw[k] = (bits[i] & 1u) ? make_double2(r, 1.0) : make_double2(1.0, r);
             if(!(lc > -DBL_MAX) && atomicCAS(&L.err[0], 0, SLK_ERR_ILLEGAL_GRAPH) == 0) L.err[1] = i;
         }
         __syncthreads();
+        if(tr) tr[1 + 8 * step] = clock64();
 
         // ---- forward: product of the chunk's matrices A_i = diag(raw_i) * [[1-th, th], [th, 1-th]] ----
         Mat2 acc; acc.a = 1.0; acc.b = 0.0; acc.c = 0.0; acc.d = 1.0;
         for(int i = lo; i < hi; ++i) {
             if(i == 0) continue;                       // locus 0 enters as the start vector
             const double2 r = s_raw[i - cta_lo];
-            const double th = __ldg(L.theta + i - 1), ith = 1.0 - th;
+            const double th = s_theta[i - cta_lo], ith = 1.0 - th;
             Mat2 A; A.a = r.x * ith; A.b = r.x * th; A.c = r.y * th; A.d = r.y * ith;
             acc = mat2_mul_rescale(A, acc);
         }
+        if(tr) tr[2 + 8 * step] = clock64();
         // inclusive scan over the threads of the CTA, later chunks multiply from the left
         for(int d = 1; d < 32; d <<= 1) {
             const Mat2 o = mat2_shfl_up(acc, d);
@@ -635,15 +649,25 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
         if(t < SLK_MS_CLUSTER) {
             Mat2* remote = cluster.map_shared_rank(s_cmat, t);
             remote[rank] = s_wmat[nwarps - 1];
+            if(rank == 0) *cluster.map_shared_rank(&s_r0, t) = s_raw[0];       // locus 0's pair, to every CTA
         }
+        if(tr) tr[3 + 8 * step] = clock64();
         cluster.sync();
+        if(tr) tr[4 + 8 * step] = clock64();
+        if(t == 0) {
+            // product of the CTAs before this one, once per CTA
+            Mat2 q; q.a = 1.0; q.b = 0.0; q.c = 0.0; q.d = 1.0;
+            for(int c = 0; c < rank; ++c) q = mat2_mul_rescale(s_cmat[c], q);
+            s_cpre = q;
+        }
+        __syncthreads();
 
         // meiosis_sampler.cc:155-187 for one locus, both possible values of the next locus's indicator:
         // bit 0 = image of 0, bit 1 = image of 1
         auto map_code = [&](int i, double f0, double f1) -> uint32_t {
-            const double u = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) i, L.step_slot[step]);
+            const double u = s_u[i - cta_lo];
             if(i == M - 1) { const int x = ms_pick(f0, f1, u); return (uint32_t)(x | (x << 1)); }
-            const double th = __ldg(L.theta + i), ith = 1.0 - th;
+            const double th = (i + 1 < cta_hi) ? s_theta[i + 1 - cta_lo] : theta_hi, ith = 1.0 - th;
             const int x0 = ms_pick(f0 * ith, f1 * th, u);     // next = 0: j != next ? theta : 1 - theta
             const int x1 = ms_pick(f0 * th, f1 * ith, u);     // next = 1
             return (uint32_t)(x0 | (x1 << 1));
@@ -655,7 +679,7 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             Mat2 q = mat2_shfl_up(acc, 1);
             if(lane == 0) { q.a = 1.0; q.b = 0.0; q.c = 0.0; q.d = 1.0; }
             if(warp > 0) q = mat2_mul_rescale(q, s_wmat[warp - 1]);
-            for(int c = rank - 1; c >= 0; --c) q = mat2_mul_rescale(q, s_cmat[c]);
+            if(rank > 0) q = mat2_mul_rescale(q, s_cpre);
             if(lo < hi) {
                 double2 r = lo == 0 ? s_raw[0] : make_double2(0.0, 0.0);
                 double v0, v1;
@@ -668,7 +692,7 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
                     i = 1;
                 }
                 else {
-                    const double2 r0 = *cluster.map_shared_rank(s_raw, 0);      // locus 0, from CTA 0
+                    const double2 r0 = s_r0;
                     const double tot0 = r0.x + r0.y;
                     const double u0 = r0.x / tot0, u1 = r0.y / tot0;
                     const double w0 = q.a * u0 + q.b * u1, w1 = q.c * u0 + q.d * u1, tot = w0 + w1;
@@ -676,11 +700,11 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
                 }
                 for(; i < hi; ++i) {                       // the reference's recurrence (:140-153), same operation order
                     r = s_raw[i - cta_lo];
-                    const double th = __ldg(L.theta + i - 1), ith = 1.0 - th;
+                    const double th = s_theta[i - cta_lo], ith = 1.0 - th;
                     double f0 = r.x * ((v1 * th) + (v0 * ith));
                     double f1 = r.y * ((v0 * th) + (v1 * ith));
-                    const double tot = f0 + f1;
-                    f0 /= tot; f1 /= tot;
+                    const double inv = 1.0 / (f0 + f1);
+                    f0 *= inv; f1 *= inv;
                     if(step == 0) { L.fb[2 * i] = f0; L.fb[2 * i + 1] = f1; }
                     s_map[i - cta_lo] = (uint8_t) map_code(i, f0, f1);
                     v0 = f0; v1 = f1;
@@ -689,6 +713,7 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             }
         }
 
+        if(tr) tr[5 + 8 * step] = clock64();
         // ---- backward: inclusive suffix scan of the maps, S_t = G_t o G_{t+1} o ... -----------------------
         for(int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_down_sync(0xffffffffu, gmap, d);
@@ -710,13 +735,20 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             remote[rank] = s_wmap[0];                      // the whole CTA's composition
         }
         cluster.sync();
+        if(tr) tr[6 + 8 * step] = clock64();
+        if(t == 0) {
+            uint32_t in = 2u;
+            for(int c = SLK_MS_CLUSTER - 1; c > rank; --c) in = compose(s_cmap[c], in);
+            s_cpost = in;
+        }
+        __syncthreads();
         {
             // the map from "right of everything" to the value entering this chunk from the right; the last
             // locus's map is constant, so the composition is too and may be evaluated at 0
             uint32_t in = __shfl_down_sync(0xffffffffu, gmap, 1);
             if(lane == 31) in = 2u;
             if(warp + 1 < nwarps) in = compose(in, s_wmap[warp + 1]);
-            for(int c = rank + 1; c < SLK_MS_CLUSTER; ++c) in = compose(in, s_cmap[c]);
+            in = compose(in, s_cpost);
             if(lo < hi) {
                 uint32_t x = apply(in, 0);
                 const uint32_t pbit = 1u << L.step_parent[step];
@@ -733,7 +765,9 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
                 }
             }
         }
+        if(tr) tr[7 + 8 * step] = clock64();
         cluster.sync();                                    // shared tables are reused by the next step
+        if(tr) tr[8 + 8 * step] = clock64();
     }
     for(int i = cta_lo + t; i < cta_hi; i += T) L.lncur[i] = s_lncur[i - cta_lo];
 }

@@ -57,12 +57,16 @@ def main():
         order = plan.msampler_ordering()
         tr = chain.debug_msampler_trace(int(order[0]), int(order[1]))
         tr = chain.debug_msampler_trace(int(order[2]), int(order[3]))
-        d = np.diff(tr[:, :7], axis=1)
+        d = np.diff(tr[:12, :7], axis=1)
+        for nm, base in (("CTA 0", 96), ("last CTA", 120)):
+            st = tr.ravel()[base:base + 17]
+            print("chain kernel %s cycles [stage, product, cta scan, cluster sync, recurrence, map scans, apply, sync] x 2 steps: %s  total %d" %
+                  (nm, np.diff(st).tolist(), int(st[-1] - st[0])))
         print("likelihood kernel cycles per phase [tables, genotypes, labels, keep, (sync), walk, finish] for sampled warps:")
         for row in d:
             if row.min() >= 0 and row.sum() > 0:
                 print("   ", row.tolist(), "total", int(row.sum()))
-        print("    start spread (cycles):", int(tr[:, 0][tr[:, 0] > 0].max() - tr[:, 0][tr[:, 0] > 0].min()))
+
     if args.trace and args.sweeps:
         import numpy as np
         st = plan.stats()
