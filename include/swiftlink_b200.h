@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SLK_ABI_VERSION 2
+#define SLK_ABI_VERSION 3
 
 typedef enum {
     SLK_OK = 0,
@@ -99,6 +99,9 @@ typedef struct {
     const double* minor_freq;                  /* [M] Snp::minor() (genetic_map.h:42); only the M-sampler and the
                                                   descent-graph likelihood read it -- NULL makes those entry
                                                   points fail with SLK_ERR_UNSUPPORTED (ABI 1 callers) */
+    int32_t disease_prior_locus_plus1;         /* 0 = none.  l + 1: at marker l every person's genotype prior is their
+                                                  disease_prob (Person::copy_disease_probs, person.h:204-208) -- the
+                                                  simulated trait locus of the ELOD calculation (elod.h:83) */
 } slk_problem;
 
 typedef struct slk_plan slk_plan;              /* device-resident flattened peel plan (shared, read-only) */
@@ -216,6 +219,23 @@ int slk_lodscore_read(slk_chain* chain, double* raw, int32_t* count);
 int slk_lodscore_normalise(slk_chain* chain, double trait_prob, double* out);
 /* ln P(trait) without marker data: Peeler::calc_trait_prob (peeler.cc:65-73) */
 int slk_trait_likelihood(slk_plan* plan, double* log_prob);
+
+/* ---- ELOD: replaces the replicate loop of Elod::run (elod.cc:55-66) ------------------------------- */
+
+/* `replicates` independent simulations on one device: LocusSampler::start_from(dg1, 1) on the
+   sampler plan (three loci: marker, simulated trait locus, marker; all genotypes untyped), the two
+   marker rows copied into a two-locus graph (DescentGraph::copy_locus, elod.cc:58-59) and
+   Peeler::process on the trait plan (two loci, n_lod = 1), log-summed.  Both plans must describe the
+   same pedigree on the same device.  Replicate r draws from the Philox stream (seed, chain, iteration =
+   0, locus = 3 r + j).  log_sum receives the LODscores accumulator (natural log, LOG_ZERO if empty),
+   count the number of replicates added; LOD = (log_sum - ln count - ln P(T)) / ln 10 (lod_score.h:86-88).
+   prob_out (optional, [replicates]) receives every replicate's ln-probability for parity tests. */
+int slk_elod_run(slk_plan* sampler_plan, slk_plan* trait_plan, uint64_t seed, uint32_t chain_id,
+                 int64_t replicates, double* log_sum, int64_t* count, double* prob_out);
+/* the three-locus graphs of replicates [first, first + n) as the run above samples them:
+   dg int32[n][3][N][2] (parity tests) */
+int slk_debug_elod_graphs(slk_plan* sampler_plan, uint64_t seed, uint32_t chain_id, int64_t first, int32_t n,
+                          int32_t* dg);
 
 /* ---- parity hooks (used by tests/; not needed by a caller) ------------------------------- */
 

@@ -71,6 +71,11 @@ int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, 
                      const double* temperatures, int burnin, int iterations, int scoring_period, double lsampler_prob,
                      int si_iterations, double* lod_out, int32_t* swap_success, int32_t* swap_failure);
 double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures);
+/* Elod(pedfile, options).run() (elod.h:33-107, elod.cc:19-85): expected LOD of every pedigree of the file by
+   simulation on the device; per_pedigree[cap] receives the individual values, the total is returned */
+double slk_host_elod(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
+                     int sex_linked, int affected_only, int peel_iterations, uint64_t seed, int device,
+                     double* per_pedigree, int cap);
 
 #ifdef __cplusplus
 }

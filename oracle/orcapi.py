@@ -49,7 +49,7 @@ def lib():
         for name in ("orc_ls_forward", "orc_ls_step", "orc_homo_p0", "orc_si_start_from", "orc_trait_prob",
                      "orc_recombination_prob", "orc_marker_transmission", "orc_log_sum",
                      "orc_lod_normalise", "orc_uniform_draw", "orc_fag_likelihood", "orc_dg_sum_prior_prob",
-                     "orc_dg_likelihood"):
+                     "orc_dg_likelihood", "orc_elod_replicate"):
             getattr(L, name).restype = C.c_double
         L.orc_matrix_doubles.restype = C.c_long
         L.orc_presum_doubles.restype = C.c_long
@@ -242,6 +242,13 @@ class MSampler(object):
         e = np.zeros((M, 2 * N), np.int32) if edges else None
         self.L.orc_ms_state(self.h, _dp(raw), _dp(fwd), _dp(fb), _ip(e) if edges else None)
         return dict(raw=raw, fwd=fwd, fb=fb, edges=e)
+
+
+def elod_replicate(p1, p2, replicate, seed, chain):
+    """(sampled three-locus graph int32 [3,N,2], ln-prob) of one ELOD replicate"""
+    dg = np.zeros((3, p1.N, 2), np.int32)
+    v = lib().orc_elod_replicate(p1.p, p2.p, C.c_long(int(replicate)), C.c_uint64(seed), C.c_uint32(chain), _ip(dg))
+    return dg, float(v)
 
 
 def marker_prob(isfounder, typed, genotype, xmale, mapprob):

@@ -50,6 +50,10 @@ int orc_is_legal(const orc_problem* p, int person, int locus, int value) {
     return (p->elim[(long) locus * p->N + person] & mask_from_trait(value)) != 0;
 }
 
+/* added to the locus in every Philox key: ELOD replicate r draws as if its three loci were rows
+   3r .. 3r+2 of one long graph (orc_elod_replicate) */
+static long g_locus_key_offset = 0;
+
 static int dg_get(const orc_problem* p, const int* dg, int person, int locus, int parent) {
     return dg[((long) locus * p->N + person) * 2 + parent];      /* descent_graph.h:35-37 */
 }
@@ -414,7 +418,7 @@ double orc_ls_step(const orc_problem* p, int* dg, int locus, int ignore_left, in
         if(dist4_out) memcpy(dist4_out + 4 * i, d, sizeof(d));
         total = d[0] + d[1] + d[2] + d[3];
         if(total != 0.0) for(int g = 0; g < 4; ++g) d[g] /= total;
-        r = orc_uniform(seed, chain, iteration, (uint32_t) locus, (uint32_t) i);
+        r = orc_uniform(seed, chain, iteration, (uint32_t)(locus + g_locus_key_offset), (uint32_t) i);
         for(int g = 0; g < 4; ++g) {
             cum += d[g];
             if(r < cum) { chosen = g; break; }
@@ -433,7 +437,7 @@ double orc_ls_step(const orc_problem* p, int* dg, int locus, int ignore_left, in
         if(mt == ORC_UA || mt == ORC_AU) mi = hetero_mi(ma, mt);
         else {
             double p0 = homo_p0(c, i, MATERNAL);
-            mi = (orc_uniform(seed, chain, iteration, (uint32_t) locus, (uint32_t)(p->nops + 2 * i + MATERNAL)) < p0) ? 0 : 1;
+            mi = (orc_uniform(seed, chain, iteration, (uint32_t)(locus + g_locus_key_offset), (uint32_t)(p->nops + 2 * i + MATERNAL)) < p0) ? 0 : 1;
         }
         dg[((long) locus * p->N + i) * 2 + MATERNAL] = mi;
 
@@ -448,7 +452,7 @@ double orc_ls_step(const orc_problem* p, int* dg, int locus, int ignore_left, in
             if(pt == ORC_UA || pt == ORC_AU) pi = hetero_mi(pa, pt);
             else {
                 double p0 = homo_p0(c, i, PATERNAL);
-                pi = (orc_uniform(seed, chain, iteration, (uint32_t) locus, (uint32_t)(p->nops + 2 * i + PATERNAL)) < p0) ? 0 : 1;
+                pi = (orc_uniform(seed, chain, iteration, (uint32_t)(locus + g_locus_key_offset), (uint32_t)(p->nops + 2 * i + PATERNAL)) < p0) ? 0 : 1;
             }
             dg[((long) locus * p->N + i) * 2 + PATERNAL] = pi;
         }
@@ -488,6 +492,25 @@ double orc_si_start_from(const orc_problem* p, int* dg, int start_locus, uint64_
         weight += log(res);
     }
     return weight;
+}
+
+/* One ELOD replicate (elod.cc:55-61): LocusSampler::start_from(dg1, 1) on the three-locus problem,
+   DescentGraph::copy_locus of loci 0 and 2 into a two-locus graph, Peeler::process on the two-locus
+   problem.  dg3 int[3][N][2] receives the sampled graph; returns ln-prob (LOG_ZERO if the peel is <= 0). */
+double orc_elod_replicate(const orc_problem* p1, const orc_problem* p2, long replicate, uint64_t seed, uint32_t chain, int* dg3) {
+    const int N = p1->N;
+    int* dg2 = (int*) calloc((size_t) 2 * N * 2, sizeof(int));
+    double result[1], prob[1], w;
+    memset(dg3, 0, sizeof(int) * 3 * N * 2);
+    g_locus_key_offset = 3 * replicate;
+    w = orc_si_start_from(p1, dg3, 1, seed, chain, 0);
+    g_locus_key_offset = 0;
+    (void) w;
+    memcpy(dg2, dg3, sizeof(int) * 2 * N);
+    memcpy(dg2 + 2 * N, dg3 + 4 * N, sizeof(int) * 2 * N);
+    orc_lod_interval(p2, dg2, 0, result, prob, -1, 0);
+    free(dg2);
+    return result[0] > 0.0 ? prob[0] : LOG_ZERO;
 }
 
 /* ---- trait R-function -------------------------------------------------------------- */

@@ -111,6 +111,10 @@ double orc_lod_normalise(double score, int count, double trait_prob);
 /* one scoring pass over all intervals (markov_chain.cc:375-383) accumulated into scores[(M-1)*nlod] */
 void orc_lod_pass(const orc_problem* p, const int* dg, double* scores, int first);
 
+/* one ELOD replicate (elod.cc:55-61) on a three-locus sampler problem and a two-locus trait problem;
+   Philox keyed as if the replicate's loci were rows 3r..3r+2 of one long graph */
+double orc_elod_replicate(const orc_problem* p1, const orc_problem* p2, long replicate, uint64_t seed, uint32_t chain, int* dg3);
+
 /* ---- M-sampler and descent-graph likelihood (msampler_oracle.c) ------------------------- */
 
 typedef struct orc_msampler orc_msampler;

@@ -71,6 +71,7 @@
 #include "markov_chain.h"
 #include "sequential_imputation.h"
 #include "meiosis_sampler.h"
+#include "elod.h"
 #include "random.h"
 #include "omp_facade.h"
 #undef private
@@ -572,6 +573,29 @@ double ref_bench_msweeps(void* h, int reps) {
         for(unsigned j = 0; j < order.size(); ++j) ms.step(*c->dg, order[j]);
     }
     return omp_get_wtime() - t0;
+}
+
+/* ---- ELOD ------------------------------------------------------------------------------ */
+
+/* Elod(pedfile, options).run() (elod.h:33-107, elod.cc:19-85) with the reference's own generator
+   (seeded from /dev/urandom by the constructor, then re-seeded here for reproducibility) */
+double ref_elod(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
+                int sex_linked, unsigned int seed) {
+    Quiet q(quiet_mode());
+    struct mcmc_options o;
+    o.elod = true;
+    o.elod_frequency = frequency;
+    o.elod_penetrance = std::vector<double>(penetrance, penetrance + 3);
+    o.elod_marker_separation = separation;
+    o.elod_replicates = replicates;
+    o.sex_linked = sex_linked != 0;
+    o.peelopt_iterations = 20000;
+    Elod e(pedfile, o);
+    rng_ready = true;
+    rng_threads = get_max_threads();
+    for(int i = 0; i < rng_threads; ++i) gsl_rng_set(r[i], seed + 7919u * (unsigned) i);
+    srand(seed);
+    return e.run();
 }
 
 /* ---- LOD scoring ----------------------------------------------------------------- */

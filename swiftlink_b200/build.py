@@ -36,8 +36,8 @@ def needs_build():
     if not os.path.exists(LIB) or not os.path.exists(SWIFT):
         return True
     src, hdr = sources()
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in src + hdr)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(SWIFT))
+    return any(os.path.getmtime(f) > t for f in src + hdr + [os.path.join(CSRC, "host", "swift_main.cc")])
 
 
 def build(force=False, verbose=False):

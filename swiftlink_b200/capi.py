@@ -25,7 +25,7 @@ SYMBOLS = [
     "slk_dg_upload", "slk_dg_download", "slk_dg_swap",
     "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
-    "slk_trait_likelihood",
+    "slk_trait_likelihood", "slk_elod_run", "slk_debug_elod_graphs",
     "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
     "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace", "slk_debug_msampler_launch",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
@@ -51,7 +51,7 @@ class Problem(C.Structure):
                 ("theta", C.POINTER(C.c_double)), ("partial_theta", C.POINTER(C.c_double)),
                 ("elimination", C.POINTER(C.c_uint8)),
                 ("n_ops", C.c_int32), ("ops", C.POINTER(PeelOp)),
-                ("minor_freq", C.POINTER(C.c_double))]
+                ("minor_freq", C.POINTER(C.c_double)), ("disease_prior_locus_plus1", C.c_int32)]
 
 
 class SlkError(RuntimeError):
@@ -129,7 +129,8 @@ def make_problem(d):
                 _ptr(keep["mapprob"], C.c_double), _ptr(keep["mapxprob"], C.c_double),
                 _ptr(keep["theta"], C.c_double), _ptr(keep["partial"], C.c_double),
                 _ptr(keep["elim"], C.c_uint8), len(ops), arr,
-                _ptr(keep["minor"], C.c_double) if keep["minor"] is not None else None)
+                _ptr(keep["minor"], C.c_double) if keep["minor"] is not None else None,
+                int(d.get("disease_prior_locus", -1)) + 1)
     return p, keep
 
 
@@ -322,6 +323,22 @@ class Chain(object):
         _check(self.L.slk_debug_lod_interval(self.h, int(interval), _ptr(res, C.c_double), _ptr(prob, C.c_double),
                                              int(dump_k), _ptr(mat, C.c_double) if mat is not None else None))
         return res, prob, mat
+
+
+def elod_run(sampler_plan, trait_plan, replicates, seed=1, chain_id=0, want_probs=False):
+    """Elod::run's replicate loop on the device: returns (log-sum accumulator, count, per-replicate ln-probs or None)"""
+    ls = C.c_double(0); cnt = C.c_int64(0)
+    probs = np.zeros(int(replicates)) if want_probs else None
+    _check(lib().slk_elod_run(sampler_plan.h, trait_plan.h, C.c_uint64(seed), C.c_uint32(chain_id), C.c_int64(int(replicates)),
+                              C.byref(ls), C.byref(cnt), _ptr(probs, C.c_double) if want_probs else None))
+    return ls.value, cnt.value, probs
+
+
+def debug_elod_graphs(sampler_plan, first, n, seed=1, chain_id=0):
+    dg = np.zeros((int(n), 3, sampler_plan.N, 2), np.int32)
+    _check(lib().slk_debug_elod_graphs(sampler_plan.h, C.c_uint64(seed), C.c_uint32(chain_id), C.c_int64(int(first)), int(n),
+                                       _ptr(dg, C.c_int32)))
+    return dg
 
 
 def debug_philox(ctr, key, device=0):

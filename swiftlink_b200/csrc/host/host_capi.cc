@@ -211,6 +211,20 @@ int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, 
     return SLK_OK;
 }
 
+double slk_host_elod(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
+                     int sex_linked, int affected_only, int peel_iterations, uint64_t seed, int device,
+                     double* per_pedigree, int cap) {
+    struct mcmc_options o;
+    o.elod = true; o.elod_frequency = frequency; o.elod_marker_separation = separation; o.elod_replicates = replicates;
+    for(int i = 0; i < 3; ++i) o.elod_penetrance[i] = penetrance[i];
+    o.sex_linked = sex_linked != 0; o.affected_only = affected_only != 0; o.peelopt_iterations = peel_iterations;
+    o.seed = seed; o.device = device;
+    Elod e(pedfile, o);
+    const double total = e.run();
+    for(int i = 0; i < (int) e.per_pedigree().size() && i < cap; ++i) per_pedigree[i] = e.per_pedigree()[i];
+    return total;
+}
+
 double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures) {
     struct mcmc_options o;
     o.mc3 = true; o.mc3_number_of_chains = n_chains;

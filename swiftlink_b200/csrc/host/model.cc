@@ -18,8 +18,11 @@ mcmc_options::mcmc_options() :
     verbose(false), burnin(50000), iterations(50000), si_iterations(1000), scoring_period(10), mcmc_runs(1),
     coda_logging(false), coda_prefix("trace"), lodscores(5), peelopt_iterations(1000000), lsampler_prob(0.5),
     thread_count(1), use_gpu(true), random_filename(""), affected_only(false), sex_linked(false),
-    seed(20261017), device(0), mc3(false), mc3_number_of_chains(1), mc3_exchange_period(10),
-    mc3_temperatures(), exchange_filename("") {}                   // defaults.h:4-24
+    seed(20261017), device(0), elod(false), elod_frequency(0.0001), elod_marker_separation(0.05), elod_replicates(1000000),
+    mc3(false), mc3_number_of_chains(1), mc3_exchange_period(10),
+    mc3_temperatures(), exchange_filename("") {                    // defaults.h:4-24
+    elod_penetrance[0] = 0.0; elod_penetrance[1] = 0.0; elod_penetrance[2] = 1.0;
+}
 
 // ---- disease model -----------------------------------------------------------------------
 
@@ -609,7 +612,7 @@ bool parse_linkage_file(const std::string& filename, GeneticMap& map, DiseaseMod
 
 // pedigree_parser.cc:15-185
 bool parse_pedigree_file(const std::string& filename, std::vector<Pedigree>& pedigrees, const DiseaseModel& dm,
-                         const GeneticMap& map) {
+                         const GeneticMap& map, bool ignore_genotypes) {
     LineReader r(filename);
     if(!r.ok()) { fprintf(stderr, "error: file not found: %s\n", filename.c_str()); return false; }
     std::string line;
@@ -648,7 +651,7 @@ bool parse_pedigree_file(const std::string& filename, std::vector<Pedigree>& ped
 
         Person p(tokens[1], tokens[2], tokens[3], s, a, dm);
         bool bad = false;
-        for(size_t i = 6; i + 1 < tokens.size(); i += 2) {
+        for(size_t i = 6; !ignore_genotypes && i + 1 < tokens.size(); i += 2) {      // pedigree_parser.cc:143
             const std::string& a1 = tokens[i];
             const std::string& a2 = tokens[i + 1];
             enum unphased_genotype g;

@@ -532,9 +532,10 @@ bool write_linkage_results(GeneticMap* map, const std::string& filename, std::ve
 
 // ---- flat problem -----------------------------------------------------------------------------------------------
 
-void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg, bool sex_linked, FlatProblem& out) {
+void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg, bool sex_linked, FlatProblem& out,
+                     bool real_founder_priors, int disease_prior_locus) {
     const int N = (int) ped.num_members(), M = (int) map.num_markers();
-    out.mother.resize(N); out.father.resize(N); out.sex.resize(N); out.typed.resize(N);
+    out.mother.resize(N); out.father.resize(N); out.sex.resize(N); out.typed.resize(N); out.prior_as_founder.resize(N);
     out.genotypes.resize((size_t) N * M);
     out.disease_prob.resize((size_t) N * 4);
     for(int i = 0; i < N; ++i) {
@@ -543,6 +544,7 @@ void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg,
         out.father[i] = p->isfounder() ? -1 : (int) p->get_paternalid();
         out.sex[i] = (int) p->get_sex();
         out.typed[i] = p->istyped() ? 1 : 0;
+        out.prior_as_founder[i] = p->isfounder() ? 1 : 0;
         for(int l = 0; l < M; ++l) out.genotypes[(size_t) i * M + l] = (uint8_t) p->get_marker(l);
         for(int g = 0; g < 4; ++g) out.disease_prob[(size_t) i * 4 + g] = p->get_disease_prob((enum phased_trait) g);
     }
@@ -587,7 +589,8 @@ void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg,
     d.n_members = N; d.n_founders = (int) ped.num_founders(); d.n_markers = M; d.n_lod = (int) map.get_lodscore_count();
     d.sex_linked = sex_linked ? 1 : 0;
     d.mother = out.mother.data(); d.father = out.father.data(); d.sex = out.sex.data(); d.typed = out.typed.data();
-    d.prior_as_founder = 0;            // reference behaviour, see include/swiftlink_b200.h
+    d.prior_as_founder = real_founder_priors ? out.prior_as_founder.data() : 0;     // NULL: reference behaviour, see include/swiftlink_b200.h
+    d.disease_prior_locus_plus1 = disease_prior_locus + 1;
     d.genotypes = out.genotypes.data(); d.disease_prob = out.disease_prob.data();
     d.marker_prob = out.marker_prob.data(); d.marker_xprob = out.marker_xprob.data();
     d.theta = out.theta.data(); d.partial_theta = out.partial_theta.data();

@@ -2,7 +2,7 @@
 // messages and output file as the reference's main.cc:185-557 / linkage_program.cc:26-171 for
 // the linkage mode; every chain runs on the GPU (-g is implied, -X is allowed with it, which the
 // reference refuses at main.cc:534-537): L-sampler and M-sampler sweeps, LOD scoring, the CODA trace.
-// Not supported by this build, and refused explicitly: --elod.
+// --elod runs the expected-LOD simulation on the device too (main.cc:570-577).
 #include <getopt.h>
 
 #include <cmath>
@@ -20,6 +20,7 @@ static void usage(const char* prog) {
     struct mcmc_options d;
     fprintf(stderr,
 "Usage: %s [OPTIONS] -p pedfile -m mapfile -d datfile\n"
+"       %s [OPTIONS] -p pedfile --elod\n"
 "\n"
 "Input files:\n"
 "  -p pedfile, --pedigree=pedfile\n"
@@ -37,6 +38,13 @@ static void usage(const char* prog) {
 "  -l FLOAT,   --lsamplerprobability=FLOAT (default = %.1f)\n"
 "  -n NUM,     --lodscores=NUM             (default = %d)\n"
 "  -R NUM,     --runs=NUM                  (default = %d)\n"
+"\n"
+"ELOD options:\n"
+"  -e          --elod\n"
+"  -f FLOAT    --frequency=FLOAT           (default = %.1e)\n"
+"  -w FLOAT    --separation=FLOAT          (default = %.4f)\n"
+"  -k FLOAT,FLOAT,FLOAT --penetrance=FLOAT,FLOAT,FLOAT(default = %.2f,%.2f,%.2f)\n"
+"  -u NUM      --replicates=NUM            (default = %d)\n"
 "\n"
 "Metropolis-coupled MCMC options (commented out in the reference's main.cc:70-75):\n"
 "  -M,         --mcmcmc\n"
@@ -60,7 +68,8 @@ static void usage(const char* prog) {
 "  -v,         --verbose\n"
 "  -h,         --help\n"
 "\n",
-    prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
+    prog, prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
+    d.elod_frequency, d.elod_marker_separation, d.elod_penetrance[0], d.elod_penetrance[1], d.elod_penetrance[2], d.elod_replicates,
     d.mc3_number_of_chains, d.mc3_exchange_period, d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
 }
 
@@ -87,9 +96,11 @@ int main(int argc, char** argv) {
         {"runs", required_argument, 0, 'R'}, {"trace", no_argument, 0, 'T'}, {"device", required_argument, 0, 'D'},
         {"seed", required_argument, 0, 'S'}, {"traceprefix", required_argument, 0, 'P'}, {"mcmcmc", no_argument, 0, 'M'},
         {"chains", required_argument, 0, 'z'}, {"exchangeperiod", required_argument, 0, 'y'},
-        {"temperatures", required_argument, 0, 't'}, {"exchangefile", required_argument, 0, 'j'}, {0, 0, 0, 0}};
+        {"temperatures", required_argument, 0, 't'}, {"exchangefile", required_argument, 0, 'j'}, {"frequency", required_argument, 0, 'f'},
+        {"separation", required_argument, 0, 'w'}, {"penetrance", required_argument, 0, 'k'}, {"replicates", required_argument, 0, 'u'},
+        {0, 0, 0, 0}};
     int ch, tmp;
-    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:P:Mz:y:t:j:", longopts, 0)) != -1) {
+    while((ch = getopt_long(argc, argv, ":p:d:m:o:i:b:s:l:c:x:q:n:vhgeaXR:TD:S:P:Mz:y:t:j:f:w:k:u:", longopts, 0)) != -1) {
         switch(ch) {
             case 'p': pedfile = optarg; break;
             case 'm': mapfile = optarg; break;
@@ -100,7 +111,24 @@ int main(int argc, char** argv) {
             case 'a': o.affected_only = true; break;
             case 'X': o.sex_linked = true; break;
             case 'h': usage(argv[0]); return EXIT_SUCCESS;
-            case 'e': fprintf(stderr, "error: --elod is not part of this build\n"); return EXIT_FAILURE;
+            case 'e': o.elod = true; break;
+            case 'f': o.elod_frequency = atof(optarg);
+                      if(o.elod_frequency <= 0.0) { fprintf(stderr, "%s: ELOD trait frequency must be greater than zero ('%f' given)\n", argv[0], o.elod_frequency); return EXIT_FAILURE; }
+                      break;
+            case 'w': o.elod_marker_separation = atof(optarg);
+                      if(o.elod_marker_separation <= 0.0) { fprintf(stderr, "%s: ELOD marker separation must be greater than zero ('%f' given)\n", argv[0], o.elod_marker_separation); return EXIT_FAILURE; }
+                      break;
+            case 'k': {
+                double pen[3]; char extra;
+                if(sscanf(optarg, "%lf,%lf,%lf%c", &pen[0], &pen[1], &pen[2], &extra) != 3) {
+                    fprintf(stderr, "%s: penetrance requires 3 floats, e.g.: 0.0,0.0,1.0 ('%s' given)\n", argv[0], optarg); return EXIT_FAILURE;
+                }
+                for(int i = 0; i < 3; ++i) {
+                    if(pen[i] < 0.0 || pen[i] > 1.0) { fprintf(stderr, "%s: penetraces must be comma delimited floats from 0.0 - 1.0 inclusive, e.g.: 0.0,0.0,1.0 ('%s' given)\n", argv[0], optarg); return EXIT_FAILURE; }
+                    o.elod_penetrance[i] = pen[i];
+                }
+                break;
+            }
             case 'T': o.coda_logging = true; break;
             case 'P': o.coda_prefix = optarg; break;
             case 'M': o.mc3 = true; break;
@@ -127,17 +155,26 @@ int main(int argc, char** argv) {
                       if(o.lsampler_prob < 0.0 || o.lsampler_prob > 1.0) { fprintf(stderr, "%s: option '-l' requires a floating point argument between 0.0 and 1.0\n", argv[0]); return EXIT_FAILURE; }
                       break;
             case 'S': o.seed = strtoull(optarg, 0, 10); break;
-            case 'i': case 'b': case 's': case 'x': case 'q': case 'n': case 'R': case 'c': case 'D': case 'z': case 'y':
+            case 'i': case 'b': case 's': case 'x': case 'q': case 'n': case 'R': case 'c': case 'D': case 'z': case 'y': case 'u':
                 if(!str2int(tmp, optarg) || tmp < 0) { fprintf(stderr, "%s: option '-%c' requires a non-negative integer argument ('%s' given)\n", argv[0], ch, optarg); return EXIT_FAILURE; }
                 if(ch == 'i') o.iterations = tmp; else if(ch == 'b') o.burnin = tmp; else if(ch == 's') o.si_iterations = tmp;
                 else if(ch == 'x') o.scoring_period = tmp; else if(ch == 'q') o.peelopt_iterations = tmp;
                 else if(ch == 'n') o.lodscores = tmp; else if(ch == 'R') o.mcmc_runs = tmp; else if(ch == 'c') o.thread_count = tmp;
                 else if(ch == 'z') o.mc3_number_of_chains = tmp; else if(ch == 'y') o.mc3_exchange_period = tmp;
+                else if(ch == 'u') o.elod_replicates = tmp;
                 else o.device = tmp;
                 break;
             case ':': fprintf(stderr, "%s: option '-%c' requires an argument\n", argv[0], optopt); return EXIT_FAILURE;
             default:  fprintf(stderr, "%s: option '-%c' is invalid: ignored\n", argv[0], optopt); break;
         }
+    }
+    if(o.elod) {                                                      // main.cc:570-577, :609-610
+        if(pedfile.empty()) { fprintf(stderr, "%s: --elod needs a pedigree file\n", argv[0]); return EXIT_FAILURE; }
+        if(o.elod_replicates < 1) { fprintf(stderr, "%s: number of ELOD replicates must be greater than zero ('%d' given)\n", argv[0], o.elod_replicates); return EXIT_FAILURE; }
+        Elod e(pedfile.c_str(), o);
+        const double elod = e.run();
+        fprintf(stderr, "\nELOD = %.3f\n", elod);
+        return EXIT_SUCCESS;
     }
     if(pedfile.empty() || mapfile.empty() || datfile.empty()) {
         fprintf(stderr, "%s: the pedigree, map and dat files are all required\n", argv[0]);

@@ -45,6 +45,10 @@ struct mcmc_options {
     bool affected_only, sex_linked;
     uint64_t seed;              // Philox seed (replaces the per-thread mt19937 seed file)
     int device;                 // CUDA device of this chain group
+    // ELOD (types.h:87-92, defaults.h:4-7)
+    bool elod;
+    double elod_frequency, elod_penetrance[3], elod_marker_separation;
+    int elod_replicates;
     // Metropolis-coupled MCMC (types.h:94-98)
     bool mc3;
     int mc3_number_of_chains, mc3_exchange_period;
@@ -60,6 +64,9 @@ class DiseaseModel {
     bool sexlinked;
  public:
     DiseaseModel() : frequency(0.001), sexlinked(false) { penetrance[0] = penetrance[1] = penetrance[2] = 0.0; }
+    DiseaseModel(double freq, const double pen[3], bool sexlink) : frequency(freq), sexlinked(sexlink) {   // disease_model.h:31-44
+        for(int i = 0; i < 3; ++i) penetrance[i] = pen[i];
+    }
     void set_freq(double f) { frequency = f; }
     void set_penetrance(double p, enum unphased_trait t) { penetrance[t] = p; }
     void set_sexlinked(bool s) { sexlinked = s; }
@@ -172,6 +179,9 @@ class Person {
     bool operator<(const Person& p) const { return isfounder_str() && !p.isfounder_str(); }   // person.h:171-173
     double get_disease_prob(enum phased_trait pt) const { return disease_prob[pt]; }
     void make_unknown_affection(const DiseaseModel& dm) { affection_status = UNKNOWN_AFFECTION; init_probs(dm); }
+    void clear_genotypes() { genotypes.clear(); }                                   // person.h:130-132
+    // "experimental for the ELOD code" (person.h:202-208): the genotype prior at `locus` becomes the disease prior
+    void copy_disease_probs(int locus) { for(int i = 0; i < 4; ++i) genotypes_prob[4 * locus + i] = disease_prob[i]; }
     void populate_trait_prob_cache(const GeneticMap& map, bool sex_linked);
     double get_trait_probability(unsigned int locus, enum phased_trait pt) const { return genotypes_prob[4 * locus + pt]; }
     bool safe_to_ignore_meiosis(const Pedigree& ped, enum parentage p, bool sex_linked) const;
@@ -204,7 +214,7 @@ class Pedigree {
 bool parse_map_file(const std::string& filename, GeneticMap& map);
 bool parse_linkage_file(const std::string& filename, GeneticMap& map, DiseaseModel& dm);
 bool parse_pedigree_file(const std::string& filename, std::vector<Pedigree>& pedigrees, const DiseaseModel& dm,
-                         const GeneticMap& map);
+                         const GeneticMap& map, bool ignore_genotypes = false);     // PedigreeParser::set_ignore_genotypes
 // Program::read_and_check_input (program.cc:18-63): map -> dat -> (force X) -> map sanity -> ped
 bool read_and_check_input(const std::string& pedfile, const std::string& mapfile, const std::string& datfile,
                           bool force_sex_linked, GeneticMap& map, DiseaseModel& dm, std::vector<Pedigree>& pedigrees);
@@ -353,14 +363,18 @@ bool write_linkage_results(GeneticMap* map, const std::string& filename, std::ve
 
 // ---- flat problem for the C ABI ---------------------------------------------------------------------
 struct FlatProblem {
-    std::vector<int32_t> mother, father, sex, typed;
+    std::vector<int32_t> mother, father, sex, typed, prior_as_founder;
     std::vector<uint8_t> genotypes, elimination;
     std::vector<double> disease_prob, marker_prob, marker_xprob, theta, partial_theta, minor_freq;
     std::vector<slk_peel_op> ops;
     slk_problem desc;
 };
 // fills `out` (and out.desc, pointing into out's vectors) from the host objects
-void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg, bool sex_linked, FlatProblem& out);
+// real_founder_priors: genotype priors computed with the resolved founder flags (the ELOD setup calls
+// populate_trait_prob_cache after the pedigree is built, elod.h:76-83) instead of the parser's
+// "everyone is a founder"; disease_prior_locus: Person::copy_disease_probs at that marker (-1: none)
+void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg, bool sex_linked, FlatProblem& out,
+                     bool real_founder_priors = false, int disease_prior_locus = -1);
 
 // ---- GPU back end (gpu_lodscores.h, gpu_markov_chain.h) -------------------------------------------------
 class GPULodscores {
@@ -416,6 +430,23 @@ class GPUMarkovChain {
     double calc_trait_prob();                   // Peeler::calc_trait_prob on the device
     double get_likelihood(DescentGraph& dg);    // DescentGraph::get_likelihood on the device
     slk_chain* get_chain() { return chain; }
+};
+
+// ---- ELOD (elod.h/.cc) ---------------------------------------------------------------------------------
+// Expected LOD of a pedigree structure by simulation: a fake map marker - trait - marker; per replicate
+// LocusSampler::start_from on the three loci (no genotypes; the trait locus's prior is each person's disease
+// probability), the two marker rows scored by Peeler::process on the two-marker map.  All replicates of a
+// pedigree run in one batch on the device (slk_elod_run).
+class Elod {
+    DiseaseModel dm;
+    std::vector<Pedigree> pedigrees;
+    GeneticMap map1, map2;
+    struct mcmc_options options;
+    std::vector<double> elods;
+ public:
+    Elod(const char* pedfile, struct mcmc_options opt);
+    double run();                               // elod.cc:19-85: prints the table, returns the total
+    const std::vector<double>& per_pedigree() const { return elods; }
 };
 
 // ---- Metropolis-coupled MCMC (mc3.h/.cc) ----------------------------------------------------------------

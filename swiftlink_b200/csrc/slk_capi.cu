@@ -850,6 +850,169 @@ int slk_debug_msampler_state(slk_chain* c, double* fb, double* lncur) {
     return check_device_error(c);
 }
 
+}  // extern "C"
+
+// ---- ELOD --------------------------------------------------------------------------------
+
+namespace {
+
+// log-sum-exp of prob[0..n): one CTA, fixed-order tree (logarithms.cc:14-23 applied pairwise)
+__global__ void __launch_bounds__(1024) slk_logsumexp_kernel(const double* prob, long long n, double* out) {
+    __shared__ double s_m[1024], s_s[1024];
+    __shared__ long long s_c[1024];
+    const int t = threadIdx.x, T = blockDim.x;
+    double m = -DBL_MAX; long long cnt = 0;
+    for(long long i = t; i < n; i += T) { const double v = prob[i]; if(v > -DBL_MAX) { if(v > m) m = v; ++cnt; } }
+    double sum = 0.0;
+    for(long long i = t; i < n; i += T) { const double v = prob[i]; if(v > -DBL_MAX) sum += exp(v - m); }
+    s_m[t] = m; s_s[t] = sum; s_c[t] = cnt;
+    __syncthreads();
+    for(int d = T >> 1; d > 0; d >>= 1) {
+        if(t < d) {
+            const double m1 = s_m[t], m2 = s_m[t + d];
+            const double mm = m1 > m2 ? m1 : m2;
+            double acc = 0.0;
+            if(s_c[t]) acc += s_s[t] * exp(m1 - mm);
+            if(s_c[t + d]) acc += s_s[t + d] * exp(m2 - mm);
+            s_m[t] = mm; s_s[t] = acc; s_c[t] += s_c[t + d];
+        }
+        __syncthreads();
+    }
+    if(t == 0) { out[0] = s_c[0] ? s_m[0] + log(s_s[0]) : -DBL_MAX; out[1] = (double) s_c[0]; }
+}
+
+struct ElodScratch {
+    uint8_t* dg; double* gs; double* prob; double* red; int* err;
+    ElodScratch() : dg(0), gs(0), prob(0), red(0), err(0) {}
+    ~ElodScratch() { cudaFree(dg); cudaFree(gs); cudaFree(prob); cudaFree(red); cudaFree(err); }
+};
+
+// the three start_from launches of a chunk of replicates on the wide graph (locus_sampler2.cc:214-241
+// with starting_locus = 1): the middle locus alone, then the left marker given its right neighbour, then
+// the right marker given its left neighbour
+int elod_sample_chunk(slk_plan* sp, const ElodScratch& sc, uint64_t seed, uint32_t chain_id, long long first, int n, cudaStream_t st) {
+    const SlkDevPlan& d = sp->dev;
+    const int tpc = d.ls.cta_threads / d.ls.team_threads;
+    for(int pass = 0; pass < 3; ++pass) {
+        SlkLaunch L;
+        memset(&L, 0, sizeof(L));
+        L.plan = d; L.dgp = sc.dg; L.gscratch = sc.gs; L.err = sc.err;
+        L.seed = seed; L.chain = chain_id; L.iteration = 0;
+        L.dump_k = -1; L.si_start = -1;
+        L.period = 3; L.window = 3; L.nunits = n;
+        // Philox is keyed by the row of the wide graph: offset the rows by the first replicate so that a
+        // replicate's draws do not depend on the chunking
+        L.offset = (pass == 0) ? 1 : (pass == 1 ? 0 : 2);
+        L.ignore_left = (pass == 2) ? 0 : 1;
+        L.ignore_right = (pass == 1) ? 0 : 1;
+        L.row_base = first * 3;
+        launch_ls_by_team(d.ls.team_threads, L, grid_for(n, tpc, sp->ls_blocks_per_sm, sp->sm_count), d.ls.cta_threads, sp->ls_cta_smem, st);
+        CU(cudaGetLastError());
+    }
+    return SLK_OK;
+}
+
+const int kElodChunk = 1 << 16;
+
+int elod_alloc(slk_plan* sp, slk_plan* tp, ElodScratch& sc, int chunk) {
+    const SlkDevPlan& d = sp->dev;
+    const SlkDevPlan& t = tp->dev;
+    size_t ls_teams = (size_t) sp->ls_blocks_per_sm * sp->sm_count * (d.ls.cta_threads / d.ls.team_threads);
+    size_t lod_teams = (size_t) tp->lod_blocks_per_sm * tp->sm_count * (t.lod.cta_threads / t.lod.team_threads);
+    size_t gs = std::max(ls_teams * (size_t)(d.ls.arena_doubles - d.ls.smem_doubles),
+                         lod_teams * (size_t)(t.lod.arena_doubles - t.lod.smem_doubles));
+    CU(cudaMalloc((void**) &sc.dg, (size_t) chunk * 3 * d.N));
+    CU(cudaMemset(sc.dg, 0, (size_t) chunk * 3 * d.N));
+    CU(cudaMalloc((void**) &sc.gs, sizeof(double) * std::max<size_t>(gs, 2)));
+    CU(cudaMalloc((void**) &sc.prob, sizeof(double) * chunk));
+    CU(cudaMalloc((void**) &sc.red, sizeof(double) * 2));
+    CU(cudaMalloc((void**) &sc.err, sizeof(int) * 4));
+    CU(cudaMemset(sc.err, 0, sizeof(int) * 4));
+    return SLK_OK;
+}
+
+int elod_check(slk_plan* sp, slk_plan* tp) {
+    if(!sp || (tp && (sp->device != tp->device || sp->dev.N != tp->dev.N || sp->dev.F != tp->dev.F)))
+        return fail(SLK_ERR_INVALID, "slk_elod: the two plans must describe one pedigree on one device");
+    if(sp->dev.M != 3 || (tp && (tp->dev.M != 2 || tp->dev.nlod != 1)))
+        return fail(SLK_ERR_INVALID, "slk_elod: sampler plan must have 3 loci, trait plan 2 loci and n_lod = 1");
+    return SLK_OK;
+}
+
+}  // namespace
+
+extern "C" int slk_elod_run(slk_plan* sp, slk_plan* tp, uint64_t seed, uint32_t chain_id, int64_t replicates,
+                            double* log_sum, int64_t* count, double* prob_out) {
+    if(!tp || !log_sum || !count || replicates < 1) return fail(SLK_ERR_INVALID, "bad argument");
+    int rc = elod_check(sp, tp);
+    if(rc != SLK_OK) return rc;
+    CU(cudaSetDevice(sp->device));
+    const int chunk = (int) std::min<int64_t>(replicates, kElodChunk);
+    ElodScratch sc;
+    rc = elod_alloc(sp, tp, sc, chunk);
+    if(rc != SLK_OK) return rc;
+    cudaStream_t st = 0;
+    const SlkDevPlan& t = tp->dev;
+    double total = -DBL_MAX;
+    long long added = 0;
+    for(int64_t first = 0; first < replicates; first += chunk) {
+        const int n = (int) std::min<int64_t>(chunk, replicates - first);
+        rc = elod_sample_chunk(sp, sc, seed, chain_id, first, n, st);
+        if(rc != SLK_OK) return rc;
+        // Peeler::process of every replicate's two marker rows (elod.cc:58-61)
+        SlkLaunch L;
+        memset(&L, 0, sizeof(L));
+        L.plan = t; L.dgp = sc.dg; L.gscratch = sc.gs; L.err = sc.err;
+        L.dump_k = -1; L.si_start = -1; L.window = 2;
+        L.period = 3; L.lod_row0 = 0; L.lod_row1 = 2;
+        L.accumulate = 0; L.nunits = n; L.dump_prob = sc.prob; L.dump_result = sc.prob;   // result is overwritten by prob
+        const int tpc = t.lod.cta_threads / t.lod.team_threads;
+        launch_lod_by_team(t.lod.team_threads, L, grid_for(n, tpc, tp->lod_blocks_per_sm, tp->sm_count), t.lod.cta_threads, tp->lod_cta_smem, st);
+        CU(cudaGetLastError());
+        slk_logsumexp_kernel<<<1, 1024, 0, st>>>(sc.prob, n, sc.red);
+        CU(cudaGetLastError());
+        double h[2]; int herr[2];
+        CU(cudaMemcpyAsync(h, sc.red, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(herr, sc.err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+        if(prob_out) CU(cudaMemcpyAsync(prob_out + first, sc.prob, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if(herr[0] != 0) {
+            if(herr[0] == SLK_ERR_ZERO_LIKELIHOOD) return fail(herr[0], "likelihood is zero at locus %d (check penetrance function?)", herr[1] % 3);
+            return fail(herr[0], "intermediate state had a likelihood of 0.0 or less (replicate %lld)", (long long) first + herr[1]);
+        }
+        // LODscores::add across chunks (lod_score.h:74-80)
+        if(h[1] > 0) {
+            total = (total == -DBL_MAX) ? h[0] : log(exp(total - h[0]) + 1.0) + h[0];
+            added += (long long) h[1];
+        }
+    }
+    *log_sum = total;
+    *count = added;
+    return SLK_OK;
+}
+
+extern "C" int slk_debug_elod_graphs(slk_plan* sp, uint64_t seed, uint32_t chain_id, int64_t first, int32_t n, int32_t* dg) {
+    if(!dg || n < 1 || first < 0) return fail(SLK_ERR_INVALID, "bad argument");
+    int rc = elod_check(sp, 0);
+    if(rc != SLK_OK) return rc;
+    CU(cudaSetDevice(sp->device));
+    ElodScratch sc;
+    rc = elod_alloc(sp, sp, sc, n);
+    if(rc != SLK_OK) return rc;
+    rc = elod_sample_chunk(sp, sc, seed, chain_id, first, n, 0);
+    if(rc != SLK_OK) return rc;
+    const size_t cells = (size_t) n * 3 * sp->dev.N;
+    int32_t* staging = 0;
+    CU(cudaMalloc((void**) &staging, cells * 2 * sizeof(int32_t)));
+    slk_dg_unpack_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(sc.dg, staging, cells);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(dg, staging, cells * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cudaFree(staging);
+    return SLK_OK;
+}
+
+extern "C" {
+
 // ---- parity hooks ----------------------------------------------------------------------
 
 static int debug_ls(slk_chain* c, uint64_t iteration, int locus, int il, int ir, bool forward_only,

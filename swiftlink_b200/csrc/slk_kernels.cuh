@@ -64,6 +64,13 @@ struct SlkLaunch {
     double* dump_result;         // sampler: [1]; LOD: [nunits]
     double* dump_prob;           // LOD: [nunits]
     long long* trace;            // optional: clock64() stamps of team 0's first unit (tuning aid)
+    // batched replicates (ELOD, elod.cc:55-66): the graph is `nunits` short chromosomes of `period` loci laid
+    // end to end; row r of the graph uses row r % period of the plan tables and has no neighbour across a
+    // chromosome boundary.  LOD scoring then peels one interval per chromosome between its rows lod_row0 and
+    // lod_row1 with the (two-locus) trait plan's interval 0.
+    int period;
+    int lod_row0, lod_row1;
+    long long row_base;          // added to the graph row in the Philox key (replicates are sampled in chunks)
 };
 
 __constant__ uint8_t c_glist[16] = {
@@ -118,6 +125,7 @@ struct TeamMem {
     uint8_t* dgr;                // right neighbour / interval end
     uint8_t* pmk;                // sampled genotypes
     int* red;
+    const double* dprob;         // [N][4] disease probabilities (global)
 };
 
 __device__ __forceinline__ MatRef mat_ref(const TeamMem& tm, int off) {
@@ -277,12 +285,19 @@ __device__ __forceinline__ TeamMem carve_team(const SlkLaunch& L, const SlkProgr
     tm.dgr = tm.dgl + lay.nbytes;
     tm.pmk = tm.dgr + lay.nbytes;
     tm.red = (int*)(base + lay.red);
+    tm.dprob = P.disease_prob;
     return tm;
 }
 
 // marker prior of person `peel` at the staged locus (person.cc:224-245 via prior classes)
 __device__ __forceinline__ void load_prior(const TeamMem& tm, int person, double tc[4]) {
     uint32_t cls = tm.gc[person] >> 4;
+    if(cls == SLK_PRIOR_PERSON) {
+        // ELOD's simulated trait locus: the person's disease probabilities (person.h:204-208)
+#pragma unroll
+        for(int g = 0; g < 4; ++g) tc[g] = tm.dprob[4 * person + g];
+        return;
+    }
 #pragma unroll
     for(int g = 0; g < 4; ++g) tc[g] = tm.scal[16 + cls * 4 + g];      // classes 0-4 fixed, 5-6 founder priors of this locus
 }
@@ -613,27 +628,28 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
             else if(unit <= L.si_start) { locus = L.si_start - unit; ign_left = true; ign_right = false; }
             else                        { locus = unit; ign_left = false; ign_right = true; }
         }
-        const bool has_left = (locus != 0), has_right = (locus != M - 1);
+        const int plocus = L.period ? locus % L.period : locus;          // row of the plan tables
+        const bool has_left = (plocus != 0), has_right = (plocus != (L.period ? L.period : M) - 1);
 
         const bool tracing = L.trace != 0 && gteam == 0 && unit == gteam && tid == 0;
         int tstamp = 0;
         if(tracing) L.trace[tstamp++] = clock64();
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
         for(int i = tid; i < N; i += T) {
-            tm.gc[i] = P.gcode[(size_t) locus * N + i];
+            tm.gc[i] = P.gcode[(size_t) plocus * N + i];
             tm.dgl[i] = has_left ? L.dgp[(size_t)(locus - 1) * N + i] : 0;
             tm.dgr[i] = has_right ? L.dgp[(size_t)(locus + 1) * N + i] : 0;
         }
         for(int i = tid; i < 28; i += T)
-            tm.scal[16 + i] = (i < 20) ? c_prior[i >> 2][i & 3] : P.fprior[(size_t) locus * 8 + (i - 20)];
+            tm.scal[16 + i] = (i < 20) ? c_prior[i >> 2][i & 3] : P.fprior[(size_t) plocus * 8 + (i - 20)];
         // the genotype draws of this locus, one per peel op (Philox keyed by chain, iteration, locus, op)
         for(int op = tid; op < P.nops; op += T)
-            tm.ru[op] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) locus, (uint32_t) op);
+            tm.ru[op] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t)(locus + L.row_base), (uint32_t) op);
         if(tid == 0) {
             // sampler_rfunction.h:84-100: theta2 (left interval) / theta (right interval)
             double th2 = 1.0, ath2 = 1.0, th = 1.0, ath = 1.0;
-            if(has_left && !ign_left)   { th2 = P.theta[locus - 1]; ath2 = 1.0 - th2; }
-            if(has_right && !ign_right) { th = P.theta[locus]; ath = 1.0 - th; }
+            if(has_left && !ign_left)   { th2 = P.theta[plocus - 1]; ath2 = 1.0 - th2; }
+            if(has_right && !ign_right) { th = P.theta[plocus]; ath = 1.0 - th; }
             tm.scal[0] = th; tm.scal[1] = ath; tm.scal[2] = th2; tm.scal[3] = ath2;
         }
         team_sync<T>(team);
@@ -797,17 +813,17 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
                     double p0 = 1.0, p1 = 1.0;                              // :44-65
                     if(has_left && !ign_left) {
                         const uint32_t v = (tm.dgl[i] >> parent) & 1u;
-                        const double th = P.theta[locus - 1], ith = 1.0 - th;
+                        const double th = P.theta[plocus - 1], ith = 1.0 - th;
                         p0 *= (v == 0) ? ith : th;
                         p1 *= (v == 1) ? ith : th;
                     }
                     if(has_right && !ign_right) {
                         const uint32_t v = (tm.dgr[i] >> parent) & 1u;
-                        const double th = P.theta[locus], ith = 1.0 - th;
+                        const double th = P.theta[plocus], ith = 1.0 - th;
                         p0 *= (v == 0) ? ith : th;
                         p1 *= (v == 1) ? ith : th;
                     }
-                    const double r = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) locus,
+                    const double r = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t)(locus + L.row_base),
                                                  (uint32_t)(P.nops + 2 * i + parent));
                     mi = (r < p0 / (p0 + p1)) ? 0u : 1u;
                 }
@@ -846,14 +862,16 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lodscore_kernel(cons
 
     for(int u = gteam; u < L.nunits; u += total_teams) {
         const int unit = L.unit_base + u;
-        const int interval = unit / P.nlod;
-        const int k = unit - interval * P.nlod;                             // position k+1 of nlod
+        const int interval = L.period ? 0 : unit / P.nlod;
+        const int k = L.period ? 0 : unit - interval * P.nlod;              // position k+1 of nlod
+        const size_t row_l = L.period ? (size_t) unit * L.period + L.lod_row0 : (size_t) interval;
+        const size_t row_r = L.period ? (size_t) unit * L.period + L.lod_row1 : (size_t) interval + 1;
 
         int ncross = 0;
         if(!L.no_dg) {
             for(int i = tid; i < N; i += T) {
-                tm.dgl[i] = L.dgp[(size_t) interval * N + i];
-                tm.dgr[i] = L.dgp[(size_t)(interval + 1) * N + i];
+                tm.dgl[i] = L.dgp[row_l * N + i];
+                tm.dgr[i] = L.dgp[row_r * N + i];
             }
             if(tid == 0) {
                 // trait_rfunction.h:50-56

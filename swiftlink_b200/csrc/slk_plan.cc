@@ -470,6 +470,7 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
             bool xmale = pb.sex_linked && pb.sex[i] == SLK_MALE;
             int g = pb.genotypes[(size_t) i * M + l];
             int cls = prior_class(founder, pb.typed[i] != 0, g, xmale);
+            if(pb.disease_prior_locus_plus1 == l + 1) cls = SLK_PRIOR_PERSON;
             uint8_t lm = legal_mask_from_elimination(pb.elimination[(size_t) l * N + i]);
             hp.gcode[(size_t) l * N + i] = (uint8_t)(lm | (cls << 4));
         }

@@ -141,7 +141,8 @@ enum {
     SLK_PRIOR_FLAT = 3,      // (.25,.25,.25,.25)
     SLK_PRIOR_XMALE = 4,     // (.5,.5,0,0)
     SLK_PRIOR_FOUNDER = 5,   // fprior[locus][0]
-    SLK_PRIOR_FOUNDER_X = 6  // fprior[locus][1]
+    SLK_PRIOR_FOUNDER_X = 6, // fprior[locus][1]
+    SLK_PRIOR_PERSON = 7     // disease_prob[person] (ELOD's simulated trait locus, person.h:204-208)
 };
 
 #endif

@@ -11,7 +11,7 @@ SYMBOLS = [
     "slk_host_marker_name", "slk_host_genotypes", "slk_host_marker_trait_prob", "slk_host_map_table",
     "slk_host_disease_model", "slk_host_elim_masks", "slk_host_build_peel", "slk_host_set_peel",
     "slk_host_num_ops", "slk_host_peel_cost", "slk_host_op_info", "slk_host_random_descentgraph",
-    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_mc3", "slk_host_mc3_temperature",
+    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_mc3", "slk_host_mc3_temperature", "slk_host_elod",
 ]
 
 
@@ -168,6 +168,19 @@ class Host(object):
         if rc != 0:
             raise capi.SlkError(rc, self.L.slk_last_error().decode())
         return dict(lod=lod.reshape(self.M - 1, self.nlod), swap_success=ok[:n_chains - 1], swap_failure=bad[:n_chains - 1])
+
+
+def elod(pedfile, frequency=1e-4, penetrance=(0.0, 0.0, 1.0), separation=0.05, replicates=1000000, sex_linked=False,
+         affected_only=False, peel_iterations=100000, seed=20261017, device=0):
+    """Elod(pedfile, options).run() on the device: (total ELOD, per-pedigree values)"""
+    L = capi.lib()
+    L.slk_host_elod.restype = C.c_double
+    pen = np.ascontiguousarray(penetrance, np.float64)
+    per = np.zeros(64)
+    total = L.slk_host_elod(pedfile.encode(), C.c_double(frequency), _dp(pen), C.c_double(separation), int(replicates),
+                            int(sex_linked), int(affected_only), int(peel_iterations), C.c_uint64(seed), int(device),
+                            _dp(per), 64)
+    return float(total), per
 
 
 def mc3_temperature(i, n_chains, temperatures=None):

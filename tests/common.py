@@ -77,3 +77,47 @@ def case_files(name, tmpdir=None):
         return synth.write_linkage(synth.generate(**INBRED), os.path.join(str(d), "inbred"))
     from oracle import refapi
     return refapi.example(name)
+
+
+def haldane(m):
+    return 0.5 * (1.0 - np.exp(-2.0 * m))
+
+
+def elod_problems(name, separation=0.05, trait_freq=1e-4):
+    """The two problems of the ELOD calculation (elod.h:40-90) on a golden pedigree: the three-locus sampler
+    problem (marker, simulated trait locus whose genotype prior is each person's disease probability, marker;
+    no genotypes; priors with the resolved founder flags) and the two-marker trait problem.  Returns
+    (device dict 1, device dict 2, oracle dict 1, oracle dict 2)."""
+    from oracle import orcapi
+    base = problem(name)
+    N, F = base["N"], base["F"]
+    assert not base["sex_linked"], "autosomal cases only (elimination masks are trivially 'everything legal')"
+
+    def snp_prob(minor):
+        major = 1.0 - minor
+        p = np.array([major * major, minor * minor, minor * major, minor * major])     # UU, AA, AU, UA (genetic_map.h:68-74)
+        return p / p.sum()
+
+    th_half, th_full = haldane(separation / 2), haldane(separation)
+
+    def partial(theta, n):
+        return haldane((-0.5 * np.log(1 - 2 * theta)) / (n + 1))
+
+    founder = (np.asarray(base["mother"]) < 0).astype(np.int32)
+    out = []
+    for M, minors, thetas in ((3, [0.5, trait_freq, 0.5], [th_half, th_half]), (2, [0.5, 0.5], [th_full])):
+        d = dict(base)
+        d.update(M=M, nlod=1, genotypes=np.zeros((N, M), np.int32), typed=np.zeros(N, np.int32),
+                 elim=np.full((M, N), 15, np.int32), theta=np.array(thetas), partial=np.array([partial(t, 1) for t in thetas]),
+                 minor=np.array(minors), mapprob=np.stack([snp_prob(m) for m in minors]),
+                 mapxprob=np.stack([snp_prob(m) for m in minors]), prior_as_founder=founder)
+        mp = np.zeros((N, M, 4))
+        for i in range(N):
+            for l in range(M):
+                mp[i, l] = orcapi.marker_prob(int(founder[i]), 0, 0, 0, d["mapprob"][l])
+        if M == 3:
+            mp[:, 1, :] = np.asarray(base["disease_prob"])          # Person::copy_disease_probs(1)
+            d["disease_prior_locus"] = 1
+        d["marker_prob"] = mp
+        out.append(d)
+    return out[0], out[1]

@@ -27,8 +27,8 @@ def test_cli_refuses_what_it_cannot_do():
     ped, mapf, dat = refapi.example("loop")
     out = subprocess.run([SWIFT, "-p", ped, "-m", mapf], capture_output=True, text=True)
     assert out.returncode != 0 and "required" in out.stderr
-    out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-e"], capture_output=True, text=True)
-    assert out.returncode != 0
+    out = subprocess.run([SWIFT, "-p", ped, "-e", "-k", "0.1,0.2"], capture_output=True, text=True)
+    assert out.returncode != 0 and "penetrance requires 3 floats" in out.stderr
     out = subprocess.run([SWIFT, "-p", ped, "-m", mapf, "-d", dat, "-l", "1.5"], capture_output=True, text=True)
     assert out.returncode != 0 and "between 0.0 and 1.0" in out.stderr
 
@@ -61,3 +61,18 @@ def test_cli_end_to_end_east(tmp_path):
         lines = tr[0].read_text().splitlines()
         assert lines[0] == "iteration likelihood" and len(lines) == 1 + 60          # iterations 300..899 every 10th
         assert all(float(ln.split("\t")[1]) < 0.0 for ln in lines[1:])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_elod():
+    """swift -p loop.ped --elod -u 100000: the reference's report format and an estimate in its Monte Carlo band"""
+    from oracle import refapi
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "elod_ref.npz"))
+    out = subprocess.run([SWIFT, "-p", refapi.example("loop")[0], "-e", "-u", "100000", "-q", "20000"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ELOD parameters:" in out.stderr and "replicates = 100000" in out.stderr
+    line = [ln for ln in out.stderr.splitlines() if ln.startswith("ELOD = ")]
+    assert len(line) == 1
+    assert abs(float(line[0].split("=")[1]) - ref["loop"].mean()) < 0.01
