@@ -43,12 +43,15 @@ import numpy as np  # noqa: E402
 
 N_MEMBERS, N_MARKERS, N_LOD, SCORING_PERIOD = 200, 10000, 5, 100
 LSAMPLER_PROB = 0.5                       # defaults.h: the reference's default -l
+# profiling aid only (profiles/*.md say when it was used): a shorter step so that a whole bench run fits under ncu
+if os.environ.get("SLK_BENCH_SCORING_PERIOD"):
+    SCORING_PERIOD = int(os.environ["SLK_BENCH_SCORING_PERIOD"])
 REF_SAMPLE_MARKERS = 1000
 METRIC = "mcmc_iterations_per_sec_incl_lod_scoring"
 UNIT = "iterations/s"
 WORKLOAD = ("synthetic 200-member consanguineous pedigree, 10k SNPs, default sampler mix (-l 0.5), LOD scoring "
-            "(5 positions/interval) every 100th iteration")
-STEP_DESC = "100 iterations (each an L-sweep w.p. 0.5, else an M-sweep over all meioses) + 1 LOD scoring pass"
+            "(5 positions/interval) every %dth iteration" % SCORING_PERIOD)
+STEP_DESC = "%d iterations (each an L-sweep w.p. 0.5, else an M-sweep over all meioses) + 1 LOD scoring pass" % SCORING_PERIOD
 
 
 def load_order():

@@ -496,19 +496,29 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     double ret = -INFINITY;
     if(!dead) {
         const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
+        // an unfixed component contributes p0 + p1 = M^a m^b + M^b m^a = M^hi' m^lo' (1 + rho^|a-b|) with
+        // rho = min(m/M, M/m) <= 1 and (hi', lo') the exponents of the larger term: the exponents are summed as
+        // integers, the (1 + rho^k) factors (each in (1, 2]) multiplied up and logged once
         uint32_t A = 0, B = 0;
-        double extra = 0.0;
+        const bool minor_smaller = lnm <= lnM;
+        const double rho = exp(-fabs(lnm - lnM));
+        double prod = 1.0;
         for(int i = 0; i < ngroups; ++i) {
             const Grp e = grp_ld(i);
             if(e.meta & 0x8000u) continue;                 // merged away (group_active false)
-            A += e.a; B += e.b;
+            uint32_t a = e.a, b = e.b;
             if(fixed_of(e) == -1) {
-                // p0 + p1 = M^a m^b + M^b m^a = M^a m^b (1 + (m/M)^(a-b))
-                const double d = (double)((int) e.a - (int) e.b) * (lnm - lnM);
-                extra += d > 0.0 ? d + log1p(exp(-d)) : log1p(exp(d));
+                // keep the larger of the two terms: more factors of the more frequent allele
+                const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+                uint32_t k = hi - lo;
+                if(minor_smaller) { a = hi; b = lo; } else { a = lo; b = hi; }
+                double t = 1.0, sq = rho;
+                while(k) { if(k & 1u) t *= sq; sq *= sq; k >>= 1; }
+                prod *= 1.0 + t;
             }
+            A += a; B += b;
         }
-        ret = ((double) A * lnM + (double) B * lnm) + extra;
+        ret = ((double) A * lnM + (double) B * lnm) + log(prod);
         if(!(ret > -1e290)) ret = -INFINITY;               // a zero allele frequency entered the product
     }
     if(nflip == 0) L.lncur[l] = ret;

@@ -33,13 +33,20 @@ def stalls(rep):
     return out
 
 
+SKIP = int(__import__("os").environ.get("SLK_SUMMARY_SKIP", "0"))       # leading launches that belong to the set-up
+
+
 def launches(path):
     rows = list(csv.reader(open(path)))
     hdr = [r for r in rows if "Kernel Name" in r][0]
     k, v = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = {}
+    seen = 0
     for r in rows:
         if len(r) == len(hdr) and r is not hdr and r[v].replace(".", "").isdigit():
+            seen += 1
+            if seen <= SKIP:
+                continue
             name = r[k].split("(")[0]
             a = agg.setdefault(name, [0, 0.0])
             a[0] += 1
@@ -50,8 +57,10 @@ def launches(path):
 def main():
     tag, lcsv, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
     lines = ["# ncu summary %s" % tag, "",
-             "Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 2 "
-             "--warmup 1` (per-launch times are cold-cache and serialised: compare shares, not absolutes).", "",
+             "Launch list: `SLK_BENCH_SCORING_PERIOD=6 ncu --metrics gpu__time_duration.sum --clock-control none ... "
+             "python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (a step of 6 iterations + 1 scoring pass instead of 100 + 1 "
+             "so that the whole run fits under ncu; the first %d launches -- sequential imputation and burn-in -- are left out; "
+             "per-launch times are cold-cache and serialised: compare shares, not absolutes)." % SKIP, "",
              "| kernel | launches | total ms | share | avg ms |", "|---|---:|---:|---:|---:|"]
     agg = launches(lcsv)
     tot = sum(a[1] for a in agg.values())
