@@ -374,6 +374,12 @@ def run_ours(args, rank, world, local_rank):
     except (IOError, ValueError):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
+            traffic = json.load(f)
+    except (IOError, ValueError):
+        pass
     loci_per_launch = M / 2.0
     ls_flops = stats["flops_ls"] * loci_per_launch
     ls_tflops = ls_flops / (ls_ms * 1e-3) / 1e12
@@ -392,21 +398,23 @@ def run_ours(args, rank, world, local_rank):
     ms_bytes = ms_bytes_per_eval * ms_evals
     roofline = {
         "kernel": "slk_ms_likelihood_kernel", "bound": "hbm", "achieved": ms_bytes / (ms_lik_ms * 1e-3) / 1e9, "peak": hbm_peak,
-        "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("slk_ms_likelihood_kernel"),
+        "traffic_source": traffic.get("_source"),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
         "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": ms_lik_ms, "units_per_launch": ms_evals,
         "note": "latency-bound integer walk (one dependent chain per thread, 939 warps resident): neither HBM nor a math "
                 "pipe is the limiter; see DESIGN.md section 4",
-        "ms_chain_kernel": {"launch_ms": ms_chain_ms, "steps_per_launch": 2},
+        "ms_chain_kernel": {"launch_ms": ms_chain_ms, "steps_per_launch": 2, "traffic": traffic.get("slk_ms_chain_kernel")},
         "lsampler_kernel": {
             "bound": "fp64", "achieved": ls_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ls_tflops / fp64_peak if fp64_peak else None,
             "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
             "algorithmic_flops_per_launch": ls_flops, "launch_ms": ls_ms, "units_per_launch": loci_per_launch,
+            "traffic": traffic.get("slk_lsampler_kernel"),
             "hbm": {"achieved": ls_bytes / (ls_ms * 1e-3) / 1e9, "frac": ls_bytes / (ls_ms * 1e-3) / 1e9 / hbm_peak,
                     "algorithmic_bytes_per_launch": ls_bytes}},
         "lodscore_kernel": {"bound": "fp64", "achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
-                            "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops,
+                            "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops, "traffic": traffic.get("slk_lodscore_kernel"),
                             "trait_positions_per_s": (M - 1) * N_LOD / (lod_ms * 1e-3)},
         "msampler": {"sweep_ms": msweep_ms, "meioses_per_sweep": n_meioses, "us_per_meiosis_step": 1e3 * msweep_ms / max(n_meioses, 1),
                      "locus_likelihoods_per_s": 1.5 * n_meioses * M / (msweep_ms * 1e-3)},

@@ -364,6 +364,28 @@ int slk_plan_validate(const slk_problem* problem, double* stats, int cap) {
     return SLK_OK;
 }
 
+// The global part of the peel arenas is scratch: every unit overwrites its team's slice and nothing
+// outlives a launch.  Marking the slab as persisting in L2 keeps the slices resident between units, so
+// the dirty lines are overwritten in place instead of being written back to HBM (ncu on the 200 x 10k
+// workload: 352 MB of DRAM writes per L-sampler launch without the window).
+static void pin_scratch_in_l2(slk_chain* c, cudaStream_t s) {
+    if(getenv("SLK_NO_L2_WINDOW") || c->gscratch_doubles < 1024) return;
+    cudaDeviceProp prop;
+    if(cudaGetDeviceProperties(&prop, c->plan->device) != cudaSuccess) { cudaGetLastError(); return; }
+    size_t bytes = c->gscratch_doubles * sizeof(double);
+    size_t carve = std::min<size_t>(bytes, (size_t) prop.persistingL2CacheMaxSize);
+    if(carve == 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    if(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = c->gscratch;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) carve / (double) attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 int slk_chain_create(slk_plan* plan, uint64_t seed, uint32_t chain_id, slk_chain** out) {
     if(!plan || !out) return fail(SLK_ERR_INVALID, "null argument");
     *out = 0;
@@ -395,6 +417,7 @@ int slk_chain_create(slk_plan* plan, uint64_t seed, uint32_t chain_id, slk_chain
         slk_chain_destroy(c);
         return fail(SLK_ERR_CUDA, "chain allocation failed: %s", msg.c_str());
     }
+    pin_scratch_in_l2(c, c->own_stream);
     *out = c;
     return slk_lodscore_init(c);
 }
@@ -415,6 +438,7 @@ int slk_chain_set_stream(slk_chain* c, void* cuda_stream) {
     if(!c) return fail(SLK_ERR_INVALID, "null chain");
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t) cuda_stream : c->own_stream;
+    if(cuda_stream) pin_scratch_in_l2(c, c->stream);
     return SLK_OK;
 }
 

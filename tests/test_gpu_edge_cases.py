@@ -170,3 +170,41 @@ def test_fully_penetrant_trait_failure_is_reported(tmp_path):
         ch.sync()
     assert e.value.code == capi.ERR_NONPOSITIVE_TRAIT
     ch.close()
+
+
+def _chain_of_families(n_families, n_markers=4, seed=1):
+    """a long thin pedigree: family k = founder father, mother (a daughter of family k-1; a founder for k = 0) and
+    two children; genotypes gene-dropped without recombination information (each marker independently)"""
+    rng = np.random.default_rng(seed)
+    father, mother, sex = [-1], [-1], [2]                        # person 0: the first mother
+    cur_mother = 0
+    for k in range(n_families):
+        f = len(father); father.append(-1); mother.append(-1); sex.append(1)
+        kids = []
+        for c in range(2):
+            kids.append(len(father)); father.append(f); mother.append(cur_mother); sex.append(2 if c == 0 else 1)
+        cur_mother = kids[0]
+    n = len(father)
+    father, mother, sex = np.array(father), np.array(mother), np.array(sex)
+    maf = rng.uniform(0.2, 0.5, n_markers)
+    a1 = np.zeros((n, n_markers), np.int8); a2 = np.zeros((n, n_markers), np.int8)
+    for i in range(n):                                           # parents precede children by construction
+        for l in range(n_markers):
+            if father[i] < 0:
+                a1[i, l] = 1 + (rng.random() < maf[l]); a2[i, l] = 1 + (rng.random() < maf[l])
+            else:
+                a1[i, l] = (a1 if rng.random() < 0.5 else a2)[mother[i], l]
+                a2[i, l] = (a1 if rng.random() < 0.5 else a2)[father[i], l]
+    typed = father >= 0
+    a1[~typed] = 0; a2[~typed] = 0
+    return dict(father=father, mother=mother, sex=sex, affected=np.zeros(n, bool), typed=typed, allele1=a1, allele2=a2,
+                maf=maf, pos_cm=1.0 + np.arange(n_markers), trait_freq=1e-3, penetrance=(0.01, 0.01, 0.9))
+
+
+def test_more_than_255_founder_alleles(tmp_path):
+    """131 founders: the M-sampler's 16-bit label / 2-word component path (2F > 255)"""
+    ped = _chain_of_families(130)
+    ped["affected"][[5, 8, 200]] = True
+    h, d, orc, plan = _setup(tmp_path, ped, iters=2000)
+    assert 2 * orc.F > 255
+    _check_everything(d, orc, plan, sweeps=2)
