@@ -389,16 +389,16 @@ def run_ours(args, rank, world, local_rank):
     # algorithmic bytes (minimal encodings): per locus update read 2x2(N-F) bits of
     # neighbouring meioses + 2N bits of genotypes + 16 B theta, write 2(N-F) bits
     ls_bytes = loci_per_launch * ((4 * nf + 2 * N + 2 * nf) / 8.0 + 16)
-    # The dominant kernel of the default mix is the M-sampler's likelihood kernel: integer / byte work, one
-    # thread per (locus, hypothesis).  Algorithmic bytes per evaluation (minimal encodings): the graph row
-    # 2(N-F) bits, the typed people's genotypes 2 nt bits, two allele-frequency logs 16 B, ln L out 8 B.
+    # The dominant kernel of the default mix is the M-sampler's (incremental) likelihood kernel: integer / byte
+    # work, one thread per (locus, hypothesis).  Algorithmic bytes per evaluation (minimal encodings): the graph
+    # row 2(N-F) bits, the typed people's genotypes 2 nt bits, two allele-frequency logs 16 B, ln L out 8 B.
     n_typed = int(np.asarray(hst.person_table()["typed"]).sum())
     ms_bytes_per_eval = (2 * nf + 2 * n_typed) / 8.0 + 24.0
     ms_evals = 3 * M                                               # three hypotheses per locus per launch
     ms_bytes = ms_bytes_per_eval * ms_evals
     roofline = {
-        "kernel": "slk_ms_likelihood_kernel", "bound": "hbm", "achieved": ms_bytes / (ms_lik_ms * 1e-3) / 1e9, "peak": hbm_peak,
-        "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("slk_ms_likelihood_kernel"),
+        "kernel": "slk_ms_step_kernel", "bound": "hbm", "achieved": ms_bytes / (ms_lik_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("slk_ms_step_kernel"),
         "traffic_source": traffic.get("_source"),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
         "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": ms_lik_ms, "units_per_launch": ms_evals,

@@ -267,7 +267,8 @@ int slk_debug_msampler_state(slk_chain* chain, double* fb, double* ln_cur);
    stamps must hold 160 values. */
 int slk_debug_msampler_trace(slk_chain* chain, int meiosis0, int meiosis1, long long* stamps);
 /* measurement aid for bench.py: enqueue `reps` launches of one M-sampler kernel for the pair
-   (meiosis0, meiosis1): which = 0 the three-hypothesis likelihood kernel, 1 the two-step chain kernel */
+   (meiosis0, meiosis1): which = 0 the three-hypothesis incremental likelihood kernel, 1 the two-step chain kernel,
+   2 the full likelihood kernel (every label recomputed; what a sweep's reset launches once) */
 int slk_debug_msampler_launch(slk_chain* chain, int meiosis0, int meiosis1, int which, int reps);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward

@@ -61,6 +61,7 @@ struct slk_plan {
     // M-sampler likelihood kernel geometry
     int ms_grid, ms_threads, ms_smem;
     int ms_chain_loci, ms_chain_smem;
+    int ms_step_smem;
 };
 
 struct slk_chain {
@@ -77,7 +78,7 @@ struct slk_chain {
     int* err;                     // device [4]
     int32_t count;                // scoring passes (LODscores::count)
     // M-sampler state (allocated on first use)
-    double* ms_lncur; double* ms_lnl; uint8_t* ms_bits; double* ms_fb; double* ms_out;
+    double* ms_lncur; double* ms_lnl; uint8_t* ms_bits; double* ms_fb; double* ms_out; void* ms_te; uint32_t* ms_stale;
     bool ms_cur_valid;            // ms_cur describes the graph now in dgp
     // debug buffers (allocated on first use)
     double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
@@ -276,6 +277,8 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
     }
     UP(ms.seq, h.ms_seq); UP(ms.typed, h.ms_typed); UP(ms.obsT, h.ms_obsT); UP(ms.minor, h.ms_minor);
     UP(ms.lnmajor, h.ms_lnmajor); UP(ms.lnminor, h.ms_lnminor);
+    UP(ms.desc_mask, h.ms_desc_mask); UP(ms.typed_index, h.ms_typed_index);
+    d.ms.W = h.ms_W;
     d.ms.n_typed = (int) h.ms_typed.size();
     d.ms.available = h.ms_available ? 1 : 0;
 #undef UP
@@ -295,7 +298,11 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
             p->ms_grid = (h.M + 31) / 32; p->ms_threads = 32;
             p->ms_smem = (int) lay.cta_tables + 32 * (int) lay.per_thread;
         }
-        if(lay.G > SLK_MS_MAXGROUPS || h.N >= 2048) p->ms_threads = 0;      // 12-bit component ids, 16-bit row offsets
+        if(lay.G > SLK_MS_MAXGROUPS || h.N >= 2048) p->ms_threads = 0;
+        {
+            const MsStepLayout sl = slk_ms_step_layout(h.N, h.F, d.ms.n_typed, h.ms_W);
+            p->ms_step_smem = (int) sl.cta_tables + 32 * (int) sl.per_thread;
+        }      // 12-bit component ids, 16-bit row offsets
         // chain kernel: raw pair (16 B) + one map byte per locus of the CTA's share of the chromosome
         {
             const int per_thread = (h.M + SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS - 1) / (SLK_MS_CLUSTER * SLK_MS_CHAIN_THREADS);
@@ -319,6 +326,8 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         e = prep_debug(d.ls.prog_smem_bytes + d.ls.team_smem_bytes, d.lod.prog_smem_bytes + d.lod.team_smem_bytes);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_likelihood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(slk_ms_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax - 4096);
     if(e != cudaSuccess || p->ls_blocks_per_sm < 1 || p->lod_blocks_per_sm < 1) {
         std::string msg = cudaGetErrorString(e);
@@ -430,7 +439,7 @@ void slk_chain_destroy(slk_chain* c) {
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
     cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
-    cudaFree(c->ms_lncur); cudaFree(c->ms_lnl); cudaFree(c->ms_bits); cudaFree(c->ms_fb); cudaFree(c->ms_out);
+    cudaFree(c->ms_lncur); cudaFree(c->ms_lnl); cudaFree(c->ms_bits); cudaFree(c->ms_te); cudaFree(c->ms_stale); cudaFree(c->ms_fb); cudaFree(c->ms_out);
     delete c;
 }
 
@@ -647,6 +656,9 @@ static int ms_ready(slk_chain* c) {
         CU(cudaMalloc((void**) &c->ms_bits, 2 * M));
         CU(cudaMalloc((void**) &c->ms_fb, sizeof(double) * 2 * M));
         CU(cudaMalloc((void**) &c->ms_out, sizeof(double) * 4));
+        CU(cudaMalloc((void**) &c->ms_te, (size_t) std::max(p->dev.ms.n_typed, 1) * M * 4));
+        CU(cudaMalloc((void**) &c->ms_stale, sizeof(uint32_t) * M * p->dev.ms.W));
+        CU(cudaMemsetAsync(c->ms_stale, 0, sizeof(uint32_t) * M * p->dev.ms.W, c->stream));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
         c->ms_cur_valid = false;
     }
@@ -662,10 +674,19 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.mother = d.mother; L.father = d.father; L.male = d.male; L.theta = d.theta;
     L.log_theta = d.log_theta; L.log_1mtheta = d.log_1mtheta;
     L.dgp = c->dgp; L.lncur = c->ms_lncur; L.lnl = c->ms_lnl; L.bits = c->ms_bits; L.fb = c->ms_fb; L.err = c->err;
+    L.te = c->ms_te; L.stale = c->ms_stale;
     L.out = c->ms_out;
     L.nsets = 1;
     L.seed = c->seed; L.chain = c->chain_id;
     return L;
+}
+
+// the incremental kernel of a sweep's steps (te and the stale masks are valid: a reset has run)
+static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
+    slk_plan* p = c->plan;
+    const int grid = p->ms_grid * L.nsets;
+    if(2 * p->dev.F > 255) slk_ms_step_kernel<true><<<grid, 32, p->ms_step_smem, c->stream>>>(L);
+    else slk_ms_step_kernel<false><<<grid, 32, p->ms_step_smem, c->stream>>>(L);
 }
 
 static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
@@ -692,7 +713,8 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1) {
         L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
         L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) m1;
     }
-    ms_launch_likelihood(c, L);
+    if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
+    else ms_launch_step(c, L);
     CU(cudaGetLastError());
     slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
     CU(cudaGetLastError());
@@ -818,7 +840,7 @@ int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long
         rc = slk_msampler_reset(c);
         if(rc != SLK_OK) return rc;
     }
-    ms_launch_likelihood(c, L);
+    ms_launch_step(c, L);
     CU(cudaGetLastError());
     if(meiosis0 != meiosis1) {
         // the chain kernel's stamps go to rows 12.. (CTA 0) and 15.. (last CTA) of the same buffer
@@ -851,10 +873,13 @@ int slk_debug_msampler_launch(slk_chain* c, int meiosis0, int meiosis1, int whic
     L.step_person[0] = p0; L.step_parent[0] = a0; L.step_slot[0] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis0;
     L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) meiosis1;
     if(which == 0) {
-        for(int r = 0; r < reps; ++r) ms_launch_likelihood(c, L);
+        for(int r = 0; r < reps; ++r) ms_launch_step(c, L);
+    }
+    else if(which == 2) {
+        for(int r = 0; r < reps; ++r) ms_launch_likelihood(c, L);      // the full (non-incremental) kernel
     }
     else {
-        ms_launch_likelihood(c, L);                    // the chain kernel needs this pair's likelihoods
+        ms_launch_step(c, L);                          // the chain kernel needs this pair's likelihoods
         for(int r = 0; r < reps; ++r) {
             L.iteration = (uint64_t) r;
             slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);

@@ -70,6 +70,8 @@ struct SlkMsLaunch {
     double* lnl;                 // [3][M] ln likelihood under each hypothesis of the launch
     uint8_t* bits;               // [2][M] current value of the indicator of step 0 / step 1 at each locus
     double* fb;                  // [M][2] forward matrix of step 0 (parity dump; write-only for the kernels)
+    void* te;                    // [nt][M] label pairs of the typed people in the current graph (u16, wide: u32)
+    uint32_t* stale;             // [M][W] te slots (2k + parent) whose entry is out of date at that locus
     int* err;
     // likelihood kernel: hypotheses.  set s flips set_n[s] indicators; a set with no flip writes lncur.
     int nsets;
@@ -170,136 +172,13 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
 // fa entry (u16): bits 0..11 component + 1 (0 = none), bit 14 / 15 = candidate allele under
 // assignment 0 / 1 is HOMOZ_B (in the frame of that component).
 
-template<bool WIDE>
-__global__ void __launch_bounds__(32)
-slk_ms_likelihood_kernel(const SlkMsLaunch L) {
-    extern __shared__ __align__(16) unsigned char ms_smem[];
-    const int N = L.N, F = L.F, M = L.M, nt = L.ms.n_typed;
-    const MsLayout lay = slk_ms_layout(N, F, nt);
-    const uint32_t t = threadIdx.x;
-    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
-    if(tr) tr[0] = clock64();
-
-    // the phase A and phase C tables overlay each other ACROSS the lanes of the warp, so the phases are
-    // separated by __syncwarp()
-    MsLane ln;
-    ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
-    const uint32_t o_te = lay.te * 32u, o_obs = lay.obs * 32u, o_ov = lay.ov * 32u;
-    const uint32_t o_lab = o_ov + lay.lab * 32u, o_row = o_ov + lay.row * 32u;
-    const uint32_t o_grp = o_ov + lay.grp * 32u, o_cnt = o_ov + lay.cnt * 32u, o_fa = o_ov + lay.fa * 32u;
-
-    // byte offset (inside the lane-interleaved label array) of the label PAIR of non-founder p: the two
-    // labels are adjacent (narrow: two bytes of one 16-bit half-word; wide: one 32-bit word)
-#define PAIR_OFF(p) (WIDE ? ln_a16_off(2u * (uint32_t)((p) - F)) : ln_a8_off(2u * (uint32_t)((p) - F)))
-    auto ln_a8_off = [](uint32_t k) -> uint32_t { return ((k & ~3u) << 5) | (k & 3u); };
-    auto ln_a16_off = [](uint32_t k) -> uint32_t { return ((k & ~1u) << 6) | ((k & 1u) << 1); };
-
-    // CTA-shared tables, built once per warp: for the k-th non-founder in topological order
-    //   x = person << 16 | offset of its graph-row byte, y = offset of its label pair,
-    //   z / w = mother's / father's label-pair offset, or 0x80000000 | 2 * parent for a founder parent;
-    // for the k-th typed person its label-pair offset or 0x80000000 | 2 * person
-    uint4* s_rec = (uint4*) ms_smem;                       // [N-F]
-    uint32_t* s_trec = (uint32_t*)(s_rec + (N - F));       // [nt]
-    uint8_t* s_auto = (uint8_t*)(s_trec + nt);             // [nt] x-linked male: maternal allele only
-    for(int k = t; k < N - F; k += 32) {
-        const int i = L.ms.seq[k], mo = L.mother[i], fa = L.father[i];
-        uint4 r;
-        r.x = ((uint32_t) i << 16) | ln_a8_off((uint32_t) i);
-        r.y = PAIR_OFF(i);
-        r.z = mo < F ? (0x80000000u | (uint32_t)(2 * mo)) : PAIR_OFF(mo);
-        r.w = fa < F ? (0x80000000u | (uint32_t)(2 * fa)) : PAIR_OFF(fa);
-        s_rec[k] = r;
-    }
-    for(int k = t; k < nt; k += 32) {
-        const int p = L.ms.typed[k];
-        s_trec[k] = p < F ? (0x80000000u | (uint32_t)(2 * p)) : PAIR_OFF(p);
-        s_auto[k] = (L.sex_linked && L.male[p]) ? 1 : 0;
-    }
-    __syncwarp();
-
-    const int nblk = (M + 31) >> 5;
-    const int set = blockIdx.x / nblk;
-    const int l = (blockIdx.x - set * nblk) * 32 + (int) t;
-    const bool live = l < M;
-    const int nflip = L.set_n[set];
-    const int p0 = nflip > 0 ? L.set_person[set][0] : -1, a0 = L.set_parent[set][0];
-    const int p1 = nflip > 1 ? L.set_person[set][1] : -1, a1 = L.set_parent[set][1];
-
+// The walk over the typed people (founder_allele_graph4.cc:34-424) shared by the two likelihood kernels.
+// `src.next(k, g, mat, pat)` supplies the k-th typed person's observed genotype and founder-allele labels.
 #define FA_LD(k)      ms_ld16(ln.a16(o_fa, (k)))
 #define FA_ST(k, v)   ms_st16(ln.a16(o_fa, (k)), (v))
-
-    if(tr) tr[1] = clock64();
-    // ---- phase A: labels -----------------------------------------------------------------------
-    if(live) {
-        const uint8_t* row = L.dgp + (size_t) l * N;
-        if(((N | (int)(size_t) L.dgp) & 3) == 0) {
-            const uint32_t* row4 = (const uint32_t*) row;
-            for(int i = F >> 2; i < (N >> 2); ++i) ms_st32(ln.a32(o_row, i), __ldg(row4 + i));
-        }
-        else {
-            for(int i = F; i < N; ++i) ms_st8(ln.a8(o_row, i), row[i]);
-        }
-        // observed genotypes of the typed people ([nt][M] in global memory: coalesced over the lanes),
-        // sixteen independent loads in flight, packed two bits each
-        {
-            const uint8_t* obs = L.ms.obsT + l;
-            for(int w = 0; w * 16 < nt; ++w) {
-                uint32_t acc = 0;
-#pragma unroll
-                for(int j = 0; j < 16; ++j) {
-                    const int k = w * 16 + j;
-                    if(k < nt) acc |= (uint32_t) __ldg(obs + (size_t) k * M) << (2 * j);
-                }
-                ms_st32(ln.a32(o_obs, w), acc);
-            }
-        }
-        if(tr) tr[2] = clock64();
-        const uint32_t lab_base = ln.base + o_lab, row_base = ln.base + o_row;
-        for(int k = 0; k < N - F; ++k) {
-            const uint4 r = s_rec[k];
-            const int i = (int)(r.x >> 16);
-            uint32_t b = ms_ld8(row_base + (r.x & 0xffffu));
-            if(i == p0) {
-                if(set < 2) L.bits[(size_t) set * M + l] = (uint8_t)((b >> a0) & 1u);
-                b ^= (1u << a0);
-            }
-            if(i == p1) b ^= (1u << a1);
-            const uint32_t bm = b & 1u, bf = (b >> 1) & 1u;
-            uint32_t m, f;
-            if(WIDE) {
-                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld16(lab_base + r.z + 2u * bm);
-                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld16(lab_base + r.w + 2u * bf);
-                ms_st32(lab_base + r.y, m | (f << 16));
-            }
-            else {
-                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld8(lab_base + r.z + bm);
-                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld8(lab_base + r.w + bf);
-                ms_st16(lab_base + r.y, m | (f << 8));
-            }
-        }
-        if(L.dump_edges && set == 0) {
-            int32_t* e = L.dump_edges + (size_t) l * 2 * N;
-            for(int i = 0; i < 2 * F; ++i) e[i] = i;
-            for(int i = 2 * F; i < 2 * N; ++i)
-                e[i] = (int32_t)(WIDE ? ms_ld16(ln.a16(o_lab, i - 2 * F)) : ms_ld8(ln.a8(o_lab, i - 2 * F)));
-        }
-        if(tr) tr[3] = clock64();
-        // ---- phase B: keep the typed people's label pairs ------------------------------------------
-        for(int k = 0; k < nt; ++k) {
-            const uint32_t c = s_trec[k];
-            if(WIDE) {
-                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffffu) | (((c & 0xffffu) + 1u) << 16)) : ms_ld32(lab_base + c);
-                ms_st32(ln.a16(o_te, 2 * k), v);
-            }
-            else {
-                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffu) | (((c & 0xffu) + 1u) << 8)) : ms_ld16(lab_base + c);
-                ms_st16(ln.a8(o_te, 2 * k), v);
-            }
-        }
-    }
-    __syncwarp();                                      // every lane is done with its labels
-    if(tr) tr[4] = clock64();
-    if(!live) return;
+template<bool WIDE, class Src>
+__device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint32_t o_cnt, uint32_t o_fa, int F, int nt,
+                                          const uint8_t* s_auto, Src& src, double lnM, double lnm, long long* tr) {
     for(int i = 0; i < F; ++i) ms_st32(ln.a32(o_fa, i), 0u);           // two u16 entries per word
 
     // ---- phase C: founder_allele_graph4.cc:34-424 ---------------------------------------------------
@@ -338,14 +217,10 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
 
     int ngroups = 0;
     bool dead = false;
-    uint32_t gw = 0;
     for(int k = 0; k < nt && !dead; ++k) {
-        if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
-        const uint32_t g = (gw >> (2 * (k & 15))) & 3u;
+        uint32_t g, mat, pat;
+        src.next(k, g, mat, pat);
         if(g == SLK_UNTYPED) continue;
-        uint32_t mat, pat;
-        if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
-        else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
         const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
         const bool het = g == SLK_HETERO;
         const uint32_t em = FA_LD(mat);
@@ -495,7 +370,6 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     if(tr) tr[5] = clock64();
     double ret = -INFINITY;
     if(!dead) {
-        const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
         // an unfixed component contributes p0 + p1 = M^a m^b + M^b m^a = M^hi' m^lo' (1 + rho^|a-b|) with
         // rho = min(m/M, M/m) <= 1 and (hi', lo') the exponents of the larger term: the exponents are summed as
         // integers, the (1 + rho^k) factors (each in (1, 2]) multiplied up and logged once
@@ -521,12 +395,314 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
         ret = ((double) A * lnM + (double) B * lnm) + log(prod);
         if(!(ret > -1e290)) ret = -INFINITY;               // a zero allele frequency entered the product
     }
+    return ret;
+}
+#undef FA_LD
+#undef FA_ST
+
+template<bool WIDE>
+__global__ void __launch_bounds__(32)
+slk_ms_likelihood_kernel(const SlkMsLaunch L) {
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    const int N = L.N, F = L.F, M = L.M, nt = L.ms.n_typed;
+    const MsLayout lay = slk_ms_layout(N, F, nt);
+    const uint32_t t = threadIdx.x;
+    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
+    if(tr) tr[0] = clock64();
+
+    // the phase A and phase C tables overlay each other ACROSS the lanes of the warp, so the phases are
+    // separated by __syncwarp()
+    MsLane ln;
+    ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
+    const uint32_t o_te = lay.te * 32u, o_obs = lay.obs * 32u, o_ov = lay.ov * 32u;
+    const uint32_t o_lab = o_ov + lay.lab * 32u, o_row = o_ov + lay.row * 32u;
+    const uint32_t o_grp = o_ov + lay.grp * 32u, o_cnt = o_ov + lay.cnt * 32u, o_fa = o_ov + lay.fa * 32u;
+
+    // byte offset (inside the lane-interleaved label array) of the label PAIR of non-founder p: the two
+    // labels are adjacent (narrow: two bytes of one 16-bit half-word; wide: one 32-bit word)
+#define PAIR_OFF(p) (WIDE ? ln_a16_off(2u * (uint32_t)((p) - F)) : ln_a8_off(2u * (uint32_t)((p) - F)))
+    auto ln_a8_off = [](uint32_t k) -> uint32_t { return ((k & ~3u) << 5) | (k & 3u); };
+    auto ln_a16_off = [](uint32_t k) -> uint32_t { return ((k & ~1u) << 6) | ((k & 1u) << 1); };
+
+    // CTA-shared tables, built once per warp: for the k-th non-founder in topological order
+    //   x = person << 16 | offset of its graph-row byte, y = offset of its label pair,
+    //   z / w = mother's / father's label-pair offset, or 0x80000000 | 2 * parent for a founder parent;
+    // for the k-th typed person its label-pair offset or 0x80000000 | 2 * person
+    uint4* s_rec = (uint4*) ms_smem;                       // [N-F]
+    uint32_t* s_trec = (uint32_t*)(s_rec + (N - F));       // [nt]
+    uint8_t* s_auto = (uint8_t*)(s_trec + nt);             // [nt] x-linked male: maternal allele only
+    for(int k = t; k < N - F; k += 32) {
+        const int i = L.ms.seq[k], mo = L.mother[i], fa = L.father[i];
+        uint4 r;
+        r.x = ((uint32_t) i << 16) | ln_a8_off((uint32_t) i);
+        r.y = PAIR_OFF(i);
+        r.z = mo < F ? (0x80000000u | (uint32_t)(2 * mo)) : PAIR_OFF(mo);
+        r.w = fa < F ? (0x80000000u | (uint32_t)(2 * fa)) : PAIR_OFF(fa);
+        s_rec[k] = r;
+    }
+    for(int k = t; k < nt; k += 32) {
+        const int p = L.ms.typed[k];
+        s_trec[k] = p < F ? (0x80000000u | (uint32_t)(2 * p)) : PAIR_OFF(p);
+        s_auto[k] = (L.sex_linked && L.male[p]) ? 1 : 0;
+    }
+    __syncwarp();
+
+    const int nblk = (M + 31) >> 5;
+    const int set = blockIdx.x / nblk;
+    const int l = (blockIdx.x - set * nblk) * 32 + (int) t;
+    const bool live = l < M;
+    const int nflip = L.set_n[set];
+    const int p0 = nflip > 0 ? L.set_person[set][0] : -1, a0 = L.set_parent[set][0];
+    const int p1 = nflip > 1 ? L.set_person[set][1] : -1, a1 = L.set_parent[set][1];
+
+    if(tr) tr[1] = clock64();
+    // ---- phase A: labels -----------------------------------------------------------------------
+    if(live) {
+        const uint8_t* row = L.dgp + (size_t) l * N;
+        if(((N | (int)(size_t) L.dgp) & 3) == 0) {
+            const uint32_t* row4 = (const uint32_t*) row;
+            for(int i = F >> 2; i < (N >> 2); ++i) ms_st32(ln.a32(o_row, i), __ldg(row4 + i));
+        }
+        else {
+            for(int i = F; i < N; ++i) ms_st8(ln.a8(o_row, i), row[i]);
+        }
+        // observed genotypes of the typed people ([nt][M] in global memory: coalesced over the lanes),
+        // sixteen independent loads in flight, packed two bits each
+        {
+            const uint8_t* obs = L.ms.obsT + l;
+            for(int w = 0; w * 16 < nt; ++w) {
+                uint32_t acc = 0;
+#pragma unroll
+                for(int j = 0; j < 16; ++j) {
+                    const int k = w * 16 + j;
+                    if(k < nt) acc |= (uint32_t) __ldg(obs + (size_t) k * M) << (2 * j);
+                }
+                ms_st32(ln.a32(o_obs, w), acc);
+            }
+        }
+        if(tr) tr[2] = clock64();
+        const uint32_t lab_base = ln.base + o_lab, row_base = ln.base + o_row;
+        for(int k = 0; k < N - F; ++k) {
+            const uint4 r = s_rec[k];
+            const int i = (int)(r.x >> 16);
+            uint32_t b = ms_ld8(row_base + (r.x & 0xffffu));
+            if(i == p0) {
+                if(set < 2) L.bits[(size_t) set * M + l] = (uint8_t)((b >> a0) & 1u);
+                b ^= (1u << a0);
+            }
+            if(i == p1) b ^= (1u << a1);
+            const uint32_t bm = b & 1u, bf = (b >> 1) & 1u;
+            uint32_t m, f;
+            if(WIDE) {
+                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld16(lab_base + r.z + 2u * bm);
+                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld16(lab_base + r.w + 2u * bf);
+                ms_st32(lab_base + r.y, m | (f << 16));
+            }
+            else {
+                m = (r.z & 0x80000000u) ? (r.z & 0xffffu) + bm : ms_ld8(lab_base + r.z + bm);
+                f = (r.w & 0x80000000u) ? (r.w & 0xffffu) + bf : ms_ld8(lab_base + r.w + bf);
+                ms_st16(lab_base + r.y, m | (f << 8));
+            }
+        }
+        if(L.dump_edges && set == 0) {
+            int32_t* e = L.dump_edges + (size_t) l * 2 * N;
+            for(int i = 0; i < 2 * F; ++i) e[i] = i;
+            for(int i = 2 * F; i < 2 * N; ++i)
+                e[i] = (int32_t)(WIDE ? ms_ld16(ln.a16(o_lab, i - 2 * F)) : ms_ld8(ln.a8(o_lab, i - 2 * F)));
+        }
+        if(tr) tr[3] = clock64();
+        // ---- phase B: keep the typed people's label pairs ------------------------------------------
+        for(int k = 0; k < nt; ++k) {
+            const uint32_t c = s_trec[k];
+            if(WIDE) {
+                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffffu) | (((c & 0xffffu) + 1u) << 16)) : ms_ld32(lab_base + c);
+                ms_st32(ln.a16(o_te, 2 * k), v);
+            }
+            else {
+                const uint32_t v = (c & 0x80000000u) ? ((c & 0xffu) | (((c & 0xffu) + 1u) << 8)) : ms_ld16(lab_base + c);
+                ms_st16(ln.a8(o_te, 2 * k), v);
+            }
+        }
+    }
+    __syncwarp();                                      // every lane is done with its labels
+    if(!live) return;
+    double ret;
+    {
+        struct SmemSource {
+            const MsLane& ln; uint32_t o_te, o_obs; uint32_t gw;
+            __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+                if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
+                g = (gw >> (2 * (k & 15))) & 3u;
+                if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
+                else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
+            }
+        } src = { ln, o_te, o_obs, 0u };
+        if(tr) tr[4] = clock64();
+        ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
+    }
+    if(nflip == 0 && L.te) {
+        // reset: publish the typed people's label pairs of the current graph (the incremental step kernel
+        // reads them) and clear the locus's stale mask
+        for(int k = 0; k < nt; ++k) {
+            if(WIDE) ((uint32_t*) L.te)[(size_t) k * M + l] = ms_ld32(ln.a16(o_te, 2 * k));
+            else     ((uint16_t*) L.te)[(size_t) k * M + l] = (uint16_t) ms_ld16(ln.a8(o_te, 2 * k));
+        }
+        for(int w = 0; w < L.ms.W; ++w) L.stale[(size_t) l * L.ms.W + w] = 0u;
+    }
     if(nflip == 0) L.lncur[l] = ret;
     else L.lnl[(size_t) set * M + l] = ret;
     if(tr) tr[6] = clock64();
-#undef FA_LD
-#undef FA_ST
 #undef PAIR_OFF
+}
+
+// ---- (1b) the same likelihood, incrementally: only the labels a hypothesis can change are recomputed ------
+//
+// Between two steps of a sweep the graph changes by one indicator per locus at most, and flipping the
+// indicator of person P can only change the labels of P's own slot and of slots below P.  The chain keeps
+// the typed people's label pairs of the CURRENT graph in global memory (te[nt][M], written by the full
+// kernel at the start of a sweep).  A hypothesis thread reads them (one person ahead of their use, coalesced
+// over the lanes) and re-derives a label only where the hypothesis's slot mask says so, by walking the
+// lineage up the graph row to a founder (a handful of byte loads).  The slot mask is
+//     below(P_0) | below(P_1) | own slots | stale[l],
+// where stale[l] collects the slots invalidated by indicators the chain kernel has flipped at this locus since
+// te was last brought up to date; the set-0 thread of the locus writes those entries back at the end of its
+// work and the chain kernel clears the mask before it records new flips.  No per-thread label array, no
+// graph-row or genotype staging: 21 KB of shared memory per warp instead of 31.
+struct MsStepLayout {
+    int wide, G;
+    uint32_t grp, cnt, fa, hmask;    // per-thread byte offsets (multiply by 32 lanes)
+    uint32_t per_thread, cta_tables;
+};
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline MsStepLayout slk_ms_step_layout(int N, int F, int nt, int W) {
+    MsStepLayout L;
+    L.wide = (2 * F > 255) ? 1 : 0;
+    L.G = nt < 2 * F ? nt : 2 * F;
+    if(L.G < 1) L.G = 1;
+    L.grp = 0;
+    L.cnt = L.grp + 4u * L.G;
+    L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
+    L.hmask = L.fa + ((4u * F + 3u) & ~3u);
+    L.per_thread = L.hmask + 4u * W;
+    L.cta_tables = ((uint32_t)(4 * N + 2 * nt + nt + 8) + 7u) & ~7u;
+    return L;
+}
+
+template<bool WIDE>
+__global__ void __launch_bounds__(32)
+slk_ms_step_kernel(const SlkMsLaunch L) {
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    const int N = L.N, F = L.F, M = L.M, nt = L.ms.n_typed, W = L.ms.W;
+    const MsStepLayout lay = slk_ms_step_layout(N, F, nt, W);
+    const uint32_t t = threadIdx.x;
+    long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
+    if(tr) tr[0] = clock64();
+
+    int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
+    int16_t* s_fa = s_mo + N;                              // [N]
+    uint16_t* s_typed = (uint16_t*)(s_fa + N);             // [nt]
+    uint8_t* s_auto = (uint8_t*)(s_typed + nt);            // [nt]
+    for(int i = t; i < N; i += 32) { s_mo[i] = L.mother[i]; s_fa[i] = L.father[i]; }
+    for(int k = t; k < nt; k += 32) {
+        const int p = L.ms.typed[k];
+        s_typed[k] = (uint16_t) p;
+        s_auto[k] = (L.sex_linked && L.male[p]) ? 1 : 0;
+    }
+    __syncwarp();
+
+    const int nblk = (M + 31) >> 5;
+    const int set = blockIdx.x / nblk;
+    const int l = (blockIdx.x - set * nblk) * 32 + (int) t;
+    if(l >= M) return;
+    const int nflip = L.set_n[set];
+    const int p0 = nflip > 0 ? L.set_person[set][0] : -1, a0 = L.set_parent[set][0];
+    const int p1 = nflip > 1 ? L.set_person[set][1] : -1, a1 = L.set_parent[set][1];
+
+    MsLane ln;
+    ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
+    const uint32_t o_grp = lay.grp * 32u, o_cnt = lay.cnt * 32u, o_fa = lay.fa * 32u, o_hm = lay.hmask * 32u;
+    const uint8_t* row = L.dgp + (size_t) l * N;
+
+    // the hypothesis's slot mask
+    for(int w = 0; w < W; ++w) {
+        uint32_t h = L.stale[(size_t) l * W + w];
+        if(p0 >= 0) h |= L.ms.desc_mask[(size_t)(p0 - F) * W + w];
+        if(p1 >= 0) h |= L.ms.desc_mask[(size_t)(p1 - F) * W + w];
+        ms_st32(ln.a32(o_hm, w), h);
+    }
+    if(p0 >= 0) {
+        const int k0 = L.ms.typed_index[p0];
+        if(k0 >= 0) { const uint32_t q = 2 * k0 + a0; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
+        if(set < 2) L.bits[(size_t) set * M + l] = (uint8_t)((row[p0] >> a0) & 1u);
+    }
+    if(p1 >= 0) {
+        const int k1 = L.ms.typed_index[p1];
+        if(k1 >= 0) { const uint32_t q = 2 * k1 + a1; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
+    }
+
+    struct StepSource {
+        const MsLane& ln; uint32_t o_hm; const uint8_t* row; const int16_t* s_mo; const int16_t* s_fa; const uint16_t* s_typed;
+        const void* te; const uint8_t* obs; int M, l, F, nt, p0, a0, p1, a1;
+        uint32_t hw;
+        uint32_t qp[4], qg[4];           // the next four typed people's label pairs / genotypes, in flight
+        // founder allele reached from slot `sl` of `person` by following the indicators of the graph row
+        __device__ __forceinline__ uint32_t trace(int person, uint32_t sl, bool flips) const {
+            int cur = person;
+            while(cur >= F) {
+                uint32_t b = row[cur];
+                if(flips) { if(cur == p0) b ^= 1u << a0; if(cur == p1) b ^= 1u << a1; }
+                const uint32_t nb = (b >> sl) & 1u;
+                cur = sl ? s_fa[cur] : s_mo[cur];
+                sl = nb;
+            }
+            return (uint32_t)(2 * cur) + sl;
+        }
+        __device__ __forceinline__ void fetch(int k, int slot) {
+            if(k < nt) {
+                qp[slot] = WIDE ? ((const uint32_t*) te)[(size_t) k * M + l] : (uint32_t)((const uint16_t*) te)[(size_t) k * M + l];
+                qg[slot] = obs[(size_t) k * M];
+            }
+        }
+        __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+            // a four-deep queue in registers (shifted, so every index is a compile-time constant)
+            const uint32_t pair = qp[0];
+            g = qg[0];
+            qp[0] = qp[1]; qg[0] = qg[1]; qp[1] = qp[2]; qg[1] = qg[2]; qp[2] = qp[3]; qg[2] = qg[3];
+            fetch(k + 4, 3);
+            if((k & 15) == 0) hw = ms_ld32(ln.a32(o_hm, k >> 4));
+            const uint32_t m2 = (hw >> (2 * (k & 15))) & 3u;
+            mat = WIDE ? (pair & 0xffffu) : (pair & 0xffu);
+            pat = WIDE ? (pair >> 16) : (pair >> 8);
+            if(m2 && g != SLK_UNTYPED) {
+                const int person = s_typed[k];
+                if(m2 & 1u) mat = trace(person, 0u, true);
+                if(m2 & 2u) pat = trace(person, 1u, true);
+            }
+        }
+    } src = { ln, o_hm, row, s_mo, s_fa, s_typed, L.te, L.ms.obsT + l, M, l, F, nt, p0, a0, p1, a1, 0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
+    src.fetch(0, 0); src.fetch(1, 1); src.fetch(2, 2); src.fetch(3, 3);
+    if(tr) tr[4] = clock64();
+    const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
+    L.lnl[(size_t) set * M + l] = ret;
+
+    // bring the locus's out-of-date entries up to date (current graph: no hypothetical flips)
+    if(set == 0) {
+        for(int w = 0; w < W; ++w) {
+            uint32_t st = L.stale[(size_t) l * W + w];
+            while(st) {
+                const uint32_t q = 32u * w + (uint32_t) __ffs(st) - 1u;
+                st &= st - 1u;
+                const uint32_t k = q >> 1, sl = q & 1u;
+                const uint32_t lab = src.trace(s_typed[k], sl, false);
+                if(WIDE) ((uint16_t*) L.te)[2 * ((size_t) k * M + l) + sl] = (uint16_t) lab;
+                else     ((uint8_t*) L.te)[2 * ((size_t) k * M + l) + sl] = (uint8_t) lab;
+            }
+        }
+    }
+    if(tr) tr[6] = clock64();
 }
 
 // ---- (2) + (3): forward pass and backward sampling along the chromosome ------------------------------
@@ -605,9 +781,11 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
 
     long long* tr = (L.trace && t == 0 && (rank == 0 || rank == SLK_MS_CLUSTER - 1)) ? L.trace + (rank ? 24 : 0) : 0;
     if(tr) tr[0] = clock64();
+    const int W = L.ms.W;
     for(int i = cta_lo + t; i < cta_hi; i += T) {
         s_lncur[i - cta_lo] = L.lncur[i]; s_changed[i - cta_lo] = 0;
         s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
+        for(int w = 0; w < W; ++w) L.stale[(size_t) i * W + w] = 0u;       // the likelihood launch brought te up to date
     }
     const double theta_hi = cta_hi < M && cta_hi > 0 ? L.theta[cta_hi - 1] : 0.5;   // interval right of the CTA's last locus
 
@@ -771,6 +949,11 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
                         *cell = (uint8_t)(*cell ^ pbit);
                         s_lncur[k] = s_lnflip[k];            // carried likelihood of the (new) current graph
                         if(step == 0) s_changed[k] = 1;
+                        // the typed people's labels below this meiosis are now out of date at this locus
+                        const int P = L.step_person[step];
+                        for(int w = 0; w < W; ++w) L.stale[(size_t) i * W + w] |= L.ms.desc_mask[(size_t)(P - L.F) * W + w];
+                        const int k0 = L.ms.typed_index[P];
+                        if(k0 >= 0) { const uint32_t q = 2 * k0 + L.step_parent[step]; L.stale[(size_t) i * W + (q >> 5)] |= 1u << (q & 31); }
                     }
                 }
             }

@@ -519,6 +519,35 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
             hp.ms_lnmajor[l] = mj > 0.0 ? log(mj) : -1e300;
             hp.ms_lnminor[l] = mn > 0.0 ? log(mn) : -1e300;
         }
+        // slot masks for the incremental step kernel: slot 2k + s of typed person k is "below" person P if its
+        // lineage can pass through P, i.e. parent_s(typed[k]) is P or a descendant of P
+        {
+            hp.ms_W = std::max(1, (2 * nt + 31) / 32);
+            hp.ms_typed_index.assign(N, -1);
+            for(int k = 0; k < nt; ++k) hp.ms_typed_index[hp.ms_typed[k]] = (int16_t) k;
+            // anc[i] = set of ancestors-or-self of i among non-founders, as a bit matrix (N-F columns)
+            const int NF = N - F, AW = (NF + 31) / 32;
+            std::vector<uint32_t> anc((size_t) N * AW, 0u);
+            for(size_t q = 0; q < hp.ms_seq.size(); ++q) {
+                const int i = hp.ms_seq[q];
+                uint32_t* a = &anc[(size_t) i * AW];
+                a[(i - F) >> 5] |= 1u << ((i - F) & 31);
+                const int par[2] = { pb.mother[i], pb.father[i] };
+                for(int s = 0; s < 2; ++s) if(par[s] >= F) for(int w = 0; w < AW; ++w) a[w] |= anc[(size_t) par[s] * AW + w];
+            }
+            hp.ms_desc_mask.assign((size_t) std::max(NF, 1) * hp.ms_W, 0u);
+            for(int k = 0; k < nt; ++k) {
+                const int i = hp.ms_typed[k];
+                if(i < F) continue;
+                const int par[2] = { pb.mother[i], pb.father[i] };
+                for(int s = 0; s < 2; ++s) {
+                    if(par[s] < F) continue;
+                    const uint32_t* a = &anc[(size_t) par[s] * AW];
+                    for(int P = 0; P < NF; ++P)
+                        if(a[P >> 5] & (1u << (P & 31))) hp.ms_desc_mask[(size_t) P * hp.ms_W + ((2 * k + s) >> 5)] |= 1u << ((2 * k + s) & 31);
+                }
+            }
+        }
         // markov_chain.cc:68-80 with Person::safe_to_ignore_meiosis (person.cc:208-222)
         std::vector<int> nchild(N, 0);
         for(int i = F; i < N; ++i) { nchild[pb.mother[i]]++; nchild[pb.father[i]]++; }

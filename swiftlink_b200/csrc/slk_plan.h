@@ -51,6 +51,9 @@ struct HostPlan {
     std::vector<uint8_t> ms_obsT;        // [n_typed][M]
     std::vector<double> ms_minor, ms_lnmajor, ms_lnminor;   // [M]
     std::vector<int32_t> ms_ordering;    // meioses an M-sweep visits (markov_chain.cc:68-80)
+    std::vector<uint32_t> ms_desc_mask;  // [N-F][W]
+    std::vector<int16_t> ms_typed_index; // [N]
+    int ms_W;
 };
 
 // shared-memory budget per SM the layout may assume (bytes); 227 KB on sm_100

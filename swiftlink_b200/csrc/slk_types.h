@@ -79,6 +79,9 @@ struct SlkMsPlan {
     const double* minor;            // [M] Snp::minor()
     const double* lnmajor;          // [M] ln(1 - minor) (-1e300 if the frequency is 0)
     const double* lnminor;          // [M] ln(minor)
+    const uint32_t* desc_mask;      // [N-F][W] te slots (2k + parent) whose lineage can pass through that person
+    const int16_t* typed_index;     // [N] index into typed[] or -1
+    int W;                          // words per slot mask = ceil(2 n_typed / 32)
     int n_typed;
     int available;                  // slk_problem.minor_freq was given
 };

@@ -62,11 +62,10 @@ def main():
             st = tr.ravel()[base:base + 17]
             print("chain kernel %s cycles [stage, product, cta scan, cluster sync, recurrence, map scans, apply, sync] x 2 steps: %s  total %d" %
                   (nm, np.diff(st).tolist(), int(st[-1] - st[0])))
-        print("likelihood kernel cycles per phase [tables, genotypes, labels, keep, (sync), walk, finish] for sampled warps:")
-        for row in d:
-            if row.min() >= 0 and row.sum() > 0:
-                print("   ", row.tolist(), "total", int(row.sum()))
-
+        print("step kernel cycles [prologue (tables, slot mask), walk, finish + write-back] for sampled warps:")
+        for row in tr[:12]:
+            if row[0] > 0 and row[6] > 0:
+                print("   ", [int(row[4] - row[0]), int(row[5] - row[4]), int(row[6] - row[5])], "total", int(row[6] - row[0]))
     if args.trace and args.sweeps:
         import numpy as np
         st = plan.stats()
