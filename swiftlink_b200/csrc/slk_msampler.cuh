@@ -625,7 +625,6 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
     const uint32_t o_grp = lay.grp * 32u, o_cnt = lay.cnt * 32u, o_fa = lay.fa * 32u, o_hm = lay.hmask * 32u;
     const uint8_t* row = L.dgp + (size_t) l * N;
-
     // the hypothesis's slot mask
     for(int w = 0; w < W; ++w) {
         uint32_t h = L.stale[(size_t) l * W + w];
@@ -652,7 +651,8 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         __device__ __forceinline__ uint32_t trace(int person, uint32_t sl, bool flips) const {
             int cur = person;
             while(cur >= F) {
-                uint32_t b = row[cur];
+                uint32_t b = row[cur];           // L1-resident after the first touch (staging the row in shared memory
+                                                 // costs more in the prologue than these few reads save)
                 if(flips) { if(cur == p0) b ^= 1u << a0; if(cur == p1) b ^= 1u << a1; }
                 const uint32_t nb = (b >> sl) & 1u;
                 cur = sl ? s_fa[cur] : s_mo[cur];
@@ -667,7 +667,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
             }
         }
         __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
-            // a four-deep queue in registers (shifted, so every index is a compile-time constant)
+            // a four-deep ring in registers: slot k & 3 is consumed and refilled for person k + 4, so a loaded
+            // value is first touched four people later (the switch keeps every index a compile-time constant)
+            // a four-deep queue in registers (shifted, so every index is a compile-time constant; a ring
+            // indexed by k & 3 through a switch measured 35 % slower: four copies of the body)
             const uint32_t pair = qp[0];
             g = qg[0];
             qp[0] = qp[1]; qg[0] = qg[1]; qp[1] = qp[2]; qg[1] = qg[2]; qp[2] = qp[3]; qg[2] = qg[3];
