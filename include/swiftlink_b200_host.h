@@ -63,6 +63,13 @@ int slk_host_write_results(slk_host* h, const char* filename, const double* lod)
 int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int burnin, int iterations,
                        int scoring_period, double lsampler_prob, int32_t* dg, double* lod_out, double* trait_prob_out);
 
+/* the -R replicate loop of LinkageProgram::run_pedigree (linkage_program.cc:96-108): `runs` independent chains
+   (chain ids 0..runs-1, each started from its own sequential-imputation state), up to `in_flight` of them resident
+   on the device at once, each on its own stream; lod_out[(M-1)*n_lod] receives the normalised LOD scores of the
+   merged table (LODscores::merge_results in replicate order).  The result does not depend on in_flight. */
+int slk_host_run_replicates(slk_host* h, int device, uint64_t seed, int runs, int in_flight, int burnin, int iterations,
+                            int scoring_period, double lsampler_prob, int si_iterations, double* lod_out);
+
 /* Mc3::run (mc3.cc:81-200, see swiftlink_b200/csrc/host/mc3.cc for the specified behaviour): a ladder
    of n_chains heated chains on one device, temperatures NULL = the reference's ladder
    1 / (1 + 0.001 * 2^i); swap_success / swap_failure [n_chains] receive the exchange counts of each

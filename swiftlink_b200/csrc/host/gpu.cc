@@ -5,6 +5,7 @@
 // in one process, one per GPU.
 #include "swiftlink_host.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cfloat>
@@ -54,7 +55,7 @@ void GPULodscores::get_results(LODscores* lod) {
 GPUMarkovChain::GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options,
                                int sequence_num, double temperature) :
     ped(ped), map(map), psg(psg), options(options), heated(*map), temperature(temperature), plan(0), chain(0),
-    seq_num(sequence_num), trait_prob(0.0), scoring_started(false) {
+    seq_num(sequence_num), trait_prob(0.0), scoring_started(false), coda(0) {
     // MarkovChain::_init: "heat up the map" (markov_chain.cc:33-34).  Thetas and allele frequencies move
     // towards 0.5; the genotype priors cached per person stay cold, as in the reference (Snp::prob is
     // not recomputed by set_minor_freq, genetic_map.h:43-47)
@@ -159,9 +160,13 @@ LODscores* GPUMarkovChain::get_result() {
 // (:351-361); optional CODA trace of the graph likelihood at the scored iterations (:362-370).
 // The graph never leaves the device between sweeps (the reference's GPU chain copies it back and
 // forth for every M-sweep, gpu_markov_chain.cc:1199-1210).
-LODscores* GPUMarkovChain::run(DescentGraph& dg) {
-    LODscores* lod = new LODscores(map);
-    const double trait_prob = calc_trait_prob();
+//
+// The loop is split into begin / iterate / finish so that a caller can keep several replicate chains
+// in flight on one device: every call only enqueues work on the chain's own stream (the CODA trace is
+// the one exception), and a chain's draws are keyed by (seed, chain id, iteration), so interleaving
+// chains changes nothing in their results.
+void GPUMarkovChain::begin(DescentGraph& dg) {
+    trait_prob = calc_trait_prob();
     printf("P(T) = %.5f\n", trait_prob / log(10.0));
     die_on(slk_dg_upload(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (upload)");
     const bool need_fag = options.lsampler_prob < 1.0 || options.coda_logging;
@@ -173,7 +178,7 @@ LODscores* GPUMarkovChain::run(DescentGraph& dg) {
             abort();
         }
     }
-    FILE* coda = 0;
+    coda = 0;
     if(options.coda_logging) {
         char buf[16];
         snprintf(buf, sizeof(buf), "%d", seq_num);
@@ -184,25 +189,30 @@ LODscores* GPUMarkovChain::run(DescentGraph& dg) {
         printf("opened trace file (%s)\n", fname.c_str());
     }
     die_on(slk_lodscore_init(chain), "GPUMarkovChain::run (init)");
-    const int total = options.iterations + options.burnin;
-    for(int i = 0; i < total; ++i) {
-        if(slk_sweep_is_lsampler(chain, (uint64_t) i, options.lsampler_prob))
-            die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (L-sampler)");
-        else
-            die_on(slk_msampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (M-sampler)");
-        if(i < options.burnin) continue;
-        if((i % options.scoring_period) == 0) {
-            if(coda) {
-                double lik = 0.0;
-                die_on(slk_dg_likelihood(chain, &lik), "GPUMarkovChain::run (trace)");
-                if(lik == LOG_ILLEGAL) { fprintf(stderr, "error: descent graph illegal...\n"); abort(); }
-                fprintf(coda, "%d\t%f\n", i + 1, lik);
-            }
-            die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::run (scoring)");
+    scoring_started = true;
+}
+
+void GPUMarkovChain::iterate(int i) {
+    if(slk_sweep_is_lsampler(chain, (uint64_t) i, options.lsampler_prob))
+        die_on(slk_lsampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (L-sampler)");
+    else
+        die_on(slk_msampler_sweep(chain, (uint64_t) i), "GPUMarkovChain::run (M-sampler)");
+    if(i < options.burnin) return;
+    if((i % options.scoring_period) == 0) {
+        if(coda) {
+            double lik = 0.0;
+            die_on(slk_dg_likelihood(chain, &lik), "GPUMarkovChain::run (trace)");
+            if(lik == LOG_ILLEGAL) { fprintf(stderr, "error: descent graph illegal...\n"); abort(); }
+            fprintf(coda, "%d\t%f\n", i + 1, lik);
         }
+        die_on(slk_lodscore_accumulate(chain), "GPUMarkovChain::run (scoring)");
     }
-    if(coda) fclose(coda);
+}
+
+LODscores* GPUMarkovChain::finish(DescentGraph& dg) {
+    if(coda) { fclose(coda); coda = 0; }
     die_on(slk_dg_download(chain, dg.get_internal_ptr()), "GPUMarkovChain::run (download)");
+    LODscores* lod = new LODscores(map);
     std::vector<double> raw(lod->num_lodscores());
     int32_t count = 0;
     die_on(slk_lodscore_read(chain, raw.data(), &count), "GPUMarkovChain::run (results)");
@@ -210,6 +220,45 @@ LODscores* GPUMarkovChain::run(DescentGraph& dg) {
     lod->set_count((unsigned int) count);
     for(unsigned int i = 0; i < raw.size(); ++i) lod->set(i, raw[i]);
     return lod;
+}
+
+LODscores* GPUMarkovChain::run(DescentGraph& dg) {
+    begin(dg);
+    const int total = options.iterations + options.burnin;
+    for(int i = 0; i < total; ++i) iterate(i);
+    return finish(dg);
+}
+
+// LinkageProgram::run_pedigree's replicate loop (linkage_program.cc:96-108) with up to `in_flight` replicates
+// resident on the device at once.  One chain leaves most of a B200 idle during an M-sweep (its
+// likelihood kernel keeps ~6 warps per SM busy, its chain kernel 8 SMs), so the replicates of a group
+// are advanced one iteration at a time in turn, each on its own stream, and their kernels overlap.
+// Results are merged in replicate order and are bit-identical to running the replicates one by one.
+LODscores* run_replicates(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int in_flight) {
+    if(in_flight < 1) in_flight = 1;
+    LODscores* total = 0;
+    for(int r0 = 0; r0 < options.mcmc_runs; r0 += in_flight) {
+        const int n = std::min(in_flight, options.mcmc_runs - r0);
+        std::vector<GPUMarkovChain*> chains;
+        std::vector<DescentGraph*> dgs;
+        for(int k = 0; k < n; ++k) {
+            dgs.push_back(new DescentGraph(ped, map, options.sex_linked));
+            chains.push_back(new GPUMarkovChain(ped, map, psg, options, r0 + k));
+            chains[k]->sequential_imputation(*dgs[k], options.si_iterations);
+        }
+        for(int k = 0; k < n; ++k) chains[k]->begin(*dgs[k]);
+        const int iters = options.iterations + options.burnin;
+        for(int i = 0; i < iters; ++i)
+            for(int k = 0; k < n; ++k) chains[k]->iterate(i);
+        for(int k = 0; k < n; ++k) {
+            LODscores* lod = chains[k]->finish(*dgs[k]);
+            if(!total) total = lod;
+            else { total->merge_results(lod); delete lod; }
+            delete chains[k];
+            delete dgs[k];
+        }
+    }
+    return total;
 }
 
 }  // namespace swiftlink

@@ -190,6 +190,19 @@ int slk_host_run_chain(slk_host* h, int device, uint64_t seed, uint32_t chain_id
     return SLK_OK;
 }
 
+int slk_host_run_replicates(slk_host* h, int device, uint64_t seed, int runs, int in_flight, int burnin, int iterations,
+                            int scoring_period, double lsampler_prob, int si_iterations, double* lod_out) {
+    if(!h->psg || runs < 1) return SLK_ERR_INVALID;
+    struct mcmc_options o;
+    o.burnin = burnin; o.iterations = iterations; o.scoring_period = scoring_period; o.si_iterations = si_iterations;
+    o.lsampler_prob = lsampler_prob; o.sex_linked = h->dm.is_sexlinked(); o.seed = seed; o.device = device; o.mcmc_runs = runs;
+    LODscores* lod = run_replicates(h->ped, &h->map, h->psg, o, in_flight);
+    const unsigned n = h->map.get_lodscore_count();
+    for(unsigned l = 0; l + 1 < h->map.num_markers(); ++l) for(unsigned k = 0; k < n; ++k) lod_out[l * n + k] = lod->get(l, k);
+    delete lod;
+    return SLK_OK;
+}
+
 int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, int n_chains, int exchange_period,
                      const double* temperatures, int burnin, int iterations, int scoring_period, double lsampler_prob,
                      int si_iterations, double* lod_out, int32_t* swap_success, int32_t* swap_failure) {

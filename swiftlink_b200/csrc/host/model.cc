@@ -17,7 +17,7 @@ namespace swiftlink {
 mcmc_options::mcmc_options() :
     verbose(false), burnin(50000), iterations(50000), si_iterations(1000), scoring_period(10), mcmc_runs(1),
     coda_logging(false), coda_prefix("trace"), lodscores(5), peelopt_iterations(1000000), lsampler_prob(0.5),
-    thread_count(1), use_gpu(true), random_filename(""), affected_only(false), sex_linked(false),
+    thread_count(4), use_gpu(true), random_filename(""), affected_only(false), sex_linked(false),
     seed(20261017), device(0), elod(false), elod_frequency(0.0001), elod_marker_separation(0.05), elod_replicates(1000000),
     mc3(false), mc3_number_of_chains(1), mc3_exchange_period(10),
     mc3_temperatures(), exchange_filename("") {                    // defaults.h:4-24

@@ -54,7 +54,7 @@ static void usage(const char* prog) {
 "  -j FILE,    --exchangefile=FILE\n"
 "\n"
 "Runtime options:\n"
-"  -c NUM,     --cores=NUM                 (accepted, ignored: the samplers run on the GPU)\n"
+"  -c NUM,     --cores=NUM                 replicate chains (-R) in flight on the device at once (default = %d)\n"
 "  -g,         --gpu                       (always on)\n"
 "  -D NUM,     --device=NUM                CUDA device (default = 0)\n"
 "\n"
@@ -70,7 +70,7 @@ static void usage(const char* prog) {
 "\n",
     prog, prog, d.iterations, d.burnin, d.si_iterations, d.scoring_period, d.lsampler_prob, d.lodscores, d.mcmc_runs,
     d.elod_frequency, d.elod_marker_separation, d.elod_penetrance[0], d.elod_penetrance[1], d.elod_penetrance[2], d.elod_replicates,
-    d.mc3_number_of_chains, d.mc3_exchange_period, d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
+    d.mc3_number_of_chains, d.mc3_exchange_period, d.thread_count, d.peelopt_iterations, (unsigned long long) d.seed, d.coda_prefix.c_str());
 }
 
 static bool str2int(int& out, const char* s) {
@@ -218,21 +218,15 @@ int main(int argc, char** argv) {
         if(o.verbose) fprintf(stderr, "\n\n%s\n\n", psg.debug_string().c_str());
 
         LODscores* total = 0;
-        for(int r = 0; r < o.mcmc_runs; ++r) {
-            LODscores* lod;
-            if(o.mc3 && o.mc3_number_of_chains > 1) {
-                Mc3 ladder(&p, &map, &psg, o, r);                 // linkage_program.cc:169-170 (commented out upstream)
-                lod = ladder.run();
+        if(o.mc3 && o.mc3_number_of_chains > 1) {
+            for(int r = 0; r < o.mcmc_runs; ++r) {
+                Mc3 ladder(&p, &map, &psg, o, r);                     // linkage_program.cc:169-170 (commented out upstream)
+                LODscores* lod = ladder.run();
+                if(!total) total = lod;
+                else { total->merge_results(lod); delete lod; }
             }
-            else {
-                DescentGraph dg(&p, &map, dm.is_sexlinked());
-                GPUMarkovChain chain(&p, &map, &psg, o, r);
-                chain.sequential_imputation(dg, o.si_iterations);
-                lod = chain.run(dg);
-            }
-            if(!total) total = lod;
-            else { total->merge_results(lod); delete lod; }
         }
+        else total = run_replicates(&p, &map, &psg, o, o.thread_count);
         all_scores.push_back(total);
     }
     bool ok = write_linkage_results(&map, outfile, all_scores, o.verbose);

@@ -410,12 +410,18 @@ class GPUMarkovChain {
     int seq_num;
     double trait_prob;
     bool scoring_started;
+    FILE* coda;
  public:
     // temperature as in MarkovChain(ped, map, psg, options, temp) (markov_chain.h:44-70): 1.0 = cold
     GPUMarkovChain(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options,
                    int sequence_num = 0, double temperature = 1.0);
     ~GPUMarkovChain();
     LODscores* run(DescentGraph& dg);           // gpu_markov_chain.cc:991 / markov_chain.cc:314
+    // run() in three parts (every call only enqueues work on the chain's stream), so that several
+    // replicate chains can be advanced in turn and overlap on the device: see run_replicates
+    void begin(DescentGraph& dg);
+    void iterate(int i);
+    LODscores* finish(DescentGraph& dg);
     // MarkovChain::step (markov_chain.cc:107-207) on the chain's device-resident graph: step_size
     // iterations numbered from start_iteration; only the cold chain scores
     void step(int start_iteration, int step_size);
@@ -431,6 +437,10 @@ class GPUMarkovChain {
     double get_likelihood(DescentGraph& dg);    // DescentGraph::get_likelihood on the device
     slk_chain* get_chain() { return chain; }
 };
+
+// the -R replicate loop of LinkageProgram::run_pedigree (linkage_program.cc:96-108), `in_flight` chains at a time
+// on options.device; the caller owns the returned (merged) table
+LODscores* run_replicates(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int in_flight);
 
 // ---- ELOD (elod.h/.cc) ---------------------------------------------------------------------------------
 // Expected LOD of a pedigree structure by simulation: a fake map marker - trait - marker; per replicate

@@ -681,12 +681,32 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     return L;
 }
 
+// Launch with programmatic stream serialization (see ms_launch_dependents / ms_wait_for_predecessor in
+// slk_msampler.cuh): the kernel may become resident before its predecessor on the stream has finished.  Only for
+// kernels that call ms_wait_for_predecessor() before touching anything the predecessor writes.
+static void ms_launch_overlapped(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, const SlkMsLaunch& L) {
+    static const bool off = getenv("SLK_NO_PDL") != 0;               // tuning aid
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3((unsigned) threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+    void* args[1] = { (void*) &L };
+    cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
 // the incremental kernel of a sweep's steps (te and the stale masks are valid: a reset has run)
 static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
     slk_plan* p = c->plan;
     const int grid = p->ms_grid * L.nsets;
-    if(2 * p->dev.F > 255) slk_ms_step_kernel<true><<<grid, 32, p->ms_step_smem, c->stream>>>(L);
-    else slk_ms_step_kernel<false><<<grid, 32, p->ms_step_smem, c->stream>>>(L);
+    if(2 * p->dev.F > 255) ms_launch_overlapped((const void*) slk_ms_step_kernel<true>, grid, 32, p->ms_step_smem, c->stream, L);
+    else ms_launch_overlapped((const void*) slk_ms_step_kernel<false>, grid, 32, p->ms_step_smem, c->stream, L);
+}
+
+static void ms_launch_chain(slk_chain* c, const SlkMsLaunch& L) {
+    ms_launch_overlapped((const void*) slk_ms_chain_kernel, SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream, L);
 }
 
 static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
@@ -698,10 +718,13 @@ static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
 
 // one or two consecutive steps of a sweep: the second meiosis's likelihood is evaluated under both
 // outcomes of the first, so the pair costs one likelihood launch and one chain launch
-static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1) {
+// `prefix`: typed people [0, prefix) are untouched by the flips of the kernel that precedes this launch on the stream
+// (the previous pair's chain kernel); 0 when the predecessor is anything else
+static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int prefix = 0) {
     const SlkDevPlan& d = c->plan->dev;
     SlkMsLaunch L = ms_launch(c);
     L.iteration = iteration;
+    L.prefix_nt = prefix;
     const int p0 = d.F + m0 / 2, a0 = m0 % 2;
     L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
     L.nsteps = 1;
@@ -716,7 +739,7 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1) {
     if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
-    slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
+    ms_launch_chain(c, L);
     CU(cudaGetLastError());
     return SLK_OK;
 }
@@ -765,7 +788,17 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     }
     // MeiosisSampler::reset at the start of every sweep (markov_chain.cc:345)
     rc = slk_msampler_reset(c);
-    for(int j = 0; j < n && rc == SLK_OK; j += 2) rc = ms_steps(c, iteration, order[j], j + 1 < n ? order[j + 1] : -1);
+    // The likelihood walk of a pair overlaps the previous pair's chain kernel up to the first typed person whose
+    // labels that pair can change (slk_ms_step_kernel).  The first pair follows the reset kernel, which writes te.
+    const std::vector<int16_t>& first = c->plan->host.ms_first_typed;
+    static const bool no_prefix = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
+    int prefix = 0;
+    for(int j = 0; j < n && rc == SLK_OK; j += 2) {
+        const int m0 = order[j], m1 = j + 1 < n ? order[j + 1] : -1;
+        rc = ms_steps(c, iteration, m0, m1, no_prefix ? 0 : prefix);
+        prefix = first[m0];
+        if(m1 >= 0) prefix = std::min(prefix, (int) first[m1]);
+    }
     return rc;
 }
 
@@ -846,7 +879,7 @@ int slk_debug_msampler_trace(slk_chain* c, int meiosis0, int meiosis1, long long
         // the chain kernel's stamps go to rows 12.. (CTA 0) and 15.. (last CTA) of the same buffer
         SlkMsLaunch L2 = L;
         L2.trace = dev + 96;
-        slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L2);
+        ms_launch_chain(c, L2);
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(stamps, dev, sizeof(long long) * 160, cudaMemcpyDeviceToHost, c->stream));
@@ -882,7 +915,7 @@ int slk_debug_msampler_launch(slk_chain* c, int meiosis0, int meiosis1, int whic
         ms_launch_step(c, L);                          // the chain kernel needs this pair's likelihoods
         for(int r = 0; r < reps; ++r) {
             L.iteration = (uint64_t) r;
-            slk_ms_chain_kernel<<<SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream>>>(L);
+            ms_launch_chain(c, L);
         }
         c->ms_cur_valid = false;                       // repeated sampling of one pair: the graph is still legal, ln cur is stale
     }

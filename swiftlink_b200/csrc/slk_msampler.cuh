@@ -75,6 +75,7 @@ struct SlkMsLaunch {
     int* err;
     // likelihood kernel: hypotheses.  set s flips set_n[s] indicators; a set with no flip writes lncur.
     int nsets;
+    int prefix_nt;               // step kernel: typed people [0, prefix_nt) do not depend on the predecessor kernel's flips
     int set_n[SLK_MS_MAXSETS];
     int set_person[SLK_MS_MAXSETS][2];
     int set_parent[SLK_MS_MAXSETS][2];
@@ -90,6 +91,15 @@ struct SlkMsLaunch {
     const double* log_theta;
     const double* log_1mtheta;
 };
+
+// Programmatic dependent launch (sm_90+): the step and chain kernels of a sweep alternate on one stream, each
+// consuming what the previous one wrote.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a
+// kernel's CTAs become resident as soon as its predecessor has executed ms_launch_dependents(), stage their
+// launch-invariant tables and then block in ms_wait_for_predecessor() until the predecessor grid has completed and
+// its writes are visible: launch latency and prologue leave the dependent chain of a sweep.  Both are no-ops for
+// a kernel launched without the attribute.
+__device__ __forceinline__ void ms_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ms_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- per-thread arrays in shared memory, interleaved so that lane t always hits bank t ---------
 
@@ -218,6 +228,7 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
     int ngroups = 0;
     bool dead = false;
     for(int k = 0; k < nt && !dead; ++k) {
+        if(k == src.sync_at) src.sync(k);              // uniform over the warp (see slk_ms_step_kernel)
         uint32_t g, mat, pat;
         src.next(k, g, mat, pat);
         if(g == SLK_UNTYPED) continue;
@@ -530,13 +541,15 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     {
         struct SmemSource {
             const MsLane& ln; uint32_t o_te, o_obs; uint32_t gw;
+            int sync_at;                                       // -1: the full kernel has no sync point
+            __device__ __forceinline__ void sync(int) {}
             __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
                 if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
                 g = (gw >> (2 * (k & 15))) & 3u;
                 if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
                 else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
             }
-        } src = { ln, o_te, o_obs, 0u };
+        } src = { ln, o_te, o_obs, 0u, -1 };
         if(tr) tr[4] = clock64();
         ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
     }
@@ -601,6 +614,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
     if(tr) tr[0] = clock64();
 
+    ms_launch_dependents();
     int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
     int16_t* s_fa = s_mo + N;                              // [N]
     uint16_t* s_typed = (uint16_t*)(s_fa + N);             // [nt]
@@ -625,9 +639,9 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
     const uint32_t o_grp = lay.grp * 32u, o_cnt = lay.cnt * 32u, o_fa = lay.fa * 32u, o_hm = lay.hmask * 32u;
     const uint8_t* row = L.dgp + (size_t) l * N;
-    // the hypothesis's slot mask
+    // the hypothesis's slot mask, without the locus's stale slots: those are the predecessor kernel's to write
     for(int w = 0; w < W; ++w) {
-        uint32_t h = L.stale[(size_t) l * W + w];
+        uint32_t h = 0;
         if(p0 >= 0) h |= L.ms.desc_mask[(size_t)(p0 - F) * W + w];
         if(p1 >= 0) h |= L.ms.desc_mask[(size_t)(p1 - F) * W + w];
         ms_st32(ln.a32(o_hm, w), h);
@@ -635,18 +649,34 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     if(p0 >= 0) {
         const int k0 = L.ms.typed_index[p0];
         if(k0 >= 0) { const uint32_t q = 2 * k0 + a0; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
-        if(set < 2) L.bits[(size_t) set * M + l] = (uint8_t)((row[p0] >> a0) & 1u);
     }
     if(p1 >= 0) {
         const int k1 = L.ms.typed_index[p1];
         if(k1 >= 0) { const uint32_t q = 2 * k1 + a1; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
     }
 
+    // The walk in two parts.  The predecessor on the stream (the chain kernel of the previous pair of steps) flips
+    // indicators of that pair's two people only, so the typed people before the first one at or below them --
+    // [0, prefix_nt), a launch parameter -- have the labels and the lineages they had before it ran: that part of
+    // the walk runs while the predecessor is still sampling.  sync() then blocks until the predecessor has
+    // completed, folds the locus's stale slots into the mask and records the indicator's current value; nothing
+    // is written to global memory before it (the predecessor is still reading ln L and `bits` of ITS steps).
     struct StepSource {
         const MsLane& ln; uint32_t o_hm; const uint8_t* row; const int16_t* s_mo; const int16_t* s_fa; const uint16_t* s_typed;
-        const void* te; const uint8_t* obs; int M, l, F, nt, p0, a0, p1, a1;
+        const void* te; const uint8_t* obs; const uint32_t* stale; uint8_t* bits_out; int M, l, F, nt, W, p0, a0, p1, a1;
+        int sync_at; bool synced;
         uint32_t hw;
         uint32_t qp[4], qg[4];           // the next four typed people's label pairs / genotypes, in flight
+        __device__ __forceinline__ void sync(int k) {
+            ms_wait_for_predecessor();
+            synced = true;
+            for(int w = 0; w < W; ++w) {
+                const uint32_t st = stale[(size_t) l * W + w];
+                if(st) ms_st32(ln.a32(o_hm, w), ms_ld32(ln.a32(o_hm, w)) | st);
+            }
+            if(k < nt) hw = ms_ld32(ln.a32(o_hm, k >> 4));
+            if(bits_out) *bits_out = (uint8_t)((row[p0] >> a0) & 1u);
+        }
         // founder allele reached from slot `sl` of `person` by following the indicators of the graph row
         __device__ __forceinline__ uint32_t trace(int person, uint32_t sl, bool flips) const {
             int cur = person;
@@ -667,10 +697,9 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
             }
         }
         __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
-            // a four-deep ring in registers: slot k & 3 is consumed and refilled for person k + 4, so a loaded
-            // value is first touched four people later (the switch keeps every index a compile-time constant)
             // a four-deep queue in registers (shifted, so every index is a compile-time constant; a ring
-            // indexed by k & 3 through a switch measured 35 % slower: four copies of the body)
+            // indexed by k & 3 through a switch measured 35 % slower: four copies of the body).  te is written by
+            // likelihood kernels only, never by the chain kernel: fetching ahead of sync() is safe.
             const uint32_t pair = qp[0];
             g = qg[0];
             qp[0] = qp[1]; qg[0] = qg[1]; qp[1] = qp[2]; qg[1] = qg[2]; qp[2] = qp[3]; qg[2] = qg[3];
@@ -685,10 +714,13 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
                 if(m2 & 2u) pat = trace(person, 1u, true);
             }
         }
-    } src = { ln, o_hm, row, s_mo, s_fa, s_typed, L.te, L.ms.obsT + l, M, l, F, nt, p0, a0, p1, a1, 0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
+    } src = { ln, o_hm, row, s_mo, s_fa, s_typed, L.te, L.ms.obsT + l, L.stale, (p0 >= 0 && set < 2) ? L.bits + (size_t) set * M + l : (uint8_t*) 0,
+              M, l, F, nt, W, p0, a0, p1, a1, L.prefix_nt > 0 ? L.prefix_nt : 0, false, 0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
+    const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
     src.fetch(0, 0); src.fetch(1, 1); src.fetch(2, 2); src.fetch(3, 3);
     if(tr) tr[4] = clock64();
-    const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
+    const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, lnM, lnm, tr);
+    if(!src.synced) src.sync(nt);                          // dead before the sync point, or the whole walk was prefix
     L.lnl[(size_t) set * M + l] = ret;
 
     // bring the locus's out-of-date entries up to date (current graph: no hypothetical flips)
@@ -750,7 +782,7 @@ __device__ __forceinline__ Mat2 mat2_shfl_up(const Mat2& v, int d) {
 // the interval to its left (8 B), the step's uniform draw (8 B), map byte, changed-in-step-0 byte.
 #define SLK_MS_CLUSTER 8
 #define SLK_MS_CHAIN_THREADS 640
-#define SLK_MS_CHAIN_BYTES_PER_LOCUS 50
+#define SLK_MS_CHAIN_BYTES_PER_LOCUS 58
 
 __global__ void __cluster_dims__(SLK_MS_CLUSTER, 1, 1) __launch_bounds__(SLK_MS_CHAIN_THREADS)
 slk_ms_chain_kernel(const SlkMsLaunch L) {
@@ -775,8 +807,8 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     double* s_lncur = (double*)(s_raw + cap);                               // [cap]
     double* s_lnflip = s_lncur + cap;                                       // [cap]
     double* s_theta = s_lnflip + cap;                                       // [cap] theta[i - 1]
-    double* s_u = s_theta + cap;                                            // [cap]
-    uint8_t* s_map = (uint8_t*)(s_u + cap);                                 // [cap]
+    double* s_u = s_theta + cap;                                            // [2][cap]
+    uint8_t* s_map = (uint8_t*)(s_u + 2 * cap);                             // [cap]
     uint8_t* s_changed = s_map + cap;                                       // [cap]
 
     auto apply = [](uint32_t f, uint32_t x) -> uint32_t { return (f >> x) & 1u; };
@@ -785,9 +817,18 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     long long* tr = (L.trace && t == 0 && (rank == 0 || rank == SLK_MS_CLUSTER - 1)) ? L.trace + (rank ? 24 : 0) : 0;
     if(tr) tr[0] = clock64();
     const int W = L.ms.W;
+    // everything that does not depend on the likelihoods is done while the likelihood kernel is still running
+    for(int i = cta_lo + t; i < cta_hi; i += T) {
+        s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
+        for(int step = 0; step < L.nsteps; ++step)
+            s_u[step * cap + i - cta_lo] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) i, L.step_slot[step]);
+    }
+    ms_wait_for_predecessor();                             // ln L of the hypotheses, the stale masks' last readers
+    // only now: the next step kernel reads te while it waits for this kernel, and the step kernel that has just
+    // completed was still refreshing te
+    ms_launch_dependents();
     for(int i = cta_lo + t; i < cta_hi; i += T) {
         s_lncur[i - cta_lo] = L.lncur[i]; s_changed[i - cta_lo] = 0;
-        s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
         for(int w = 0; w < W; ++w) L.stale[(size_t) i * W + w] = 0u;       // the likelihood launch brought te up to date
     }
     const double theta_hi = cta_hi < M && cta_hi > 0 ? L.theta[cta_hi - 1] : 0.5;   // interval right of the CTA's last locus
@@ -803,7 +844,6 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             const double lc = s_lncur[k];
             const double r = exp(lf - lc);                 // -inf -> 0
             s_lnflip[k] = lf;
-            s_u[k] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) i, L.step_slot[step]);
             s_raw[k] = (bits[i] & 1u) ? make_double2(r, 1.0) : make_double2(1.0, r);
             if(!(lc > -DBL_MAX) && atomicCAS(&L.err[0], 0, SLK_ERR_ILLEGAL_GRAPH) == 0) L.err[1] = i;
         }
@@ -856,7 +896,7 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
         // meiosis_sampler.cc:155-187 for one locus, both possible values of the next locus's indicator:
         // bit 0 = image of 0, bit 1 = image of 1
         auto map_code = [&](int i, double f0, double f1) -> uint32_t {
-            const double u = s_u[i - cta_lo];
+            const double u = s_u[step * cap + i - cta_lo];
             if(i == M - 1) { const int x = ms_pick(f0, f1, u); return (uint32_t)(x | (x << 1)); }
             const double th = (i + 1 < cta_hi) ? s_theta[i + 1 - cta_lo] : theta_hi, ith = 1.0 - th;
             const int x0 = ms_pick(f0 * ith, f1 * th, u);     // next = 0: j != next ? theta : 1 - theta

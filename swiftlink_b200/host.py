@@ -11,7 +11,7 @@ SYMBOLS = [
     "slk_host_marker_name", "slk_host_genotypes", "slk_host_marker_trait_prob", "slk_host_map_table",
     "slk_host_disease_model", "slk_host_elim_masks", "slk_host_build_peel", "slk_host_set_peel",
     "slk_host_num_ops", "slk_host_peel_cost", "slk_host_op_info", "slk_host_random_descentgraph",
-    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_mc3", "slk_host_mc3_temperature", "slk_host_elod",
+    "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_replicates", "slk_host_run_mc3", "slk_host_mc3_temperature", "slk_host_elod",
 ]
 
 
@@ -154,6 +154,18 @@ class Host(object):
             raise capi.SlkError(rc, self.L.slk_last_error().decode())
         return dict(lod=lod.reshape(self.M - 1, self.nlod), dg=dg, trait_prob=tp.value)
 
+
+    def run_replicates(self, runs, in_flight, burnin, iterations, scoring_period=10, seed=1, device=0, lsampler_prob=0.5,
+                       si_iterations=2):
+        """LinkageProgram::run_pedigree's -R loop with up to `in_flight` replicate chains resident on the device at once;
+        returns the merged, normalised LOD table"""
+        lod = np.zeros((self.M - 1) * self.nlod)
+        rc = self.L.slk_host_run_replicates(self.h, int(device), C.c_uint64(seed), int(runs), int(in_flight), int(burnin),
+                                            int(iterations), int(scoring_period), C.c_double(lsampler_prob),
+                                            int(si_iterations), _dp(lod))
+        if rc != 0:
+            raise capi.SlkError(rc, self.L.slk_last_error().decode())
+        return lod.reshape(self.M - 1, self.nlod)
 
     def run_mc3(self, n_chains, burnin, iterations, exchange_period=10, temperatures=None, scoring_period=10,
                 seed=1, chain_id=0, device=0, lsampler_prob=0.5, si_iterations=10):

@@ -208,3 +208,27 @@ def test_more_than_255_founder_alleles(tmp_path):
     h, d, orc, plan = _setup(tmp_path, ped, iters=2000)
     assert 2 * orc.F > 255
     _check_everything(d, orc, plan, sweeps=2)
+
+
+def test_msampler_many_loci_overlapped_launches(tmp_path):
+    """4 000 loci (125 likelihood CTAs per hypothesis, every CTA of the chain kernel's cluster busy): the step and
+    chain kernels of a sweep are launched with programmatic stream serialisation and the likelihood walk starts
+    before the previous pair's chain kernel has finished -- whole M-sweeps still reproduce the oracle's graphs bit
+    for bit, interleaved with L-sweeps that invalidate the carried state"""
+    from swiftlink_b200 import capi
+    ped = synth.generate(n_members=60, n_markers=4000, seed=8, spacing_cm=0.02, n_generations=4, loops=(2, 10),
+                         min_generation=2, founder_frac=(0.1, 0.5), min_affected=0, cousin_prob=0.3)
+    h, d, orc, plan = _setup(tmp_path, ped, iters=3000)
+    ch = capi.Chain(plan, seed=11, chain_id=1)
+    ch.lsampler_locus_by_locus(0)
+    ref = ch.dg_download()
+    for it in (100, 101, 102):
+        assert orc.ms_sweep(ref, 11, 1, it) == 0
+        ch.msampler_sweep(it)
+        assert (ch.dg_download() == ref).all(), it
+        if it == 100:
+            assert orc.ls_sweep(ref, 11, 1, 7) == 0
+            ch.lsampler_sweep(7)
+    want = orc.dg_likelihood(ref)
+    assert abs(ch.dg_likelihood() - want) <= 1e-12 * abs(want)
+    ch.close()

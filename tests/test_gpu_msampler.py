@@ -218,3 +218,21 @@ def test_mc3_ladder_runs_and_scores(name, tmp_path):
     ref = fx["lod_curves_default_mix"].mean(axis=(1, 2))
     assert abs(lod.mean() - ref.mean()) < 6.0 * ref.std(ddof=1) + 0.75
     h.close()
+
+
+def test_replicates_in_flight_do_not_change_the_result(tmp_path):
+    """LinkageProgram::run_pedigree's -R loop (linkage_program.cc:96-108): three replicate chains advanced in turn on
+    three streams give bit for bit the merged LOD table of the same replicates run one after the other (a chain's draws
+    are keyed by seed, chain id and iteration, not by when its kernels run)"""
+    from common import case_files, FORCE_X, ref_available
+    if not ref_available():
+        pytest.skip("example inputs live in oracle/_ref/examples")
+    from swiftlink_b200 import host as H
+    h = H.Host(*case_files("east", tmp_path), sex_linked=bool(FORCE_X["east"]))
+    assert h.set_peel([o["peelnode"] for o in problem("east")["ops"]])
+    one = h.run_replicates(3, 1, burnin=60, iterations=240, seed=77)
+    many = h.run_replicates(3, 3, burnin=60, iterations=240, seed=77)
+    two = h.run_replicates(3, 2, burnin=60, iterations=240, seed=77)
+    assert np.isfinite(one).all()
+    assert (one == many).all() and (one == two).all()
+    h.close()
