@@ -395,6 +395,10 @@ static void pin_scratch_in_l2(slk_chain* c, cudaStream_t s) {
     if(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
+// chains that hold M-sampler state (host-side bookkeeping; the C ABI is driven by one thread per device, as the
+// reference's is): decides whether the chain kernel may claim whole SMs, see ms_launch_chain
+static int g_ms_chains = 0;
+
 int slk_chain_create(slk_plan* plan, uint64_t seed, uint32_t chain_id, slk_chain** out) {
     if(!plan || !out) return fail(SLK_ERR_INVALID, "null argument");
     *out = 0;
@@ -435,6 +439,7 @@ void slk_chain_destroy(slk_chain* c) {
     if(!c) return;
     cudaSetDevice(c->plan->device);
     if(c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    if(c->ms_lncur) --g_ms_chains;
     cudaFree(c->dgp); cudaFree(c->dg_staging); cudaFree(c->lod); cudaFree(c->lod_out);
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
@@ -661,6 +666,7 @@ static int ms_ready(slk_chain* c) {
         CU(cudaMemsetAsync(c->ms_stale, 0, sizeof(uint32_t) * M * p->dev.ms.W, c->stream));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
         c->ms_cur_valid = false;
+        ++g_ms_chains;
     }
     return SLK_OK;
 }
@@ -677,6 +683,8 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.te = c->ms_te; L.stale = c->ms_stale;
     L.out = c->ms_out;
     L.nsets = 1;
+    L.prev_n = getenv("SLK_MS_DEBUG_PREV0") ? 0 : -1;   // predecessor unknown: the step kernel waits for it before it visits anybody
+                                                        // (the variable is a timing aid for the debug launches: results are invalid)
     L.seed = c->seed; L.chain = c->chain_id;
     return L;
 }
@@ -705,8 +713,17 @@ static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
     else ms_launch_overlapped((const void*) slk_ms_step_kernel<false>, grid, 32, p->ms_step_smem, c->stream, L);
 }
 
+// The chain kernel runs while the next pair's likelihood kernel is already walking (see slk_ms_step_kernel).  Its
+// eight 640-thread CTAs would slow down the likelihood CTAs that share their SMs, and the slowest CTA sets the
+// period of the whole sweep (measured: 94 us per pair against 79 us for a CTA elsewhere).  When this is the only
+// chain sampling meioses in the process, the kernel therefore asks for (nearly) all of an SM's shared memory, so
+// that no likelihood CTA is placed next to it; with several chains in flight it stays small so that it never has
+// to wait for eight SMs to drain.
 static void ms_launch_chain(slk_chain* c, const SlkMsLaunch& L) {
-    ms_launch_overlapped((const void*) slk_ms_chain_kernel, SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, c->plan->ms_chain_smem, c->stream, L);
+    static const char* force = getenv("SLK_MS_CHAIN_EXCLUSIVE");     // tuning aid: "0" / "1"
+    const bool exclusive = force ? force[0] == '1' : g_ms_chains <= 1;
+    const size_t smem = exclusive ? (size_t)(slk::kSmemPerBlockMax - 4096) : (size_t) c->plan->ms_chain_smem;
+    ms_launch_overlapped((const void*) slk_ms_chain_kernel, SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, smem, c->stream, L);
 }
 
 static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
@@ -718,13 +735,20 @@ static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
 
 // one or two consecutive steps of a sweep: the second meiosis's likelihood is evaluated under both
 // outcomes of the first, so the pair costs one likelihood launch and one chain launch
-// `prefix`: typed people [0, prefix) are untouched by the flips of the kernel that precedes this launch on the stream
-// (the previous pair's chain kernel); 0 when the predecessor is anything else
-static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int prefix = 0) {
+static unsigned long long* g_ms_timeline = 0;     // SLK_MS_TIMELINE (tuning aid, single-threaded use)
+static int g_ms_tl_slot = 0;
+
+// (q0, q1): the meioses of the chain kernel that precedes this launch on the stream (the previous pair of the
+// sweep; q1 < 0: a single step), q0 < 0 when the predecessor is anything else
+static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -1, int q1 = -1) {
     const SlkDevPlan& d = c->plan->dev;
     SlkMsLaunch L = ms_launch(c);
     L.iteration = iteration;
-    L.prefix_nt = prefix;
+    L.prev_n = -1;
+    if(q0 >= 0) {
+        L.prev_n = 1; L.prev_person[0] = d.F + q0 / 2; L.prev_parent[0] = q0 % 2;
+        if(q1 >= 0) { L.prev_n = 2; L.prev_person[1] = d.F + q1 / 2; L.prev_parent[1] = q1 % 2; }
+    }
     const int p0 = d.F + m0 / 2, a0 = m0 % 2;
     L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
     L.nsteps = 1;
@@ -736,9 +760,11 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int prefix
         L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
         L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) m1;
     }
+    L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
     if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
+    L.tl_slot = g_ms_tl_slot + 1;
     ms_launch_chain(c, L);
     CU(cudaGetLastError());
     return SLK_OK;
@@ -788,16 +814,34 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     }
     // MeiosisSampler::reset at the start of every sweep (markov_chain.cc:345)
     rc = slk_msampler_reset(c);
-    // The likelihood walk of a pair overlaps the previous pair's chain kernel up to the first typed person whose
-    // labels that pair can change (slk_ms_step_kernel).  The first pair follows the reset kernel, which writes te.
-    const std::vector<int16_t>& first = c->plan->host.ms_first_typed;
-    static const bool no_prefix = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
-    int prefix = 0;
+    // The likelihood walk of a pair runs ahead of the previous pair's chain kernel for every typed person that
+    // pair cannot affect (slk_ms_step_kernel).  The first pair follows the reset kernel, which writes te.
+    static const bool no_overlap = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
+    static const bool timeline = getenv("SLK_MS_TIMELINE") != 0;        // tuning aid: %globaltimer stamps of every launch
+    unsigned long long* tl = 0;
+    if(timeline) { CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * 8 * (n + 2))); CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 8 * (n + 2), c->stream)); }
+    g_ms_timeline = tl;
+    int q0 = -1, q1 = -1;
     for(int j = 0; j < n && rc == SLK_OK; j += 2) {
         const int m0 = order[j], m1 = j + 1 < n ? order[j + 1] : -1;
-        rc = ms_steps(c, iteration, m0, m1, no_prefix ? 0 : prefix);
-        prefix = first[m0];
-        if(m1 >= 0) prefix = std::min(prefix, (int) first[m1]);
+        g_ms_tl_slot = j;
+        rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1);
+        q0 = m0; q1 = m1;
+    }
+    g_ms_timeline = 0;
+    if(tl) {
+        std::vector<unsigned long long> h((size_t) 8 * (n + 2));
+        CU(cudaMemcpyAsync(h.data(), tl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(tl);
+        const unsigned long long t0 = h[0];
+        for(int j = 40; j < 56 && j + 1 < n; j += 2) {
+            const unsigned long long* a = &h[(size_t) 8 * j];          // step kernel: start, walk, before wait, after wait, end
+            const unsigned long long* b = &h[(size_t) 8 * (j + 1)];    // chain kernel: start, before wait, after wait, end
+            fprintf(stderr, "pair %3d  step: start %7.1f walk %7.1f wait %7.1f..%7.1f end %7.1f | chain: start %7.1f wait %7.1f..%7.1f end %7.1f (us)\n", j / 2,
+                    (a[0] - t0) * 1e-3, (a[1] - t0) * 1e-3, (a[2] - t0) * 1e-3, (a[3] - t0) * 1e-3, (a[4] - t0) * 1e-3,
+                    (b[0] - t0) * 1e-3, (b[1] - t0) * 1e-3, (b[2] - t0) * 1e-3, (b[3] - t0) * 1e-3);
+        }
     }
     return rc;
 }

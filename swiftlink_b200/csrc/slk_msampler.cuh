@@ -75,7 +75,9 @@ struct SlkMsLaunch {
     int* err;
     // likelihood kernel: hypotheses.  set s flips set_n[s] indicators; a set with no flip writes lncur.
     int nsets;
-    int prefix_nt;               // step kernel: typed people [0, prefix_nt) do not depend on the predecessor kernel's flips
+    int prev_n;                  // step kernel: the predecessor on the stream is the chain kernel of these prev_n (0-2)
+    int prev_person[2];          //   meioses (-1: the predecessor is something else, nothing may run ahead of it)
+    int prev_parent[2];
     int set_n[SLK_MS_MAXSETS];
     int set_person[SLK_MS_MAXSETS][2];
     int set_parent[SLK_MS_MAXSETS][2];
@@ -87,6 +89,8 @@ struct SlkMsLaunch {
     uint32_t chain;
     int32_t* dump_edges;         // optional [M][2N] (set 0)
     long long* trace;            // optional: clock64() stamps (tuning aid), see slk_debug_msampler_trace
+    unsigned long long* timeline;// optional: %globaltimer stamps of CTA 0, 8 per launch (tuning aid, SLK_MS_TIMELINE)
+    int tl_slot;
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
     const double* log_1mtheta;
@@ -98,6 +102,8 @@ struct SlkMsLaunch {
 // launch-invariant tables and then block in ms_wait_for_predecessor() until the predecessor grid has completed and
 // its writes are visible: launch latency and prologue leave the dependent chain of a sweep.  Both are no-ops for
 // a kernel launched without the attribute.
+__device__ __forceinline__ unsigned long long ms_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define MS_TL(i) do { if(L.timeline && blockIdx.x == 0 && threadIdx.x == 0) L.timeline[8 * L.tl_slot + (i)] = ms_globaltimer(); } while(0)
 __device__ __forceinline__ void ms_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void ms_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -227,11 +233,14 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
 
     int ngroups = 0;
     bool dead = false;
-    for(int k = 0; k < nt && !dead; ++k) {
-        if(k == src.sync_at) src.sync(k);              // uniform over the warp (see slk_ms_step_kernel)
+    // The likelihood does not depend on the order in which the typed people are visited (the exponents are
+    // integers; only the rounding of the unfixed components' product does, in the last bits).  The source decides
+    // the order: the full kernel visits everyone once, the step kernel in two phases (see slk_ms_step_kernel).
+    const int niter = src.iterations(nt);
+    for(int it = 0; it < niter && !dead; ++it) {
         uint32_t g, mat, pat;
-        src.next(k, g, mat, pat);
-        if(g == SLK_UNTYPED) continue;
+        const int k = src.next(it, g, mat, pat);       // < 0: nobody to visit in this iteration
+        if(k < 0 || g == SLK_UNTYPED) continue;
         const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
         const bool het = g == SLK_HETERO;
         const uint32_t em = FA_LD(mat);
@@ -541,15 +550,15 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     {
         struct SmemSource {
             const MsLane& ln; uint32_t o_te, o_obs; uint32_t gw;
-            int sync_at;                                       // -1: the full kernel has no sync point
-            __device__ __forceinline__ void sync(int) {}
-            __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+            __device__ __forceinline__ int iterations(int nt) const { return nt; }
+            __device__ __forceinline__ int next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
                 if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
                 g = (gw >> (2 * (k & 15))) & 3u;
                 if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
                 else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
+                return k;
             }
-        } src = { ln, o_te, o_obs, 0u, -1 };
+        } src = { ln, o_te, o_obs, 0u };
         if(tr) tr[4] = clock64();
         ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
     }
@@ -600,7 +609,7 @@ static inline MsStepLayout slk_ms_step_layout(int N, int F, int nt, int W) {
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
     L.hmask = L.fa + ((4u * F + 3u) & ~3u);
     L.per_thread = L.hmask + 4u * W;
-    L.cta_tables = ((uint32_t)(4 * N + 2 * nt + nt + 8) + 7u) & ~7u;
+    L.cta_tables = ((uint32_t)(4 * N + 2 * nt + nt + 4 + 4 * W + 2 * nt + 8 + 8) + 7u) & ~7u;
     return L;
 }
 
@@ -613,6 +622,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     const uint32_t t = threadIdx.x;
     long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
     if(tr) tr[0] = clock64();
+    MS_TL(0);
 
     ms_launch_dependents();
     int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
@@ -624,6 +634,35 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         const int p = L.ms.typed[k];
         s_typed[k] = (uint16_t) p;
         s_auto[k] = (L.sex_linked && L.male[p]) ? 1 : 0;
+    }
+    // slots the predecessor kernel's flips can change (its two meioses: own slot and everything below; all of them
+    // if the predecessor is not a chain kernel), and the visiting order of the walk: first the typed people who
+    // have none of those slots (ascending), then the others (ascending)
+    uint32_t* s_prev = (uint32_t*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u));      // [W]
+    uint16_t* s_ord = (uint16_t*)(s_prev + W);                                      // [nt]
+    int* s_n0 = (int*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u) + 4u * W + ((2u * nt + 3u) & ~3u));
+    for(int w = t; w < W; w += 32) {
+        uint32_t m = L.prev_n < 0 ? 0xffffffffu : 0u;
+        for(int j = 0; j < L.prev_n; ++j) {
+            m |= L.ms.desc_mask[(size_t)(L.prev_person[j] - F) * W + w];
+            const int kk = L.ms.typed_index[L.prev_person[j]];
+            if(kk >= 0 && ((2 * kk + L.prev_parent[j]) >> 5) == w) m |= 1u << ((2 * kk + L.prev_parent[j]) & 31);
+        }
+        s_prev[w] = m;
+    }
+    __syncwarp();
+    {
+        int n = 0;
+        for(int pass = 0; pass < 2; ++pass) {
+            for(int k0 = 0; k0 < nt; k0 += 32) {
+                const int k = k0 + (int) t;
+                const bool mine = k < nt && ((((s_prev[k >> 4] >> (2 * (k & 15))) & 3u) != 0) == (pass == 1));
+                const uint32_t b = __ballot_sync(0xffffffffu, mine);
+                if(mine) s_ord[n + __popc(b & ((1u << t) - 1u))] = (uint16_t) k;
+                n += __popc(b);
+            }
+            if(pass == 0 && t == 0) *s_n0 = n;
+        }
     }
     __syncwarp();
 
@@ -655,26 +694,31 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         if(k1 >= 0) { const uint32_t q = 2 * k1 + a1; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
     }
 
-    // The walk in two parts.  The predecessor on the stream (the chain kernel of the previous pair of steps) flips
-    // indicators of that pair's two people only, so the typed people before the first one at or below them --
-    // [0, prefix_nt), a launch parameter -- have the labels and the lineages they had before it ran: that part of
-    // the walk runs while the predecessor is still sampling.  sync() then blocks until the predecessor has
-    // completed, folds the locus's stale slots into the mask and records the indicator's current value; nothing
-    // is written to global memory before it (the predecessor is still reading ln L and `bits` of ITS steps).
+    // The walk in two phases.  The predecessor on the stream (the chain kernel of the previous pair of steps) flips
+    // indicators of that pair's two people only.  A typed person none of whose slots is one of theirs or below
+    // them (s_prev) has the label pair and the lineages it had before that kernel ran, so phase 0 visits those
+    // people -- 93 % of them on the 200-member pedigree -- while the predecessor is still sampling.  sync() then
+    // blocks until the predecessor has completed, folds the locus's stale slots into the mask and records the
+    // indicator's current value, and phase 1 visits the rest (s_ord is the whole order, *s_n0 the phase boundary).  Nothing is written to global memory before sync()
+    // (the predecessor is still reading ln L and `bits` of ITS steps); te is only ever written by likelihood
+    // kernels, so its entries are streamed ahead of their use in both phases.
     struct StepSource {
         const MsLane& ln; uint32_t o_hm; const uint8_t* row; const int16_t* s_mo; const int16_t* s_fa; const uint16_t* s_typed;
+        const uint16_t* s_ord; int n0;
         const void* te; const uint8_t* obs; const uint32_t* stale; uint8_t* bits_out; int M, l, F, nt, W, p0, a0, p1, a1;
-        int sync_at; bool synced;
-        uint32_t hw;
-        uint32_t qp[4], qg[4];           // the next four typed people's label pairs / genotypes, in flight
-        __device__ __forceinline__ void sync(int k) {
+        bool synced; unsigned long long* tl;
+        uint32_t hw_next;
+        uint32_t qk[4], qp[4], qg[4];    // the next four people of the order: index, label pair, genotype (loads in flight)
+        __device__ __forceinline__ int iterations(int n) const { return n; }
+        __device__ __forceinline__ void sync() {
+            if(tl) tl[2] = ms_globaltimer();
             ms_wait_for_predecessor();
+            if(tl) tl[3] = ms_globaltimer();
             synced = true;
             for(int w = 0; w < W; ++w) {
                 const uint32_t st = stale[(size_t) l * W + w];
                 if(st) ms_st32(ln.a32(o_hm, w), ms_ld32(ln.a32(o_hm, w)) | st);
             }
-            if(k < nt) hw = ms_ld32(ln.a32(o_hm, k >> 4));
             if(bits_out) *bits_out = (uint8_t)((row[p0] >> a0) & 1u);
         }
         // founder allele reached from slot `sl` of `person` by following the indicators of the graph row
@@ -690,21 +734,29 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
             }
             return (uint32_t)(2 * cur) + sl;
         }
-        __device__ __forceinline__ void fetch(int k, int slot) {
-            if(k < nt) {
+        __device__ __forceinline__ void fetch(int it, int slot) {
+            if(it < nt) {
+                const uint32_t k = s_ord[it];
+                qk[slot] = k;
                 qp[slot] = WIDE ? ((const uint32_t*) te)[(size_t) k * M + l] : (uint32_t)((const uint16_t*) te)[(size_t) k * M + l];
                 qg[slot] = obs[(size_t) k * M];
             }
         }
-        __device__ __forceinline__ void next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
-            // a four-deep queue in registers (shifted, so every index is a compile-time constant; a ring
-            // indexed by k & 3 through a switch measured 35 % slower: four copies of the body).  te is written by
-            // likelihood kernels only, never by the chain kernel: fetching ahead of sync() is safe.
-            const uint32_t pair = qp[0];
+        __device__ __forceinline__ int next(int it, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+            if(it == n0) {                               // uniform: every lane of the launch is at the same iteration
+                sync();
+                hw_next = ms_ld32(ln.a32(o_hm, qk[0] >> 4));
+            }
+            // Four-deep queues in registers (shifted, so every index is a compile-time constant; a ring indexed by
+            // it & 3 through a switch measured 35 % slower: four copies of the body).  The person's index and mask
+            // word are fetched one iteration ahead too: nothing of the order's indirection is on the walk's
+            // dependent chain.
+            const uint32_t k = qk[0], pair = qp[0], hw = hw_next;
             g = qg[0];
-            qp[0] = qp[1]; qg[0] = qg[1]; qp[1] = qp[2]; qg[1] = qg[2]; qp[2] = qp[3]; qg[2] = qg[3];
-            fetch(k + 4, 3);
-            if((k & 15) == 0) hw = ms_ld32(ln.a32(o_hm, k >> 4));
+            qk[0] = qk[1]; qp[0] = qp[1]; qg[0] = qg[1]; qk[1] = qk[2]; qp[1] = qp[2]; qg[1] = qg[2];
+            qk[2] = qk[3]; qp[2] = qp[3]; qg[2] = qg[3];
+            fetch(it + 4, 3);
+            hw_next = ms_ld32(ln.a32(o_hm, qk[0] >> 4));
             const uint32_t m2 = (hw >> (2 * (k & 15))) & 3u;
             mat = WIDE ? (pair & 0xffffu) : (pair & 0xffu);
             pat = WIDE ? (pair >> 16) : (pair >> 8);
@@ -713,14 +765,20 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
                 if(m2 & 1u) mat = trace(person, 0u, true);
                 if(m2 & 2u) pat = trace(person, 1u, true);
             }
+            return (int) k;
         }
-    } src = { ln, o_hm, row, s_mo, s_fa, s_typed, L.te, L.ms.obsT + l, L.stale, (p0 >= 0 && set < 2) ? L.bits + (size_t) set * M + l : (uint8_t*) 0,
-              M, l, F, nt, W, p0, a0, p1, a1, L.prefix_nt > 0 ? L.prefix_nt : 0, false, 0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
+    } src = { ln, o_hm, row, s_mo, s_fa, s_typed, s_ord, *s_n0, L.te, L.ms.obsT + l, L.stale,
+              (p0 >= 0 && set < 2) ? L.bits + (size_t) set * M + l : (uint8_t*) 0,
+              M, l, F, nt, W, p0, a0, p1, a1, false,
+              (L.timeline && blockIdx.x == 0 && t == 0) ? L.timeline + 8 * L.tl_slot : (unsigned long long*) 0,
+              0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
     const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
-    src.fetch(0, 0); src.fetch(1, 1); src.fetch(2, 2); src.fetch(3, 3);
+    for(int j = 0; j < 4; ++j) src.fetch(j, j);
+    src.hw_next = ms_ld32(ln.a32(o_hm, src.qk[0] >> 4));
     if(tr) tr[4] = clock64();
+    MS_TL(1);
     const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, lnM, lnm, tr);
-    if(!src.synced) src.sync(nt);                          // dead before the sync point, or the whole walk was prefix
+    if(!src.synced) src.sync();                            // every lane left the walk (impossible graph) in phase 0
     L.lnl[(size_t) set * M + l] = ret;
 
     // bring the locus's out-of-date entries up to date (current graph: no hypothetical flips)
@@ -738,6 +796,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         }
     }
     if(tr) tr[6] = clock64();
+    MS_TL(4);
 }
 
 // ---- (2) + (3): forward pass and backward sampling along the chromosome ------------------------------
@@ -817,13 +876,16 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     long long* tr = (L.trace && t == 0 && (rank == 0 || rank == SLK_MS_CLUSTER - 1)) ? L.trace + (rank ? 24 : 0) : 0;
     if(tr) tr[0] = clock64();
     const int W = L.ms.W;
+    MS_TL(0);
     // everything that does not depend on the likelihoods is done while the likelihood kernel is still running
     for(int i = cta_lo + t; i < cta_hi; i += T) {
         s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
         for(int step = 0; step < L.nsteps; ++step)
             s_u[step * cap + i - cta_lo] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t) i, L.step_slot[step]);
     }
+    MS_TL(1);
     ms_wait_for_predecessor();                             // ln L of the hypotheses, the stale masks' last readers
+    MS_TL(2);
     // only now: the next step kernel reads te while it waits for this kernel, and the step kernel that has just
     // completed was still refreshing te
     ms_launch_dependents();
@@ -1006,6 +1068,7 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
         if(tr) tr[8 + 8 * step] = clock64();
     }
     for(int i = cta_lo + t; i < cta_hi; i += T) L.lncur[i] = s_lncur[i - cta_lo];
+    MS_TL(3);
 }
 
 // ---- descent-graph likelihood (descent_graph.cc:150-265) ------------------------------------------

@@ -548,22 +548,6 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
                 }
             }
         }
-        // first typed person (in walk order) whose label pair a flip of meiosis (person, parent) can change: its
-        // own slot or a slot below it.  The walk of the NEXT pair of steps does not depend on the outcome of
-        // this pair's steps before that index (slk_ms_step_kernel's prefix).
-        hp.ms_first_typed.assign((size_t) 2 * std::max(N - F, 0), (int16_t) nt);
-        for(int i = 0; i < 2 * (N - F); ++i) {
-            const int P = i / 2, par = i % 2;
-            int first = nt;
-            for(int w = 0; w < hp.ms_W && first == nt; ++w) {
-                const uint32_t m = hp.ms_desc_mask[(size_t) P * hp.ms_W + w];
-                if(m) first = (32 * w + __builtin_ctz(m)) >> 1;
-            }
-            const int own = hp.ms_typed_index[F + P];
-            if(own >= 0 && own < first) first = own;
-            (void) par;
-            hp.ms_first_typed[i] = (int16_t) first;
-        }
         // markov_chain.cc:68-80 with Person::safe_to_ignore_meiosis (person.cc:208-222)
         std::vector<int> nchild(N, 0);
         for(int i = F; i < N; ++i) { nchild[pb.mother[i]]++; nchild[pb.father[i]]++; }

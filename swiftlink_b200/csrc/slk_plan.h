@@ -53,7 +53,6 @@ struct HostPlan {
     std::vector<int32_t> ms_ordering;    // meioses an M-sweep visits (markov_chain.cc:68-80)
     std::vector<uint32_t> ms_desc_mask;  // [N-F][W]
     std::vector<int16_t> ms_typed_index; // [N]
-    std::vector<int16_t> ms_first_typed; // [2(N-F)] first typed index whose labels a flip of that meiosis can change (nt: none)
     int ms_W;
 };
 
