@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "swiftlink_b200.h"
@@ -761,6 +762,7 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
         L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) m1;
     }
     L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
+    L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == 100) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
     if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
@@ -819,7 +821,8 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     static const bool no_overlap = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
     static const bool timeline = getenv("SLK_MS_TIMELINE") != 0;        // tuning aid: %globaltimer stamps of every launch
     unsigned long long* tl = 0;
-    if(timeline) { CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * 8 * (n + 2))); CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 8 * (n + 2), c->stream)); }
+    const int tl_words = 8 * (n + 2) + 2 * 3 * c->plan->ms_grid;
+    if(timeline) { CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * tl_words)); CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * tl_words, c->stream)); }
     g_ms_timeline = tl;
     int q0 = -1, q1 = -1;
     for(int j = 0; j < n && rc == SLK_OK; j += 2) {
@@ -830,10 +833,30 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     }
     g_ms_timeline = 0;
     if(tl) {
-        std::vector<unsigned long long> h((size_t) 8 * (n + 2));
+        std::vector<unsigned long long> h((size_t) tl_words);
         CU(cudaMemcpyAsync(h.data(), tl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(tl);
+        {
+            // every CTA of the step kernel of pair 50: start and end relative to the first start
+            const int g3 = 3 * c->plan->ms_grid, off = 8 * (n + 2);
+            unsigned long long first = ~0ull;
+            for(int b = 0; b < g3; ++b) if(h[off + 2 * b] && h[off + 2 * b] < first) first = h[off + 2 * b];
+            std::vector<double> st, en;
+            double set_end[3] = {0, 0, 0}, set_dur[3] = {0, 0, 0};
+            for(int b = 0; b < g3; ++b) {
+                if(!h[off + 2 * b + 1]) continue;
+                const double a = (h[off + 2 * b] - first) * 1e-3, e = (h[off + 2 * b + 1] - first) * 1e-3;
+                st.push_back(a); en.push_back(e);
+                const int set = b / c->plan->ms_grid;
+                set_end[set] = std::max(set_end[set], e); set_dur[set] += (e - a) / c->plan->ms_grid;
+            }
+            std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end());
+            if(!st.empty())
+                fprintf(stderr, "step kernel CTAs (%d): start p50 %.1f p99 %.1f max %.1f | end p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f | per set: mean duration %.1f %.1f %.1f last end %.1f %.1f %.1f (us)\n",
+                        (int) st.size(), st[st.size() / 2], st[st.size() * 99 / 100], st.back(), en[en.size() / 10], en[en.size() / 2], en[en.size() * 9 / 10],
+                        en[en.size() * 99 / 100], en.back(), set_dur[0], set_dur[1], set_dur[2], set_end[0], set_end[1], set_end[2]);
+        }
         const unsigned long long t0 = h[0];
         for(int j = 40; j < 56 && j + 1 < n; j += 2) {
             const unsigned long long* a = &h[(size_t) 8 * j];          // step kernel: start, walk, before wait, after wait, end

@@ -90,7 +90,7 @@ struct SlkMsLaunch {
     int32_t* dump_edges;         // optional [M][2N] (set 0)
     long long* trace;            // optional: clock64() stamps (tuning aid), see slk_debug_msampler_trace
     unsigned long long* timeline;// optional: %globaltimer stamps of CTA 0, 8 per launch (tuning aid, SLK_MS_TIMELINE)
-    int tl_slot;
+    int tl_slot, tl_cta_off;     // tl_cta_off > 0: also (start, end) of every CTA of this launch at timeline[tl_cta_off + 2 * cta]
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
     const double* log_1mtheta;
@@ -623,6 +623,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
     if(tr) tr[0] = clock64();
     MS_TL(0);
+    if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x] = ms_globaltimer();
 
     ms_launch_dependents();
     int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
@@ -797,6 +798,8 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     }
     if(tr) tr[6] = clock64();
     MS_TL(4);
+    __syncwarp();
+    if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x + 1] = ms_globaltimer();
 }
 
 // ---- (2) + (3): forward pass and backward sampling along the chromosome ------------------------------
