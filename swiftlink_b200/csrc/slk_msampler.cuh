@@ -32,6 +32,10 @@
 //                              A launch evaluates up to three hypotheses: "meiosis j flipped", and for the
 //                              NEXT meiosis of the sweep "j+1 flipped" / "j and j+1 flipped", i.e. both
 //                              outcomes of step j -- so two steps cost one likelihood latency.
+//   slk_ms_step_kernel         the same likelihood incrementally (only the labels a hypothesis can change are
+//                              re-derived), used for every step of a sweep; launched with programmatic stream
+//                              serialisation, it walks the typed people the previous pair's chain kernel cannot
+//                              affect while that kernel is still sampling, then waits for it and walks the rest.
 //   slk_ms_chain_kernel        one 8-CTA cluster, one or two steps.  (2) is a product of 2x2 non-negative
 //                              matrices diag(raw_i) * T(theta_{i-1}): every thread multiplies the matrices
 //                              of its chunk of loci, a scan over threads / warps / CTAs (distributed
@@ -589,7 +593,7 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
 // where stale[l] collects the slots invalidated by indicators the chain kernel has flipped at this locus since
 // te was last brought up to date; the set-0 thread of the locus writes those entries back at the end of its
 // work and the chain kernel clears the mask before it records new flips.  No per-thread label array, no
-// graph-row or genotype staging: 21 KB of shared memory per warp instead of 31.
+// graph-row or genotype staging: 24 KB of shared memory per warp instead of 31.
 struct MsStepLayout {
     int wide, G;
     uint32_t grp, cnt, fa, hmask;    // per-thread byte offsets (multiply by 32 lanes)
