@@ -401,20 +401,31 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
         const bool minor_smaller = lnm <= lnM;
         const double rho = exp(-fabs(lnm - lnM));
         double prod = 1.0;
-        for(int i = 0; i < ngroups; ++i) {
-            const Grp e = grp_ld(i);
-            if(e.meta & 0x8000u) continue;                 // merged away (group_active false)
-            uint32_t a = e.a, b = e.b;
-            if(fixed_of(e) == -1) {
-                // keep the larger of the two terms: more factors of the more frequent allele
-                const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
-                uint32_t k = hi - lo;
-                if(minor_smaller) { a = hi; b = lo; } else { a = lo; b = hi; }
-                double t = 1.0, sq = rho;
-                while(k) { if(k & 1u) t *= sq; sq *= sq; k >>= 1; }
-                prod *= 1.0 + t;
+        for(int i0 = 0; i0 < ngroups; i0 += 4) {
+            // four table words in flight at a time (the loads are ordered asm statements: one per iteration would
+            // pay a shared-memory latency each)
+            Grp eq[4];
+#pragma unroll
+            for(int j = 0; j < 4; ++j) {
+                if(i0 + j < ngroups) eq[j] = grp_ld(i0 + j);
+                else { eq[j].meta = 0x8000u; eq[j].a = eq[j].b = 0u; }
             }
-            A += a; B += b;
+#pragma unroll
+            for(int j = 0; j < 4; ++j) {
+                const Grp e = eq[j];
+                if(e.meta & 0x8000u) continue;             // merged away (group_active false)
+                uint32_t a = e.a, b = e.b;
+                if(fixed_of(e) == -1) {
+                    // keep the larger of the two terms: more factors of the more frequent allele
+                    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+                    uint32_t k = hi - lo;
+                    if(minor_smaller) { a = hi; b = lo; } else { a = lo; b = hi; }
+                    double t = 1.0, sq = rho;
+                    while(k) { if(k & 1u) t *= sq; sq *= sq; k >>= 1; }
+                    prod *= 1.0 + t;
+                }
+                A += a; B += b;
+            }
         }
         ret = ((double) A * lnM + (double) B * lnm) + log(prod);
         if(!(ret > -1e290)) ret = -INFINITY;               // a zero allele frequency entered the product
@@ -778,6 +789,8 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
               (L.timeline && blockIdx.x == 0 && t == 0) ? L.timeline + 8 * L.tl_slot : (unsigned long long*) 0,
               0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
     const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
+    // predecessor unknown (the reset kernel, which writes te, or anything else): nothing is read ahead of it
+    if(L.prev_n < 0) ms_wait_for_predecessor();
     for(int j = 0; j < 4; ++j) src.fetch(j, j);
     src.hw_next = ms_ld32(ln.a32(o_hm, src.qk[0] >> 4));
     if(tr) tr[4] = clock64();
