@@ -216,9 +216,9 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
         else ms_st32(ln.a32(o_grp, g), meta | (a << 16) | (b << 24));
     };
     // root of component g: returns the root id, its entry, the parity of g's frame to the root's
-    auto find = [&](uint32_t g, Grp& re, uint32_t& par) -> uint32_t {
+    // (the entry of g is passed in: where two components are looked up, both first loads are issued together)
+    auto find_from = [&](uint32_t g, Grp e, Grp& re, uint32_t& par) -> uint32_t {
         const uint32_t g0 = g;
-        Grp e = grp_ld(g);
         par = 0;
         int hops = 0;
         while((e.meta & 0xfffu) != g) {
@@ -231,6 +231,7 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
         re = e;
         return g;
     };
+    auto find = [&](uint32_t g, Grp& re, uint32_t& par) -> uint32_t { return find_from(g, grp_ld(g), re, par); };
     auto fixed_of = [](const Grp& e) -> int { return (int)((e.meta >> 13) & 3u) - 1; };   // -1 unfixed, 0, 1
     // write root `g` with state f and exponents (a, b)
     auto put = [&](uint32_t g, int f, uint32_t a, uint32_t b) { grp_st(g, g | ((uint32_t)(f + 1) << 13), a, b); };
@@ -243,13 +244,14 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
     const int niter = src.iterations(nt);
     for(int it = 0; it < niter && !dead; ++it) {
         uint32_t g, mat, pat;
-        const int k = src.next(it, g, mat, pat);       // < 0: nobody to visit in this iteration
+        bool single;                                    // x-linked male: the maternal allele only
+        const int k = src.next(it, g, mat, pat, single);       // < 0: nobody to visit in this iteration
         if(k < 0 || g == SLK_UNTYPED) continue;
         const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
         const bool het = g == SLK_HETERO;
-        const uint32_t em = FA_LD(mat);
+        const uint32_t em = FA_LD(mat), ep = FA_LD(pat);        // both loads in flight together
 
-        if(mat == pat || s_auto[k]) {
+        if(mat == pat || single) {
             if(het) { dead = true; break; }
             if(em & 0xfffu) {
                 Grp re; uint32_t par;
@@ -273,13 +275,14 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
             continue;
         }
 
-        const uint32_t ep = FA_LD(pat);
         // legal(g, a1, a2) and get_other_allele(g, a1) on one-bit alleles (founder_allele_graph4.cc:427-455)
 #define LEGAL(x, y) (het ? ((x) != (y)) : ((x) == gB && (y) == gB))
         if((em & 0xfffu) && (ep & 0xfffu)) {
             Grp re1, re2; uint32_t par1, par2;
-            const uint32_t g1 = find((em & 0xfffu) - 1u, re1, par1);
-            const uint32_t g2 = find((ep & 0xfffu) - 1u, re2, par2);
+            const uint32_t i1 = (em & 0xfffu) - 1u, i2 = (ep & 0xfffu) - 1u;
+            const Grp e1 = grp_ld(i1), e2 = grp_ld(i2);
+            const uint32_t g1 = find_from(i1, e1, re1, par1);
+            const uint32_t g2 = find_from(i2, e2, re2, par2);       // (a path compression of i1 leaves e2 a valid, longer route)
             const uint32_t m0 = (em >> (14 + par1)) & 1u, m1 = (em >> (15 - par1)) & 1u;
             const uint32_t q0 = (ep >> (14 + par2)) & 1u, q1 = (ep >> (15 - par2)) & 1u;
             int f1 = fixed_of(re1);
@@ -564,16 +567,17 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
     double ret;
     {
         struct SmemSource {
-            const MsLane& ln; uint32_t o_te, o_obs; uint32_t gw;
+            const MsLane& ln; uint32_t o_te, o_obs; uint32_t gw; const uint8_t* s_auto;
             __device__ __forceinline__ int iterations(int nt) const { return nt; }
-            __device__ __forceinline__ int next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+            __device__ __forceinline__ int next(int k, uint32_t& g, uint32_t& mat, uint32_t& pat, bool& single) {
+                single = s_auto[k] != 0;
                 if((k & 15) == 0) gw = ms_ld32(ln.a32(o_obs, k >> 4));
                 g = (gw >> (2 * (k & 15))) & 3u;
                 if(WIDE) { const uint32_t v = ms_ld32(ln.a16(o_te, 2 * k)); mat = v & 0xffffu; pat = v >> 16; }
                 else { const uint32_t v = ms_ld16(ln.a8(o_te, 2 * k)); mat = v & 0xffu; pat = v >> 8; }
                 return k;
             }
-        } src = { ln, o_te, o_obs, 0u };
+        } src = { ln, o_te, o_obs, 0u, s_auto };
         if(tr) tr[4] = clock64();
         ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, L.ms.lnmajor[l], L.ms.lnminor[l], tr);
     }
@@ -674,7 +678,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
                 const int k = k0 + (int) t;
                 const bool mine = k < nt && ((((s_prev[k >> 4] >> (2 * (k & 15))) & 3u) != 0) == (pass == 1));
                 const uint32_t b = __ballot_sync(0xffffffffu, mine);
-                if(mine) s_ord[n + __popc(b & ((1u << t) - 1u))] = (uint16_t) k;
+                if(mine) s_ord[n + __popc(b & ((1u << t) - 1u))] = (uint16_t)(k | (s_auto[k] ? 0x8000 : 0));     // N < 2048
                 n += __popc(b);
             }
             if(pass == 0 && t == 0) *s_n0 = n;
@@ -752,27 +756,28 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         }
         __device__ __forceinline__ void fetch(int it, int slot) {
             if(it < nt) {
-                const uint32_t k = s_ord[it];
-                qk[slot] = k;
+                const uint32_t ko = s_ord[it], k = ko & 0x7fffu;
+                qk[slot] = ko;
                 qp[slot] = WIDE ? ((const uint32_t*) te)[(size_t) k * M + l] : (uint32_t)((const uint16_t*) te)[(size_t) k * M + l];
                 qg[slot] = obs[(size_t) k * M];
             }
         }
-        __device__ __forceinline__ int next(int it, uint32_t& g, uint32_t& mat, uint32_t& pat) {
+        __device__ __forceinline__ int next(int it, uint32_t& g, uint32_t& mat, uint32_t& pat, bool& single) {
             if(it == n0) {                               // uniform: every lane of the launch is at the same iteration
                 sync();
-                hw_next = ms_ld32(ln.a32(o_hm, qk[0] >> 4));
+                hw_next = ms_ld32(ln.a32(o_hm, (qk[0] & 0x7fffu) >> 4));
             }
             // Four-deep queues in registers (shifted, so every index is a compile-time constant; a ring indexed by
             // it & 3 through a switch measured 35 % slower: four copies of the body).  The person's index and mask
             // word are fetched one iteration ahead too: nothing of the order's indirection is on the walk's
             // dependent chain.
-            const uint32_t k = qk[0], pair = qp[0], hw = hw_next;
+            const uint32_t k = qk[0] & 0x7fffu, pair = qp[0], hw = hw_next;
+            single = (qk[0] & 0x8000u) != 0;
             g = qg[0];
             qk[0] = qk[1]; qp[0] = qp[1]; qg[0] = qg[1]; qk[1] = qk[2]; qp[1] = qp[2]; qg[1] = qg[2];
             qk[2] = qk[3]; qp[2] = qp[3]; qg[2] = qg[3];
             fetch(it + 4, 3);
-            hw_next = ms_ld32(ln.a32(o_hm, qk[0] >> 4));
+            hw_next = ms_ld32(ln.a32(o_hm, (qk[0] & 0x7fffu) >> 4));
             const uint32_t m2 = (hw >> (2 * (k & 15))) & 3u;
             mat = WIDE ? (pair & 0xffffu) : (pair & 0xffu);
             pat = WIDE ? (pair >> 16) : (pair >> 8);
@@ -792,7 +797,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     // predecessor unknown (the reset kernel, which writes te, or anything else): nothing is read ahead of it
     if(L.prev_n < 0) ms_wait_for_predecessor();
     for(int j = 0; j < 4; ++j) src.fetch(j, j);
-    src.hw_next = ms_ld32(ln.a32(o_hm, src.qk[0] >> 4));
+    src.hw_next = ms_ld32(ln.a32(o_hm, (src.qk[0] & 0x7fffu) >> 4));
     if(tr) tr[4] = clock64();
     MS_TL(1);
     const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, lnM, lnm, tr);
