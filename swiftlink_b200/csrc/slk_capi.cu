@@ -760,9 +760,15 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
         L.set_n[1] = 1; L.set_person[1][0] = p1; L.set_parent[1][0] = a1;
         L.set_n[2] = 2; L.set_person[2][0] = p0; L.set_parent[2][0] = a0; L.set_person[2][1] = p1; L.set_parent[2][1] = a1;
         L.step_person[1] = p1; L.step_parent[1] = a1; L.step_slot[1] = SLK_SLOT_MEIOSIS + (uint32_t) m1;
+        // the te refresh goes to the single-flip hypothesis with fewer slots below its person
+        const std::vector<uint32_t>& dm = c->plan->host.ms_desc_mask;
+        const int W = c->plan->host.ms_W;
+        int n0 = 0, n1 = 0;
+        for(int w = 0; w < W; ++w) { n0 += __builtin_popcount(dm[(size_t)(p0 - d.F) * W + w]); n1 += __builtin_popcount(dm[(size_t)(p1 - d.F) * W + w]); }
+        L.refresh_set = n1 < n0 ? 1 : 0;
     }
     L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
-    L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == 100) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
+    L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == (getenv("SLK_MS_TL_SLOT") ? atoi(getenv("SLK_MS_TL_SLOT")) : 100)) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
     if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
@@ -844,13 +850,25 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
             for(int b = 0; b < g3; ++b) if(h[off + 2 * b] && h[off + 2 * b] < first) first = h[off + 2 * b];
             std::vector<double> st, en;
             double set_end[3] = {0, 0, 0}, set_dur[3] = {0, 0, 0};
+            std::vector<std::pair<double, int> > slow;
+            std::vector<int> per_sm(1024, 0);
+            for(int b = 0; b < g3; ++b) if(h[off + 2 * b + 1]) per_sm[h[off + 2 * b + 1] & 1023u]++;
             for(int b = 0; b < g3; ++b) {
                 if(!h[off + 2 * b + 1]) continue;
-                const double a = (h[off + 2 * b] - first) * 1e-3, e = (h[off + 2 * b + 1] - first) * 1e-3;
+                const double a = (h[off + 2 * b] - first) * 1e-3, e = ((h[off + 2 * b + 1] >> 10) - first) * 1e-3;
+                slow.push_back(std::make_pair(e, b));
                 st.push_back(a); en.push_back(e);
                 const int set = b / c->plan->ms_grid;
                 set_end[set] = std::max(set_end[set], e); set_dur[set] += (e - a) / c->plan->ms_grid;
             }
+            std::sort(slow.begin(), slow.end());
+            for(int q = 0; q < 12 && q < (int) slow.size(); ++q) {
+                const int b = slow[slow.size() - 1 - q].second, sm = (int)(h[off + 2 * b + 1] & 1023u);
+                fprintf(stderr, "  slow CTA %4d (set %d, loci %5d..) end %.1f us on SM %3d (%d CTAs of this launch there)\n", b, b / c->plan->ms_grid,
+                        32 * (b % c->plan->ms_grid), slow[slow.size() - 1 - q].first, sm, per_sm[sm]);
+            }
+            { int h6 = 0, h7 = 0, h8 = 0; for(int i = 0; i < 1024; ++i) { if(per_sm[i] == 6) ++h6; if(per_sm[i] == 7) ++h7; if(per_sm[i] >= 8) ++h8; }
+              fprintf(stderr, "  SMs with 6 / 7 / 8+ CTAs of the launch: %d / %d / %d\n", h6, h7, h8); }
             std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end());
             if(!st.empty())
                 fprintf(stderr, "step kernel CTAs (%d): start p50 %.1f p99 %.1f max %.1f | end p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f | per set: mean duration %.1f %.1f %.1f last end %.1f %.1f %.1f (us)\n",

@@ -79,6 +79,7 @@ struct SlkMsLaunch {
     int* err;
     // likelihood kernel: hypotheses.  set s flips set_n[s] indicators; a set with no flip writes lncur.
     int nsets;
+    int refresh_set;             // step kernel: the hypothesis set whose threads also bring te up to date (the lighter one)
     int prev_n;                  // step kernel: the predecessor on the stream is the chain kernel of these prev_n (0-2)
     int prev_person[2];          //   meioses (-1: the predecessor is something else, nothing may run ahead of it)
     int prev_parent[2];
@@ -642,7 +643,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     long long* tr = (L.trace && t == 0 && (blockIdx.x & 63) == 0 && (blockIdx.x >> 6) < 12) ? L.trace + 8 * (blockIdx.x >> 6) : 0;
     if(tr) tr[0] = clock64();
     MS_TL(0);
-    if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x] = ms_globaltimer();
+    if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x] = ms_globaltimer() & 0xffffffffffffull;
 
     ms_launch_dependents();
     int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
@@ -804,8 +805,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     if(!src.synced) src.sync();                            // every lane left the walk (impossible graph) in phase 0
     L.lnl[(size_t) set * M + l] = ret;
 
-    // bring the locus's out-of-date entries up to date (current graph: no hypothetical flips)
-    if(set == 0) {
+    // bring the locus's out-of-date entries up to date (current graph: no hypothetical flips); the threads of the
+    // other sets never use those entries (their masks contain the stale slots), so any set may do it: the host picks
+    // the one whose hypothesis has fewer slots to re-derive
+    if(set == L.refresh_set) {
         for(int w = 0; w < W; ++w) {
             uint32_t st = L.stale[(size_t) l * W + w];
             while(st) {
@@ -821,7 +824,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     if(tr) tr[6] = clock64();
     MS_TL(4);
     __syncwarp();
-    if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x + 1] = ms_globaltimer();
+    if(L.timeline && L.tl_cta_off > 0 && t == 0) {
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        L.timeline[L.tl_cta_off + 2 * blockIdx.x + 1] = ((ms_globaltimer() & 0xffffffffffffull) << 10) | (smid & 1023u);
+    }
 }
 
 // ---- (2) + (3): forward pass and backward sampling along the chromosome ------------------------------
