@@ -236,3 +236,34 @@ def test_replicates_in_flight_do_not_change_the_result(tmp_path):
     assert np.isfinite(one).all()
     assert (one == many).all() and (one == two).all()
     h.close()
+
+
+def test_bench_pedigree_sweeps_match_oracle():
+    """the bench workload's pedigree (200 members, 53 founders, 107 typed, cutsets up to 6; first 1 500 SNPs): M-sweeps
+    (939-CTA-scale likelihood launches overlapped with the cluster chain kernel) and L-sweeps reproduce the oracle's
+    graphs bit for bit, and the graph likelihood agrees"""
+    import sys
+    from common import ROOT
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    from oracle import orcapi
+    from swiftlink_b200 import capi, host as H
+    hst = H.Host(*bench.workload_files(1500, "t_sweeps"), lodscores=bench.N_LOD)
+    assert hst.set_peel_by_names(bench.load_order()["order"])
+    d = hst.problem_dict()
+    orc, plan = orcapi.Problem(d), capi.Plan(d)
+    ch = capi.Chain(plan, seed=77, chain_id=3)
+    ch.sequential_imputation(0, hst.M // 2)
+    ref = ch.dg_download()
+    for it in (1, 2, 3, 4):
+        if it == 3:
+            assert orc.ls_sweep(ref, 77, 3, it) == 0
+            ch.lsampler_sweep(it)
+        else:
+            assert orc.ms_sweep(ref, 77, 3, it) == 0
+            ch.msampler_sweep(it)
+        assert (ch.dg_download() == ref).all(), it
+    want = orc.dg_likelihood(ref)
+    assert abs(ch.dg_likelihood() - want) <= TOL * abs(want)
+    ch.close(); plan.close(); hst.close()
