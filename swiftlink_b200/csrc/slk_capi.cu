@@ -684,8 +684,8 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.te = c->ms_te; L.stale = c->ms_stale;
     L.out = c->ms_out;
     L.nsets = 1;
-    L.prev_n = getenv("SLK_MS_DEBUG_PREV0") ? 0 : -1;   // predecessor unknown: the step kernel waits for it before it visits anybody
-                                                        // (the variable is a timing aid for the debug launches: results are invalid)
+    static const bool prev0 = getenv("SLK_MS_DEBUG_PREV0") != 0;  // timing aid for the debug launches only: results are invalid
+    L.prev_n = prev0 ? 0 : -1;   // predecessor unknown: the step kernel waits for it before it visits anybody
     L.seed = c->seed; L.chain = c->chain_id;
     return L;
 }
@@ -769,7 +769,8 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
     }
     L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
     L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == (getenv("SLK_MS_TL_SLOT") ? atoi(getenv("SLK_MS_TL_SLOT")) : 100)) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
-    if(getenv("SLK_MS_FULL_KERNEL")) ms_launch_likelihood(c, L);       // tuning aid: recompute every label each step
+    static const bool full_kernel = getenv("SLK_MS_FULL_KERNEL") != 0;
+    if(full_kernel) ms_launch_likelihood(c, L);                        // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
     L.tl_slot = g_ms_tl_slot + 1;
