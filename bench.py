@@ -456,7 +456,10 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
         "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": ms_lik_ms, "units_per_launch": ms_evals,
         "note": "latency-bound integer walk (one dependent chain per thread, 939 warps resident): neither HBM nor a math "
-                "pipe is the limiter; see DESIGN.md section 4",
+                "pipe is the limiter; in a sweep the launch overlaps the previous pair's chain kernel (programmatic "
+                "dependent launch), launch_ms is the kernel timed alone; see DESIGN.md section 4",
+        "ncu": {"issue_slots_busy_pct": traffic.get("_issue_active_pct", {}), "fp64_pipe_busy_pct": traffic.get("_fp64_pipe_pct", {}),
+                "source": traffic.get("_issue_source")},
         "ms_chain_kernel": {"launch_ms": ms_chain_ms, "steps_per_launch": 2, "traffic": traffic.get("slk_ms_chain_kernel")},
         "lsampler_kernel": {
             "bound": "fp64", "achieved": ls_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
