@@ -178,6 +178,14 @@ int slk_lsampler_locus_by_locus(slk_chain* chain, uint64_t iteration);
    (sequential_imputation.cc:76-108); reading it synchronises. */
 int slk_sequential_imputation(slk_chain* chain, uint64_t run, int start_locus, double* log_weight);
 
+/* SequentialImputation::parallel_run (sequential_imputation.cc:47-115): n_runs independent walks of
+   LocusSampler::start_from -- run numbers first_run .. first_run + n_runs - 1, walk i starting at start_loci[i] --
+   in one launch per wave of resident teams (one team per walk) instead of one SM-filling launch per walk.  Draws,
+   weights and graphs are those of n_runs calls of slk_sequential_imputation; log_weights[n_runs] (optional) receives
+   every walk's log weight, *best_run the index of the first maximal one, whose graph becomes the chain's graph. */
+int slk_sequential_imputation_batch(slk_chain* chain, uint64_t first_run, int n_runs, const int32_t* start_loci,
+                                    double* log_weights, int32_t* best_run);
+
 /* ---- M-sampler: replaces run_gpu_msampler_reset_kernel / run_gpu_msampler_likelihood_kernel /
         run_gpu_msampler_sampling_kernel (cuda_common.h:240-244, cuda_msampler2.cu) and the CPU
         MeiosisSampler (meiosis_sampler.cc:17-203) the live reference falls back to --------------- */

@@ -23,7 +23,7 @@ SYMBOLS = [
     "slk_plan_create", "slk_plan_destroy", "slk_plan_stats", "slk_plan_validate",
     "slk_chain_create", "slk_chain_destroy", "slk_chain_set_stream", "slk_chain_sync",
     "slk_dg_upload", "slk_dg_download", "slk_dg_swap",
-    "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation",
+    "slk_lsampler_window", "slk_lsampler_sweep", "slk_lsampler_locus_by_locus", "slk_sequential_imputation", "slk_sequential_imputation_batch",
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood", "slk_elod_run", "slk_debug_elod_graphs",
     "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
@@ -233,6 +233,17 @@ class Chain(object):
         _check(self.L.slk_sequential_imputation(self.h, C.c_uint64(run), int(start_locus),
                                                 C.byref(w) if want_weight else None))
         return w.value if want_weight else None
+
+    def sequential_imputation_batch(self, start_loci, first_run=0):
+        """n independent start_from walks in one launch per wave of teams; returns (log weights, index of the best),
+        the best walk's graph becomes the chain's graph"""
+        st = np.ascontiguousarray(start_loci, np.int32)
+        w = np.zeros(len(st))
+        best = C.c_int32(-1)
+        _check(self.L.slk_sequential_imputation_batch(self.h, C.c_uint64(first_run), int(len(st)),
+                                                      st.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      w.ctypes.data_as(C.POINTER(C.c_double)), C.byref(best)))
+        return w, int(best.value)
 
     def lodscore_init(self):
         _check(self.L.slk_lodscore_init(self.h))

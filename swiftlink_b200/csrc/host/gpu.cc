@@ -83,18 +83,16 @@ double GPUMarkovChain::sequential_imputation(DescentGraph& dg, int iterations) {
         die_on(slk_dg_download(chain, dg.get_internal_ptr()), "sequential imputation (download)");
         return 0.0;
     }
+    // the reference runs its `iterations` walks on the OpenMP threads and keeps the best (sequential_imputation.cc:
+    // 47-115); here they are teams of one launch (slk_sequential_imputation_batch)
     HostRng rng(options.seed ^ (0x5349ull << 32) ^ (uint64_t) seq_num);
-    double best = -1e300;
-    std::vector<int> keep(dg.get_internal_size() / sizeof(int));
-    for(int run = 0; run < iterations; ++run) {
-        double w = 0.0;
-        die_on(slk_sequential_imputation(chain, (uint64_t) run, rng.uniform_int(M), &w), "sequential imputation");
-        if(w > best) {
-            best = w;
-            die_on(slk_dg_download(chain, keep.data()), "sequential imputation (download)");
-        }
-    }
-    memcpy(dg.get_internal_ptr(), keep.data(), dg.get_internal_size());
+    std::vector<int32_t> starts((size_t) iterations);
+    for(int run = 0; run < iterations; ++run) starts[run] = (int32_t) rng.uniform_int(M);
+    std::vector<double> weights((size_t) iterations);
+    int32_t best_run = -1;
+    die_on(slk_sequential_imputation_batch(chain, 0, iterations, starts.data(), weights.data(), &best_run), "sequential imputation");
+    const double best = best_run >= 0 ? weights[best_run] : -1e300;
+    die_on(slk_dg_download(chain, dg.get_internal_ptr()), "sequential imputation (download)");
     printf("starting likelihood (log10) = %.3f\n", best / log(10.0));
     return best;
 }

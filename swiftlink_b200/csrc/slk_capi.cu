@@ -567,6 +567,67 @@ int slk_sequential_imputation(slk_chain* c, uint64_t run, int start_locus, doubl
     return SLK_OK;
 }
 
+// SequentialImputation::parallel_run (sequential_imputation.cc:47-115): `n_runs` independent start_from walks
+// (run numbers first_run .. first_run + n_runs - 1, start locus start_loci[i]), one team each, in waves of as many
+// teams as are resident; the best (first maximal) weight's graph becomes the chain's graph.  Same draws, weights
+// and graphs as n_runs calls of slk_sequential_imputation, which uses one team of one SM at a time.
+int slk_sequential_imputation_batch(slk_chain* c, uint64_t first_run, int n_runs, const int32_t* start_loci,
+                                    double* log_weights, int32_t* best_run) {
+    if(!c || !start_loci || n_runs < 1) return fail(SLK_ERR_INVALID, "null argument");
+    slk_plan* p = c->plan;
+    const SlkDevPlan& d = p->dev;
+    for(int i = 0; i < n_runs; ++i)
+        if(start_loci[i] < 0 || start_loci[i] >= d.M) return fail(SLK_ERR_INVALID, "start locus out of range");
+    CU(cudaSetDevice(p->device));
+    const size_t cells = (size_t) d.M * d.N;
+    const int tpc = d.ls.cta_threads / d.ls.team_threads;
+    const int teams = p->ls_blocks_per_sm * p->sm_count * tpc;        // one wave: the scratch slab has a slice per resident team
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int wave = std::min(n_runs, teams);
+    wave = (int) std::max<size_t>(1, std::min<size_t>((size_t) wave, (free_b / 2) / std::max<size_t>(cells, 1)));
+    uint8_t* graphs = 0; int* starts = 0; double* weights = 0;
+    CU(cudaMalloc((void**) &graphs, cells * (size_t) wave));
+    cudaError_t e = cudaMalloc((void**) &starts, sizeof(int) * (size_t) wave);
+    if(e == cudaSuccess) e = cudaMalloc((void**) &weights, sizeof(double) * (size_t) wave);
+    int rc = e == cudaSuccess ? SLK_OK : fail(SLK_ERR_CUDA, "sequential imputation buffers: %s", cudaGetErrorString(e));
+    std::vector<double> w((size_t) wave);
+    double best = 0.0; int best_i = -1;
+    c->ms_cur_valid = false;
+    for(int r0 = 0; r0 < n_runs && rc == SLK_OK; r0 += wave) {
+        const int n = std::min(wave, n_runs - r0);
+        e = cudaMemsetAsync(graphs, 0, cells * (size_t) n, c->stream);
+        if(e == cudaSuccess) e = cudaMemcpyAsync(starts, start_loci + r0, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, c->stream);
+        if(e != cudaSuccess) { rc = fail(SLK_ERR_CUDA, "sequential imputation: %s", cudaGetErrorString(e)); break; }
+        SlkLaunch L = base_launch(c);
+        L.dgp = graphs;
+        L.iteration = first_run + (uint64_t) r0;
+        L.window = 1; L.offset = 0; L.nunits = d.M;
+        L.si_start = 0; L.si_batch = n; L.si_starts = starts;
+        L.dump_result = weights;
+        const int grid = std::min((n + tpc - 1) / tpc, p->ls_blocks_per_sm * p->sm_count);
+        launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
+        e = cudaGetLastError();
+        if(e == cudaSuccess) e = cudaMemcpyAsync(w.data(), weights, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost, c->stream);
+        if(e != cudaSuccess) { rc = fail(SLK_ERR_CUDA, "sequential imputation: %s", cudaGetErrorString(e)); break; }
+        rc = check_device_error(c);
+        if(rc != SLK_OK) break;
+        int wave_best = -1;
+        for(int i = 0; i < n; ++i) {
+            if(log_weights) log_weights[r0 + i] = w[i];
+            if(best_i < 0 || w[i] > best) { best = w[i]; best_i = r0 + i; wave_best = i; }
+        }
+        if(wave_best >= 0) {
+            e = cudaMemcpyAsync(c->dgp, graphs + cells * (size_t) wave_best, cells, cudaMemcpyDeviceToDevice, c->stream);
+            if(e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if(e != cudaSuccess) rc = fail(SLK_ERR_CUDA, "sequential imputation: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(graphs); cudaFree(starts); cudaFree(weights);
+    if(best_run) *best_run = best_i;
+    return rc;
+}
+
 int slk_lsampler_sweep(slk_chain* c, uint64_t iteration) {
     if(!c) return fail(SLK_ERR_INVALID, "null chain");
     // same draw as the oracle: first parity class of the sweep

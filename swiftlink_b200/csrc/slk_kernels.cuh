@@ -53,6 +53,8 @@ struct SlkLaunch {
     int nunits;
     int ignore_left, ignore_right;
     int si_start;                // >= 0: sequential imputation walk from this locus (one team, loci in sequence)
+    int si_batch;                // > 0: that many independent walks, one per team (graph g in rows [g M, (g + 1) M) of dgp)
+    const int* si_starts;        // [si_batch] start locus of each walk
     int no_dg;                   // trait peel without a descent graph (P(T))
     int accumulate;              // LOD: 1 = log-sum into lod[], 0 = write dump_result/dump_prob
     int unit_base;               // LOD: first unit (debug: interval * nlod)
@@ -618,14 +620,23 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
     const int N = P.N, F = P.F, M = P.M;
     const bool sex_linked = P.sex_linked != 0;
 
-    for(int unit = gteam; unit < L.nunits; unit += total_teams) {
+    // Batched sequential imputation (L.si_batch > 0): team g walks graph g -- M loci in sequence, rows [g M, (g + 1) M)
+    // of the graph buffer, run number L.iteration + g, start locus L.si_starts[g] -- so that hundreds of the
+    // reference's independent start_from runs (sequential_imputation.cc:47-115) share one launch.
+    const int si_batch = L.si_batch;
+    for(int graph = si_batch ? gteam : 0; graph < (si_batch ? si_batch : 1); graph += (si_batch ? total_teams : 1)) {
+    uint8_t* const dgp = L.dgp + (si_batch ? (size_t) graph * (size_t) M * (size_t) N : (size_t) 0);
+    const uint64_t iteration = L.iteration + (uint64_t)(si_batch ? graph : 0);
+    const int si_start = si_batch ? L.si_starts[graph] : L.si_start;
+    double* const si_weight = L.dump_result ? L.dump_result + (si_batch ? graph : 0) : (double*) 0;
+    for(int unit = si_batch ? 0 : gteam; unit < L.nunits; unit += (si_batch ? 1 : total_teams)) {
         int locus = L.offset + unit * L.window;
         bool ign_left = L.ignore_left != 0, ign_right = L.ignore_right != 0;
-        if(L.si_start >= 0) {
+        if(si_start >= 0) {
             // LocusSampler::start_from (locus_sampler2.cc:209-241): the start locus alone, then
             // leftwards conditioning on the right neighbour only, then rightwards on the left one
-            if(unit == 0)               { locus = L.si_start; ign_left = true; ign_right = true; }
-            else if(unit <= L.si_start) { locus = L.si_start - unit; ign_left = true; ign_right = false; }
+            if(unit == 0)               { locus = si_start; ign_left = true; ign_right = true; }
+            else if(unit <= si_start) { locus = si_start - unit; ign_left = true; ign_right = false; }
             else                        { locus = unit; ign_left = false; ign_right = true; }
         }
         const int plocus = L.period ? locus % L.period : locus;          // row of the plan tables
@@ -637,14 +648,14 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
         for(int i = tid; i < N; i += T) {
             tm.gc[i] = P.gcode[(size_t) plocus * N + i];
-            tm.dgl[i] = has_left ? L.dgp[(size_t)(locus - 1) * N + i] : 0;
-            tm.dgr[i] = has_right ? L.dgp[(size_t)(locus + 1) * N + i] : 0;
+            tm.dgl[i] = has_left ? dgp[(size_t)(locus - 1) * N + i] : 0;
+            tm.dgr[i] = has_right ? dgp[(size_t)(locus + 1) * N + i] : 0;
         }
         for(int i = tid; i < 28; i += T)
             tm.scal[16 + i] = (i < 20) ? c_prior[i >> 2][i & 3] : P.fprior[(size_t) plocus * 8 + (i - 20)];
         // the genotype draws of this locus, one per peel op (Philox keyed by chain, iteration, locus, op)
         for(int op = tid; op < P.nops; op += T)
-            tm.ru[op] = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t)(locus + L.row_base), (uint32_t) op);
+            tm.ru[op] = slk_uniform(L.seed, L.chain, iteration, (uint32_t)(locus + L.row_base), (uint32_t) op);
         if(tid == 0) {
             // sampler_rfunction.h:84-100: theta2 (left interval) / theta (right interval)
             double th2 = 1.0, ath2 = 1.0, th = 1.0, ath = 1.0;
@@ -722,9 +733,9 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
 
         const uint32_t* last_rec = pg.stream + pg.op_start[P.last_op];
         const double result = mat_load(mat_ref(tm, (int) last_rec[1]), 0);
-        if(L.dump_result && tid == 0) {
-            if(L.si_start >= 0) L.dump_result[0] = (unit == 0 ? 0.0 : L.dump_result[0]) + log(result);   // SI weight
-            else L.dump_result[0] = result;
+        if(si_weight && tid == 0) {
+            if(si_start >= 0) si_weight[0] = (unit == 0 ? 0.0 : si_weight[0]) + log(result);   // SI weight
+            else si_weight[0] = result;
         }
         if(result == 0.0) {
             // locus_sampler2.cc:137-142 exits the program; here the locus is left untouched
@@ -823,18 +834,19 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
                         p0 *= (v == 0) ? ith : th;
                         p1 *= (v == 1) ? ith : th;
                     }
-                    const double r = slk_uniform(L.seed, L.chain, L.iteration, (uint32_t)(locus + L.row_base),
+                    const double r = slk_uniform(L.seed, L.chain, iteration, (uint32_t)(locus + L.row_base),
                                                  (uint32_t)(P.nops + 2 * i + parent));
                     mi = (r < p0 / (p0 + p1)) ? 0u : 1u;
                 }
                 out |= mi << parent;
             }
-            L.dgp[(size_t) locus * N + i] = (uint8_t) out;
+            dgp[(size_t) locus * N + i] = (uint8_t) out;
         }
         if(tracing) L.trace[tstamp++] = clock64();
         if(DBG && L.dump_pmk) for(int i = tid; i < N; i += T) L.dump_pmk[i] = tm.pmk[i];
-        if(L.si_start >= 0) __threadfence();        // the next locus of the walk reads the row just written
+        if(si_start >= 0) __threadfence();          // the next locus of the walk reads the row just written
         team_sync<T>(team);
+    }
     }
 }
 

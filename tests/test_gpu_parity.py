@@ -213,6 +213,30 @@ def test_sequential_imputation_matches_oracle(gpu, name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_sequential_imputation_batch_matches_single_walks(gpu, name):
+    """SequentialImputation::parallel_run as one launch (a team per walk): every walk's weight equals the oracle's and
+    the single-walk entry point's, and the chain ends up with the graph of the first maximal weight"""
+    fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
+    rng = np.random.default_rng(17)
+    n = 37
+    starts = rng.integers(0, orc.M, size=n)
+    w, best = ch.sequential_imputation_batch(starts, first_run=5)
+    got = ch.dg_download()
+    want_w, graphs = [], []
+    for i in range(n):
+        dg = np.zeros_like(got)
+        want_w.append(orc.si_start_from(dg, int(starts[i]), 77, 3, 5 + i))
+        graphs.append(dg)
+    want_w = np.array(want_w)
+    assert np.all(np.abs(w - want_w) <= LOG_TOL * np.abs(want_w))
+    assert best == int(np.argmax(w)) and (got == graphs[best]).all()
+    # and the one-walk-per-launch entry point agrees bit for bit
+    for i in (0, n // 2, n - 1):
+        w1 = ch.sequential_imputation(run=5 + i, start_locus=int(starts[i]))
+        assert w1 == w[i] and (ch.dg_download() == graphs[i]).all()
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_locus_by_locus_matches_oracle(gpu, name):
     """the -s 0 start state: every locus drawn on its own, all loci in one launch"""
     fx, orc, ch = golden(name), oracle_problem(name), gpu(name)
