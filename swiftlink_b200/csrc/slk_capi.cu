@@ -828,6 +828,38 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
         for(int w = 0; w < W; ++w) { n0 += __builtin_popcount(dm[(size_t)(p0 - d.F) * W + w]); n1 += __builtin_popcount(dm[(size_t)(p1 - d.F) * W + w]); }
         L.refresh_set = n1 < n0 ? 1 : 0;
     }
+    // the launch's record (visiting order, phase boundary, hypothesis slot masks), when it fits the parameter block
+    {
+        const slk::HostPlan& hp = c->plan->host;
+        const int nt = d.ms.n_typed, W = hp.ms_W, words = slk_ms_pair_rec_words(nt, W);
+        static const bool no_rec = getenv("SLK_MS_NO_REC") != 0;          // tuning aid: let the kernel derive it
+        if(words <= SLK_MS_REC_WORDS && nt > 0 && !no_rec) {
+            std::vector<uint32_t> prev((size_t) W, L.prev_n < 0 ? 0xffffffffu : 0u);
+            auto add = [&](std::vector<uint32_t>& m, int person, int parent) {
+                for(int w = 0; w < W; ++w) m[w] |= hp.ms_desc_mask[(size_t)(person - d.F) * W + w];
+                const int kk = hp.ms_typed_index[person];
+                if(kk >= 0) m[(2 * kk + parent) >> 5] |= 1u << ((2 * kk + parent) & 31);
+            };
+            for(int j = 0; j < L.prev_n; ++j) add(prev, L.prev_person[j], L.prev_parent[j]);
+            uint32_t* rec = L.rec;
+            memset(rec, 0, sizeof(uint32_t) * (size_t) words);
+            for(int s = 0; s < L.nsets; ++s) {
+                std::vector<uint32_t> hm((size_t) W, 0u);
+                for(int j = 0; j < L.set_n[s]; ++j) add(hm, L.set_person[s][j], L.set_parent[s][j]);
+                for(int w = 0; w < W; ++w) rec[1 + s * W + w] = hm[w];
+            }
+            uint16_t* ord = (uint16_t*)(rec + 1 + 3 * W);
+            int n = 0;
+            for(int pass = 0; pass < 2; ++pass) {
+                for(int k = 0; k < nt; ++k) {
+                    const bool aff = ((prev[k >> 4] >> (2 * (k & 15))) & 3u) != 0;
+                    if(aff == (pass == 1)) ord[n++] = (uint16_t)(k | (hp.ms_typed_auto[k] ? 0x8000 : 0));
+                }
+                if(pass == 0) rec[0] = (uint32_t) n;
+            }
+            L.rec_n = words;
+        }
+    }
     L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
     L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == (getenv("SLK_MS_TL_SLOT") ? atoi(getenv("SLK_MS_TL_SLOT")) : 100)) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
     static const bool full_kernel = getenv("SLK_MS_FULL_KERNEL") != 0;

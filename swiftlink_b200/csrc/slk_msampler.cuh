@@ -60,6 +60,7 @@
 #define SLK_SLOT_MEIOSIS  0x40000000u
 
 #define SLK_MS_MAXSETS 3
+#define SLK_MS_REC_WORDS 448
 #define SLK_MS_MAXGROUPS 4095
 
 struct SlkMsLaunch {
@@ -99,6 +100,10 @@ struct SlkMsLaunch {
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
     const double* log_1mtheta;
+    // step kernel: host-built record of this launch (slk_ms_pair_rec_words words; rec_n = 0: none, the kernel derives
+    // it).  It travels in the kernel parameters: no copy to order against the launches, no buffer to keep alive.
+    int rec_n;
+    uint32_t rec[SLK_MS_REC_WORDS];
 };
 
 // Programmatic dependent launch (sm_90+): the step and chain kernels of a sweep alternate on one stream, each
@@ -633,6 +638,15 @@ static inline MsStepLayout slk_ms_step_layout(int N, int F, int nt, int W) {
     return L;
 }
 
+// Host-built record of one launch of a sweep (all records of a sweep are uploaded with one copy before its first
+// kernel): word 0 = number of typed people the predecessor cannot affect (the phase boundary), then the slot masks of
+// the three hypotheses (3 x W words, without the locus's stale slots), then the visiting order, two 16-bit entries per
+// word (index | single-allele flag << 15).  With a record the per-warp prologue is one batch of independent loads.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int slk_ms_pair_rec_words(int nt, int W) { return 1 + 3 * W + (nt + 1) / 2; }
+
 template<bool WIDE>
 __global__ void __launch_bounds__(32)
 slk_ms_step_kernel(const SlkMsLaunch L) {
@@ -651,6 +665,17 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     uint16_t* s_typed = (uint16_t*)(s_fa + N);             // [nt]
     uint8_t* s_auto = (uint8_t*)(s_typed + nt);            // [nt]
     for(int i = t; i < N; i += 32) { s_mo[i] = L.mother[i]; s_fa[i] = L.father[i]; }
+    uint32_t* s_prev = (uint32_t*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u));      // [W]
+    uint16_t* s_ord = (uint16_t*)(s_prev + W);                                      // [nt]
+    int* s_n0 = (int*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u) + 4u * W + ((2u * nt + 3u) & ~3u));
+    const bool rec = L.rec_n > 0;
+    if(rec) {
+        // the order and the phase boundary come from the host
+        for(int k = t; k < nt; k += 32) s_typed[k] = L.ms.typed[k];
+        for(int k = t; k < (nt + 1) / 2; k += 32) ((uint32_t*) s_ord)[k] = L.rec[1 + 3 * W + k];
+        if(t == 0) *s_n0 = (int) L.rec[0];
+    }
+    else {
     for(int k = t; k < nt; k += 32) {
         const int p = L.ms.typed[k];
         s_typed[k] = (uint16_t) p;
@@ -659,9 +684,6 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     // slots the predecessor kernel's flips can change (its two meioses: own slot and everything below; all of them
     // if the predecessor is not a chain kernel), and the visiting order of the walk: first the typed people who
     // have none of those slots (ascending), then the others (ascending)
-    uint32_t* s_prev = (uint32_t*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u));      // [W]
-    uint16_t* s_ord = (uint16_t*)(s_prev + W);                                      // [nt]
-    int* s_n0 = (int*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u) + 4u * W + ((2u * nt + 3u) & ~3u));
     for(int w = t; w < W; w += 32) {
         uint32_t m = L.prev_n < 0 ? 0xffffffffu : 0u;
         for(int j = 0; j < L.prev_n; ++j) {
@@ -685,6 +707,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
             if(pass == 0 && t == 0) *s_n0 = n;
         }
     }
+    }
     __syncwarp();
 
     const int nblk = (M + 31) >> 5;
@@ -700,6 +723,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     const uint32_t o_grp = lay.grp * 32u, o_cnt = lay.cnt * 32u, o_fa = lay.fa * 32u, o_hm = lay.hmask * 32u;
     const uint8_t* row = L.dgp + (size_t) l * N;
     // the hypothesis's slot mask, without the locus's stale slots: those are the predecessor kernel's to write
+    if(rec) {
+        for(int w = 0; w < W; ++w) ms_st32(ln.a32(o_hm, w), L.rec[1 + set * W + w]);
+    }
+    else {
     for(int w = 0; w < W; ++w) {
         uint32_t h = 0;
         if(p0 >= 0) h |= L.ms.desc_mask[(size_t)(p0 - F) * W + w];
@@ -713,6 +740,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     if(p1 >= 0) {
         const int k1 = L.ms.typed_index[p1];
         if(k1 >= 0) { const uint32_t q = 2 * k1 + a1; ms_st32(ln.a32(o_hm, q >> 5), ms_ld32(ln.a32(o_hm, q >> 5)) | (1u << (q & 31))); }
+    }
     }
 
     // The walk in two phases.  The predecessor on the stream (the chain kernel of the previous pair of steps) flips

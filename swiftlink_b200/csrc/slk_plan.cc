@@ -508,6 +508,8 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
         }
         for(int i = 0; i < N; ++i) if(pb.typed[i]) hp.ms_typed.push_back((uint16_t) i);
         const int nt = (int) hp.ms_typed.size();
+        hp.ms_typed_auto.assign((size_t) std::max(nt, 1), 0);
+        for(int k = 0; k < nt; ++k) hp.ms_typed_auto[k] = (pb.sex_linked && pb.sex[hp.ms_typed[k]] == SLK_MALE) ? 1 : 0;
         hp.ms_obsT.resize((size_t) std::max(nt, 1) * M);
         for(int k = 0; k < nt; ++k)
             for(int l = 0; l < M; ++l) hp.ms_obsT[(size_t) k * M + l] = pb.genotypes[(size_t) hp.ms_typed[k] * M + l];

@@ -48,6 +48,7 @@ struct HostPlan {
     // M-sampler
     bool ms_available;
     std::vector<uint16_t> ms_seq, ms_typed;
+    std::vector<uint8_t> ms_typed_auto;  // [nt] x-linked male: the maternal allele only
     std::vector<uint8_t> ms_obsT;        // [n_typed][M]
     std::vector<double> ms_minor, ms_lnmajor, ms_lnminor;   // [M]
     std::vector<int32_t> ms_ordering;    // meioses an M-sweep visits (markov_chain.cc:68-80)

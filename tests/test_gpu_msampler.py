@@ -267,3 +267,21 @@ def test_bench_pedigree_sweeps_match_oracle():
     want = orc.dg_likelihood(ref)
     assert abs(ch.dg_likelihood() - want) <= TOL * abs(want)
     ch.close(); plan.close(); hst.close()
+
+
+@pytest.mark.parametrize("env", ["SLK_MS_NO_REC", "SLK_NO_PDL", "SLK_MS_NO_PREFIX"])
+def test_msampler_fallback_paths(env):
+    """the library's alternative launch paths -- launch record derived inside the kernel instead of on the host, plain
+    launches instead of programmatic dependent ones, nothing running ahead of the predecessor -- give the same graphs
+    (the switches are read once per process, hence the subprocess)"""
+    import os
+    import subprocess
+    import sys
+    from common import ROOT
+    e = dict(os.environ)
+    e[env] = "1"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_msampler.py"), "-q", "-x",
+                          "-k", "test_sweeps_match_oracle or test_steps_match_oracle"], env=e, capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "passed" in out.stdout
