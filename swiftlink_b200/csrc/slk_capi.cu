@@ -262,19 +262,8 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
     for(int k = 0; k < 2; ++k) {
         const slk::HostProgram& hp = k ? h.lod : h.ls;
         SlkProgram& dp = k ? d.lod : d.ls;
-#define UPP(field) if(e == cudaSuccess) e = upload(hp.field, &dp.field, p->owned)
-        UPP(stream); UPP(op_start); UPP(lops); UPP(lpf); UPP(flevel_quads); UPP(flevel_start); UPP(bops); UPP(blevel_start);
-#undef UPP
-        dp.stream_words = (int) hp.stream.size();
-        dp.n_flevels = (int) hp.flevel_start.size() - 1;
-        dp.n_blevels = (int) hp.blevel_start.size() - 1;
-        dp.arena_doubles = hp.arena_doubles;
-        dp.smem_doubles = hp.smem_doubles;
-        dp.team_threads = hp.team_threads;
-        dp.cta_threads = hp.cta_threads;
-        dp.prog_smem_bytes = hp.prog_smem_bytes;
-        dp.team_smem_bytes = hp.team_smem_bytes;
-        dp.table_doubles_per_child = hp.table_doubles_per_child;
+        dp = hp.layout;
+        if(e == cudaSuccess) e = upload(hp.blob, &dp.blob, p->owned);
     }
     UP(ms.seq, h.ms_seq); UP(ms.typed, h.ms_typed); UP(ms.obsT, h.ms_obsT); UP(ms.minor, h.ms_minor);
     UP(ms.lnmajor, h.ms_lnmajor); UP(ms.lnminor, h.ms_lnminor);
@@ -348,8 +337,8 @@ void slk_plan_destroy(slk_plan* p) {
 static int fill_stats(const slk::HostPlan& h, const slk_plan* p, double* out, int cap) {
     double v[20] = {
         (double) h.nops, (double) h.sum_cells, (double) h.sum_presum, h.flops_ls, h.flops_lod,
-        (double)(h.ls.flevel_start.size() - 1), (double)(h.ls.blevel_start.size() - 1),
-        (double)(h.lod.flevel_start.size() - 1), (double) h.ls.arena_doubles, (double) h.lod.arena_doubles,
+        (double) h.ls.flevel_items.size(), (double)(h.ls.blevel_start.size() - 1),
+        (double) h.lod.flevel_items.size(), (double) h.ls.arena_doubles, (double) h.lod.arena_doubles,
         (double) h.lod.valid_cells, (double) h.max_cutset, (double) h.ls.team_threads, (double) h.lod.team_threads,
         (double) h.ls.smem_doubles, (double) h.lod.smem_doubles,
         p ? (double) p->ls_blocks_per_sm : 0.0, p ? (double) p->lod_blocks_per_sm : 0.0,

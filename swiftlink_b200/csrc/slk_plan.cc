@@ -10,6 +10,7 @@
 //   * trait validity   = disease_prob != 0 on every cutset digit      (:162-179)
 //   * marker priors    = Person::populate_trait_prob_cache            (person.cc:224-299)
 #include "slk_plan.h"
+#include "slk_peel.h"
 
 #include <algorithm>
 #include <cmath>
@@ -113,8 +114,37 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, HostProgram& pr) {
+// padded size of a 4^c matrix: two doubles after every 16 (shared-memory bank spreading), even
+static int padded_size(int ncut) {
+    const int n = 1 << (2 * ncut);
+    const int p = n + ((n >> 4) << 1);
+    return (p + 1) & ~1;
+}
+
+static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, HostProgram& pr, std::string& err) {
     const int nops = pb.n_ops;
+    const int N = pb.n_members;
+
+    // ---- the global order of people: position in the peel sequence ----
+    std::vector<int> ppos(N, -1);
+    for(int i = 0; i < nops; ++i) ppos[pb.ops[i].peelnode] = i;
+    std::vector<std::vector<int> > scut(nops);
+    for(int i = 0; i < nops; ++i) {
+        const slk_peel_op& op = pb.ops[i];
+        scut[i].assign(op.cutset, op.cutset + op.ncut);
+        std::sort(scut[i].begin(), scut[i].end(), [&](int a, int b) { return ppos[a] < ppos[b]; });
+        for(int d = 0; d < op.ncut; ++d) {
+            if(ppos[scut[i][d]] <= i) {
+                std::ostringstream e; e << "op " << i << ": cutset member " << scut[i][d] << " is peeled before the op that is keyed on it";
+                err = e.str(); return false;
+            }
+        }
+    }
+    auto spos = [&](int i, int person) -> int {
+        for(size_t d = 0; d < scut[i].size(); ++d) if(scut[i][d] == person) return (int) d;
+        if(pb.ops[i].peelnode == person) return SLK_POS_PEEL;
+        return -1;
+    };
 
     // ---- forward levels: an op runs after every function it consumes ----
     std::vector<int> flevel(nops, 0), consumer(nops, -1);
@@ -128,103 +158,93 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         flevel[i] = lv;
         n_flevels = std::max(n_flevels, lv + 1);
     }
+    pr.flevel = flevel;
 
     // ---- backward levels: an op is sampled after the ops that peel its cutset members ----
-    std::vector<int> peeled_by(pb.n_members, -1);
-    for(int i = 0; i < nops; ++i) peeled_by[pb.ops[i].peelnode] = i;
     std::vector<int> blevel(nops, 0);
     int n_blevels = 0;
     for(int i = nops - 1; i >= 0; --i) {
         int lv = 0;
-        for(int d = 0; d < pb.ops[i].ncut; ++d) lv = std::max(lv, blevel[peeled_by[pb.ops[i].cutset[d]]] + 1);
+        for(int d = 0; d < pb.ops[i].ncut; ++d) lv = std::max(lv, blevel[ppos[pb.ops[i].cutset[d]]] + 1);
         blevel[i] = lv;
         n_blevels = std::max(n_blevels, lv + 1);
     }
 
-    // ---- static validity: cells per op ----
+    // ---- static validity: cells per op (sorted digits) ----
     std::vector<long> ncells(nops), nrows(nops);
     std::vector<uint64_t> static_lmw(nops, 0);
-    std::vector<uint8_t> dmask(pb.n_members, 0);
-    for(int i = 0; i < pb.n_members; ++i)
+    std::vector<uint8_t> dmask(N, 0);
+    for(int i = 0; i < N; ++i)
         for(int g = 0; g < 4; ++g) if(pb.disease_prob[i*4 + g] != 0.0) dmask[i] |= (uint8_t)(1 << g);
     pr.valid_cells = 0;
     for(int i = 0; i < nops; ++i) {
         const slk_peel_op& op = pb.ops[i];
-        long n = 1;
+        long n = 1, rows = 1;
         for(int d = 0; d < op.ncut; ++d) {
-            uint8_t m = trait ? dmask[op.cutset[d]] : 15;
+            uint8_t m = trait ? dmask[scut[i][d]] : 15;
             static_lmw[i] |= (uint64_t) m << (4 * d);
             n *= __builtin_popcount(m);
+            if(d > 0) rows *= __builtin_popcount(m);
         }
         ncells[i] = n;
         // rows = valid assignments of digits 1..c-1 (digit 0 is the register tile's slot axis)
-        nrows[i] = (op.ncut > 0) ? n / __builtin_popcount((unsigned)(static_lmw[i] & 15u)) : 1;
+        nrows[i] = rows;
         pr.valid_cells += n;
     }
 
-    // ---- arena ----
-    pr.mat_off.assign(nops, 0);
-    std::vector<int> level_order;
-    for(int lv = 0; lv < n_flevels; ++lv) for(int i = 0; i < nops; ++i) if(flevel[i] == lv) level_order.push_back(i);
+    // ---- geometry (needed before the arena: what stays in shared memory depends on it) ----
+    const int tpc_doubles = trait ? 4 : 16;
+    pr.table_doubles_per_child = tpc_doubles;
+    const int table_bytes = slk_team_layout(N, pb.n_founders, nops, 0, tpc_doubles).total;
+    const long work = trait ? pr.valid_cells : hp.sum_cells;
+    int team = 32;
+    if(work > 1024)  team = 64;
+    if(work > 4096)  team = 128;
+    if(work > 8192)  team = 256;
+    long padded_total = 0;
+    for(int i = 0; i < nops; ++i) padded_total += padded_size(pb.ops[i].ncut);
+    // One unit is latency bound (a chain of ~50 dependent levels), so the SM needs several units in
+    // flight.  When the whole arena of a team would crowd the others out of shared memory, only the
+    // small matrices (cutset <= 4, the ones hit by the many small latency-bound ops) stay in shared
+    // memory and the few large ones go to the L2-resident global slab.
+    const bool hybrid = (size_t) padded_total * 8 + table_bytes > 100 * 1024;
+    team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
+    if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
+    pr.team_threads = team;
+    // the CTA holds a whole number of teams, at most SLK_LS_MAXTHREADS (768) threads and at most 15 teams
+    // (one named barrier each)
+    int cta = env_int(trait ? "SLK_LOD_CTA_THREADS" : "SLK_LS_CTA_THREADS", env_int("SLK_CTA_THREADS", hybrid ? 768 : 128));
+    cta = std::max(team, std::min(cta, 768));
+    cta = (cta / team) * team;
+    if(team > 32 && cta / team > 15) cta = 15 * team;
+    pr.cta_threads = cta;
+    const int teams_per_cta = pr.cta_threads / team;
 
-    if(trait) {
-        // matrices die after the level of their single consumer
-        Liveness lv;
-        std::vector<std::vector<int> > dies_after(n_flevels);
-        for(int i = 0; i < nops; ++i) if(consumer[i] >= 0) dies_after[flevel[consumer[i]]].push_back(i);
-        size_t k = 0;
-        for(int l = 0; l < n_flevels; ++l) {
-            for(; k < level_order.size() && flevel[level_order[k]] == l; ++k) {
-                int i = level_order[k];
-                pr.mat_off[i] = lv.alloc(1 << (2 * pb.ops[i].ncut));
-            }
-            for(size_t q = 0; q < dies_after[l].size(); ++q) {
-                int i = dies_after[l][q];
-                lv.release(pr.mat_off[i], 1 << (2 * pb.ops[i].ncut));
-            }
-        }
-        int hw = 0;
-        for(int i = 0; i < nops; ++i) hw = std::max(hw, pr.mat_off[i] + (1 << (2 * pb.ops[i].ncut)));
-        pr.arena_doubles = hw;
-    }
-    else {
-        // everything stays live until the backward pass; large matrices go last so that, if the
-        // arena outgrows shared memory, it is the few big ones that land in the global slab
-        std::vector<int> order(nops);
-        for(int i = 0; i < nops; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int a, int b) { return pb.ops[a].ncut < pb.ops[b].ncut; });
-        int off = 0;
-        for(int q = 0; q < nops; ++q) {
-            pr.mat_off[order[q]] = off;
-            off += 1 << (2 * pb.ops[order[q]].ncut);
-        }
-        pr.arena_doubles = off;
-    }
-
-    // ---- forward schedule: ops per level, quads (4 cells per thread) per op ----
-    pr.lops.clear(); pr.lpf.clear(); pr.flevel_quads.clear();
-    pr.flevel_start.assign(1, 0);
+    // ---- forward schedule: ops per level, every op's rows padded to a multiple of four items ----
+    pr.imap.clear(); pr.flevel_items.clear(); pr.flevel_map.clear();
+    std::vector<uint32_t> qstart(nops, 0);
     for(int l = 0; l < n_flevels; ++l) {
-        // big ops first inside a level so that the threads of a warp mostly share an op
+        // big ops first inside a level, ops of the same shape next to each other so that the threads of a
+        // warp that hold different ops still follow the same control flow
         std::vector<int> ops_here;
         for(int i = 0; i < nops; ++i) if(flevel[i] == l) ops_here.push_back(i);
-        // ... and ops of the same shape next to each other so that the threads of a warp that
-        // do hold different ops still follow the same control flow
         auto shape = [&](int i) {
             const slk_peel_op& o = pb.ops[i];
             return std::make_tuple(-nrows[i], o.type, o.nprev, o.nchild, o.ncut);
         };
         std::stable_sort(ops_here.begin(), ops_here.end(), [&](int a, int b) { return shape(a) < shape(b); });
-        uint32_t quads = 0;
+        uint32_t items = 0;
+        pr.flevel_map.push_back((uint32_t) pr.imap.size());
         for(size_t q = 0; q < ops_here.size(); ++q) {
-            pr.lops.push_back((uint16_t) ops_here[q]);
-            pr.lpf.push_back(quads);
-            quads += (uint32_t) nrows[ops_here[q]];
+            const int i = ops_here[q];
+            qstart[i] = items;
+            const uint32_t groups = (uint32_t)((nrows[i] + 3) / 4);
+            for(uint32_t g = 0; g < groups; ++g) pr.imap.push_back((uint16_t) i);
+            items += 4 * groups;
         }
-        pr.flevel_quads.push_back(quads);
-        pr.flevel_start.push_back((uint16_t) pr.lops.size());
+        pr.flevel_items.push_back(items);
     }
+    if(pr.imap.empty()) pr.imap.push_back(0);
 
     pr.bops.clear();
     pr.blevel_start.assign(1, 0);
@@ -240,132 +260,220 @@ static void emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         pr.blevel_start.push_back((uint16_t) pr.bops.size());
     }
 
-    // ---- stream ----
-    pr.stream.clear();
+    // ---- stream size (needed for the shared-memory budget) ----
+    int stream_words = 0;
     pr.op_start.assign(nops, 0);
     for(int i = 0; i < nops; ++i) {
         const slk_peel_op& op = pb.ops[i];
-        pr.op_start[i] = (uint16_t) pr.stream.size();
-        int nkids = 0;
-        if(op.type == SLK_CHILD_PEEL) nkids = 1;
-        else if(op.type == SLK_PARENT_PEEL) nkids = op.nchild;
+        int nkids = (op.type == SLK_CHILD_PEEL) ? 1 : (op.type == SLK_PARENT_PEEL ? op.nchild : 0);
+        if(stream_words / 4 > 65535) { err = "peel program too large for 16-bit record offsets"; return false; }
+        pr.op_start[i] = (uint16_t)(stream_words / 4);
+        stream_words += round_up(SLK_REC_HEADER + SLK_REC_PREV * op.nprev + nkids, 4);
+    }
+    // CTA-shared copy of the program blob: stream, op_start, imap, level tables, genotype-list LUT, (trait)
+    // disease probabilities, each at a 16-byte aligned offset
+    SlkProgram& lay = pr.layout;
+    memset(&lay, 0, sizeof(lay));
+    {
+        int o = 0;
+        lay.off_stream = o;        o += round_up(stream_words * 4, 16);
+        lay.off_op_start = o;      o += round_up(nops * 2, 16);
+        lay.off_imap = o;          o += round_up((int) pr.imap.size() * 2, 16);
+        lay.off_flevel_items = o;  o += round_up(n_flevels * 4, 16);
+        lay.off_flevel_map = o;    o += round_up(n_flevels * 4, 16);
+        lay.off_bops = o;          o += round_up(nops * 2, 16);
+        lay.off_blevel_start = o;  o += round_up((n_blevels + 1) * 2, 16);
+        lay.off_glist = o;         o += 16;
+        lay.off_dprob = -1;
+        if(trait) { lay.off_dprob = o; o += N * 32; }
+        lay.blob_bytes = o;
+    }
+    pr.prog_smem_bytes = lay.blob_bytes;
+
+    // ---- arena ----
+    pr.mat_off.assign(nops, 0);
+    pr.mat_pad.assign(nops, 0);
+    const int budget = kSmemPerBlockMax - pr.prog_smem_bytes;           // one CTA per SM worst case
+    int per_team_budget = budget / teams_per_cta - table_bytes;
+    if(per_team_budget < 0) per_team_budget = 0;
+    int limit_doubles = per_team_budget / 8;
+    limit_doubles = std::min(limit_doubles, std::max(0, env_int(trait ? "SLK_LOD_SMEM_DOUBLES" : "SLK_LS_SMEM_DOUBLES", limit_doubles)));
+
+    if(trait) {
+        // matrices die after the level of their single consumer; every matrix uses the padded layout
+        std::vector<int> level_order;
+        for(int lv = 0; lv < n_flevels; ++lv) for(int i = 0; i < nops; ++i) if(flevel[i] == lv) level_order.push_back(i);
+        Liveness lv;
+        std::vector<std::vector<int> > dies_after(n_flevels);
+        for(int i = 0; i < nops; ++i) if(consumer[i] >= 0) dies_after[flevel[consumer[i]]].push_back(i);
+        size_t k = 0;
+        for(int l = 0; l < n_flevels; ++l) {
+            for(; k < level_order.size() && flevel[level_order[k]] == l; ++k) {
+                int i = level_order[k];
+                pr.mat_off[i] = lv.alloc(padded_size(pb.ops[i].ncut));
+                pr.mat_pad[i] = 1;
+            }
+            for(size_t q = 0; q < dies_after[l].size(); ++q) {
+                int i = dies_after[l][q];
+                lv.release(pr.mat_off[i], padded_size(pb.ops[i].ncut));
+            }
+        }
+        int hw = 0;
+        for(int i = 0; i < nops; ++i) hw = std::max(hw, pr.mat_off[i] + padded_size(pb.ops[i].ncut));
+        pr.arena_doubles = hw;
+        int smem_doubles = std::min(pr.arena_doubles, limit_doubles);
+        if(smem_doubles < pr.arena_doubles) {
+            // only whole matrices live in shared memory: cut at a matrix boundary no span straddles
+            int cut = 0;
+            std::vector<std::pair<int,int> > spans;
+            for(int i = 0; i < nops; ++i) spans.push_back(std::make_pair(pr.mat_off[i], padded_size(pb.ops[i].ncut)));
+            std::sort(spans.begin(), spans.end());
+            for(size_t q = 0; q < spans.size(); ++q)
+                if(spans[q].first + spans[q].second <= smem_doubles) cut = std::max(cut, spans[q].first + spans[q].second);
+            bool ok = false;
+            while(!ok) {
+                ok = true;
+                for(size_t q = 0; q < spans.size(); ++q)
+                    if(spans[q].first < cut && spans[q].first + spans[q].second > cut) { cut = spans[q].first; ok = false; }
+            }
+            smem_doubles = cut;
+        }
+        pr.smem_doubles = smem_doubles;
+    }
+    else {
+        // everything stays live until the backward pass; small matrices first: they form the shared-memory
+        // prefix (padded layout), the large ones go to the global slab (plain layout, 128-byte aligned)
+        std::vector<int> order(nops);
+        for(int i = 0; i < nops; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pb.ops[a].ncut < pb.ops[b].ncut; });
+        const int maxcut_smem = env_int("SLK_LS_SMEM_MAXCUT", hybrid ? 4 : SLK_MAX_CUTSET);
+        int off = 0;
+        size_t q = 0;
+        for(; q < order.size(); ++q) {
+            const int i = order[q];
+            const int sz = padded_size(pb.ops[i].ncut);
+            if(off + sz > limit_doubles || pb.ops[i].ncut > maxcut_smem) break;
+            pr.mat_off[i] = off; pr.mat_pad[i] = 1;
+            off += sz;
+        }
+        pr.smem_doubles = off;
+        off = round_up(off, 16);
+        if(q == order.size()) off = pr.smem_doubles;
+        const int gbase = off;
+        for(; q < order.size(); ++q) {
+            const int i = order[q];
+            pr.mat_off[i] = off; pr.mat_pad[i] = 0;
+            off += round_up(1 << (2 * pb.ops[i].ncut), 16);
+        }
+        // the global part starts at arena offset smem_doubles in the kernels' address arithmetic
+        if(gbase != pr.smem_doubles) for(size_t r = 0; r < order.size(); ++r) {
+            const int i = order[r];
+            if(!pr.mat_pad[i]) pr.mat_off[i] -= gbase - pr.smem_doubles;
+        }
+        pr.arena_doubles = off - (gbase - pr.smem_doubles);
+    }
+    pr.team_smem_bytes = slk_team_layout(N, pb.n_founders, nops, pr.smem_doubles, tpc_doubles).total;
+
+    // ---- stream ----
+    pr.stream.assign((size_t) stream_words, 0u);
+    for(int i = 0; i < nops; ++i) {
+        const slk_peel_op& op = pb.ops[i];
+        uint32_t* rec = &pr.stream[(size_t) pr.op_start[i] * 4];
+        const int c = op.ncut;
+        int nkids = (op.type == SLK_CHILD_PEEL) ? 1 : (op.type == SLK_PARENT_PEEL ? op.nchild : 0);
 
         bool peel_in_prev = false;
         for(int j = 0; j < op.nprev; ++j) {
             const slk_peel_op& pv = pb.ops[op.prev[j]];
             for(int d = 0; d < pv.ncut; ++d) if(pv.cutset[d] == op.peelnode) peel_in_prev = true;
         }
-
-        pr.stream.push_back((uint32_t) op.type | ((uint32_t) op.ncut << 4) | ((uint32_t) op.nprev << 8) |
-                            ((uint32_t) nkids << 12) | ((uint32_t) op.peelnode << 16));
-        pr.stream.push_back((uint32_t) pr.mat_off[i]);
-        pr.stream.push_back((uint32_t) hp.dense_off[i]);
-        pr.stream.push_back(peel_in_prev ? 1u : 0u);
-        pr.stream.push_back((uint32_t)(static_lmw[i] & 0xffffffffu));
-        pr.stream.push_back((uint32_t)(static_lmw[i] >> 32));
-        pr.stream.push_back(trait ? (uint32_t) dmask[op.peelnode] : 15u);
-        for(int d = 0; d < op.ncut; d += 2) {
-            uint32_t w = (uint32_t) op.cutset[d];
-            if(d + 1 < op.ncut) w |= (uint32_t) op.cutset[d + 1] << 16;
-            pr.stream.push_back(w);
-        }
-        for(int j = 0; j < op.nprev; ++j) {
-            const slk_peel_op& pv = pb.ops[op.prev[j]];
-            uint32_t peel_shift = SLK_NO_SHIFT, d0_shift = SLK_NO_SHIFT;
-            // (dst digit in the consumed matrix) <- (src digit of the consumer's cutset);
-            // digit 0 of the consumer is the register tile's slot axis and is kept out of the runs
+        rec[0] = (uint32_t) op.type | ((uint32_t) c << 4) | ((uint32_t) op.nprev << 8) | ((uint32_t) nkids << 12) |
+                 ((uint32_t) op.peelnode << 16);
+        rec[1] = (uint32_t) pr.mat_off[i] | (pr.mat_pad[i] ? SLK_MAT_PAD : 0u);
+        rec[2] = qstart[i];
+        rec[3] = peel_in_prev ? 1u : 0u;
+        rec[4] = (uint32_t) hp.dense_off[i];
+        uint64_t refpos = 0;
+        for(int d = 0; d < c; ++d) refpos |= (uint64_t) find_pos(op, scut[i][d]) << (4 * d);
+        rec[5] = (uint32_t)(refpos & 0xffffffffu);
+        rec[6] = (uint32_t)(refpos >> 32);
+        rec[7] = trait ? (uint32_t) dmask[op.peelnode] : 15u;
+        for(int d = 0; d < c; ++d) rec[8 + (d >> 1)] |= (uint32_t) scut[i][d] << (16 * (d & 1));
+        rec[13] = (uint32_t)(static_lmw[i] & 0xffffffffu);
+        rec[14] = (uint32_t)(static_lmw[i] >> 32);
+        uint32_t* pw = rec + SLK_REC_HEADER;
+        for(int j = 0; j < op.nprev; ++j, pw += SLK_REC_PREV) {
+            const int x = op.prev[j];
+            const std::vector<int>& xs = scut[x];
+            // sorted layout: the consumer's peel node, if the consumed function is keyed on it, is its digit 0
+            // and the consumer's digit 0 comes next; every other digit is one of the consumer's row digits
+            size_t first = 0;
+            uint32_t kind;
+            const bool has_v = !xs.empty() && xs[0] == op.peelnode;
+            if(has_v) first = 1;
+            const bool has_s = c > 0 && xs.size() > first && xs[first] == scut[i][0];
+            if(has_s) first += 1;
+            kind = has_v ? (has_s ? SLK_KEY_VS : SLK_KEY_V) : (has_s ? SLK_KEY_S : SLK_KEY_R);
+            // (digit of the consumed matrix's row index) <- (row digit of the consumer's cell), merged into runs
             std::vector<std::pair<int,int> > maps;
-            for(int d = 0; d < pv.ncut; ++d) {
-                int pos = find_pos(op, pv.cutset[d]);
-                if(pos == SLK_POS_PEEL) peel_shift = 2 * d;
-                else if(pos == 0) d0_shift = 2 * d;
-                else maps.push_back(std::make_pair(d, pos));
+            for(size_t r = first; r < xs.size(); ++r) {
+                const int pos = spos(i, xs[r]);
+                if(pos < 1 || pos == SLK_POS_PEEL) {
+                    std::ostringstream e; e << "op " << i << ": previous function " << x << " breaks the sorted-digit layout";
+                    err = e.str(); return false;
+                }
+                maps.push_back(std::make_pair((int)(r - first), pos));
             }
             std::vector<uint32_t> runs;
             for(size_t q = 0; q < maps.size(); ) {
                 size_t e = q + 1;
                 while(e < maps.size() && maps[e].first == maps[e-1].first + 1 && maps[e].second == maps[e-1].second + 1) ++e;
-                uint32_t nbits = 2 * (uint32_t)(e - q);
+                const uint32_t nbits = 2 * (uint32_t)(e - q);
                 runs.push_back((uint32_t)(2 * maps[q].second) | ((uint32_t)(2 * maps[q].first) << 5) | (nbits << 10));
                 q = e;
             }
-            pr.stream.push_back((uint32_t) pr.mat_off[op.prev[j]]);
-            pr.stream.push_back(peel_shift | ((uint32_t) runs.size() << 8) | (d0_shift << 16));
-            for(size_t q = 0; q < runs.size(); q += 2) {
-                uint32_t w = runs[q];
-                if(q + 1 < runs.size()) w |= runs[q + 1] << 16;
-                pr.stream.push_back(w);
-            }
+            if(runs.size() > 5) { err = "gather of a previous function needs more than five runs"; return false; }
+            while(runs.size() < 5) runs.push_back(0u);
+            size_t nruns = 0;
+            for(size_t q = 0; q < 5; ++q) if(runs[q]) nruns = q + 1;
+            pw[0] = (uint32_t) pr.mat_off[x] | (pr.mat_pad[x] ? SLK_MAT_PAD : 0u);
+            pw[1] = kind | ((uint32_t) nruns << 8) | (runs[4] << 16);
+            pw[2] = runs[0] | (runs[1] << 16);
+            pw[3] = runs[2] | (runs[3] << 16);
         }
         for(int k = 0; k < nkids; ++k) {
             int kid = (op.type == SLK_CHILD_PEEL) ? op.peelnode : op.children[k];
-            int kid_pos = find_pos(op, kid);
-            int mat_pos = find_pos(op, pb.mother[kid]);
-            int pat_pos = find_pos(op, pb.father[kid]);
+            int kid_pos = spos(i, kid);
+            int mat_pos = spos(i, pb.mother[kid]);
+            int pat_pos = spos(i, pb.father[kid]);
             uint32_t male = (pb.sex[kid] == SLK_MALE) ? 1u : 0u;
-            pr.stream.push_back((uint32_t) kid | ((uint32_t) kid_pos << 16) | ((uint32_t) mat_pos << 20) |
-                                ((uint32_t) pat_pos << 24) | (male << 28));
+            pw[k] = (uint32_t) kid | ((uint32_t) kid_pos << 16) | ((uint32_t) mat_pos << 20) |
+                    ((uint32_t) pat_pos << 24) | (male << 28);
         }
     }
-
-    // ---- geometry ----
-    const int N = pb.n_members;
-    pr.prog_smem_bytes = round_up((int)(pr.stream.size() * 4 + pr.lpf.size() * 4 + pr.flevel_quads.size() * 4 +
-                                        pr.op_start.size() * 2 + pr.lops.size() * 2 +
-                                        pr.flevel_start.size() * 2 + pr.bops.size() * 2 +
-                                        pr.blevel_start.size() * 2 + 64), 16);
-    const int tpc_doubles = trait ? 4 : 16;
-    pr.table_doubles_per_child = tpc_doubles;
-    const int table_bytes = slk_team_layout(N, pb.n_founders, nops, 0, tpc_doubles).total;
-    const long work = trait ? pr.valid_cells : hp.sum_cells;
-    int team = 32;
-    if(work > 1024)  team = 64;
-    if(work > 4096)  team = 128;
-    if(work > 8192)  team = 256;
-    // One unit is latency bound (a chain of ~50 dependent levels), so the SM needs several units in
-    // flight.  When the whole arena of a team would crowd the others out of shared memory, only the
-    // small matrices (cutset <= 4, the ones hit by the many small latency-bound ops) stay in shared
-    // memory and the few large ones go to the L2-resident global slab (measured on B200 with the
-    // 200-member pedigree: 8.4 ms per sweep against 11.5 ms with everything in shared memory).
-    int small_doubles = 0;
-    for(int i = 0; i < nops; ++i) if(pb.ops[i].ncut <= 4) small_doubles = std::max(small_doubles, pr.mat_off[i] + (1 << (2 * pb.ops[i].ncut)));
-    const bool hybrid = (size_t) pr.arena_doubles * 8 + table_bytes > 100 * 1024;
-    team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
-    if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
-    pr.team_threads = team;
-    pr.cta_threads = std::max(team, env_int(trait ? "SLK_LOD_CTA_THREADS" : "SLK_LS_CTA_THREADS", env_int("SLK_CTA_THREADS", hybrid ? 768 : 128)));
-
-    const int teams_per_cta = pr.cta_threads / team;
-    const int budget = kSmemPerBlockMax - pr.prog_smem_bytes;           // one CTA per SM worst case
-    int per_team_budget = budget / teams_per_cta - table_bytes;
-    if(per_team_budget < 0) per_team_budget = 0;
-    int smem_doubles = std::min(pr.arena_doubles, per_team_budget / 8);
-    if(hybrid && !trait) smem_doubles = std::min(smem_doubles, small_doubles);
-    smem_doubles = env_int(trait ? "SLK_LOD_SMEM_DOUBLES" : "SLK_LS_SMEM_DOUBLES", smem_doubles);
-    smem_doubles = std::min(smem_doubles, std::min(pr.arena_doubles, per_team_budget / 8));
-    if(smem_doubles < pr.arena_doubles) {
-        // only whole matrices live in shared memory: cut at a matrix boundary
-        int cut = 0;
-        std::vector<std::pair<int,int> > spans;
-        for(int i = 0; i < nops; ++i) spans.push_back(std::make_pair(pr.mat_off[i], 1 << (2 * pb.ops[i].ncut)));
-        std::sort(spans.begin(), spans.end());
-        for(size_t q = 0; q < spans.size(); ++q) {
-            // (the trait arena reuses space, so spans may overlap; a boundary is any span start
-            //  not inside an earlier span that crosses the cut)
-            if(spans[q].first + spans[q].second <= smem_doubles) cut = std::max(cut, spans[q].first + spans[q].second);
-        }
-        // make sure no span straddles the cut
-        bool ok = false;
-        while(!ok) {
-            ok = true;
-            for(size_t q = 0; q < spans.size(); ++q) {
-                if(spans[q].first < cut && spans[q].first + spans[q].second > cut) { cut = spans[q].first; ok = false; }
-            }
-        }
-        smem_doubles = cut;
-    }
-    pr.smem_doubles = smem_doubles;
-    pr.team_smem_bytes = slk_team_layout(N, pb.n_founders, nops, smem_doubles, tpc_doubles).total;
+    // ---- the device image ----
+    pr.blob.assign((size_t) lay.blob_bytes, 0);
+    memcpy(&pr.blob[lay.off_stream], pr.stream.data(), pr.stream.size() * 4);
+    memcpy(&pr.blob[lay.off_op_start], pr.op_start.data(), pr.op_start.size() * 2);
+    memcpy(&pr.blob[lay.off_imap], pr.imap.data(), pr.imap.size() * 2);
+    memcpy(&pr.blob[lay.off_flevel_items], pr.flevel_items.data(), pr.flevel_items.size() * 4);
+    memcpy(&pr.blob[lay.off_flevel_map], pr.flevel_map.data(), pr.flevel_map.size() * 4);
+    memcpy(&pr.blob[lay.off_bops], pr.bops.data(), pr.bops.size() * 2);
+    memcpy(&pr.blob[lay.off_blevel_start], pr.blevel_start.data(), pr.blevel_start.size() * 2);
+    memcpy(&pr.blob[lay.off_glist], kSlkGlist, 16);
+    if(trait) memcpy(&pr.blob[lay.off_dprob], pb.disease_prob, (size_t) N * 32);
+    lay.stream_words = stream_words;
+    lay.imap_len = (int) pr.imap.size();
+    lay.n_flevels = n_flevels;
+    lay.n_blevels = n_blevels;
+    lay.arena_doubles = pr.arena_doubles;
+    lay.smem_doubles = pr.smem_doubles;
+    lay.team_threads = pr.team_threads;
+    lay.cta_threads = pr.cta_threads;
+    lay.prog_smem_bytes = pr.prog_smem_bytes;
+    lay.team_smem_bytes = pr.team_smem_bytes;
+    lay.table_doubles_per_child = pr.table_doubles_per_child;
+    return true;
 }
 
 bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
@@ -565,11 +673,8 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
 
     hp.ls = HostProgram(); hp.lod = HostProgram();
     hp.ls.arena_doubles = hp.lod.arena_doubles = 0;
-    emit_program(pb, hp, false, hp.ls);
-    emit_program(pb, hp, true, hp.lod);
-    if(hp.ls.stream.size() > 65535 || hp.lod.stream.size() > 65535) {
-        err = "peel program too large for 16-bit offsets"; return false;
-    }
+    if(!emit_program(pb, hp, false, hp.ls, err)) return false;
+    if(!emit_program(pb, hp, true, hp.lod, err)) return false;
     return true;
 }
 

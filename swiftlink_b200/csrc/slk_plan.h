@@ -13,14 +13,17 @@ namespace slk {
 
 struct HostProgram {
     std::vector<uint32_t> stream;
-    std::vector<uint16_t> op_start;
-    std::vector<uint16_t> lops;
-    std::vector<uint32_t> lpf;
-    std::vector<uint32_t> flevel_quads;
-    std::vector<uint16_t> flevel_start;
+    std::vector<uint16_t> op_start;  // record offset / 4
+    std::vector<uint16_t> imap;      // op of every group of four forward items
+    std::vector<uint32_t> flevel_items;
+    std::vector<uint32_t> flevel_map;
     std::vector<uint16_t> bops;
     std::vector<uint16_t> blevel_start;
-    std::vector<int> mat_off;        // arena offset per op
+    std::vector<int> mat_off;        // arena offset per op (doubles)
+    std::vector<uint8_t> mat_pad;    // 1: padded layout (two doubles after every 16)
+    std::vector<int> flevel;         // forward level of each op
+    std::vector<uint8_t> blob;       // the device image of the program (slk_types.h)
+    SlkProgram layout;               // offsets into the blob + geometry (blob pointer unset)
     int arena_doubles;
     int smem_doubles;
     int team_threads;
