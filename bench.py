@@ -72,70 +72,105 @@ def workload_files(n_markers, tag):
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------
 
-def reference_measure(steps, warmup, quiet=True):
-    """Times the reference's own CPU path.  Returns (iterations/s extrapolated to M = 10k, info)."""
+def reference_open(n_markers):
+    """the compiled reference on the bench pedigree (first n_markers SNPs), the committed elimination order, one
+    sequential-imputation run as start state (the reference's own); returns (Ref, threads, host cores, set-up seconds)"""
     from oracle import refapi
     if not refapi.available():
-        return None, dict(error="oracle/_ref/libswiftref.so not built")
+        return None, 0, 0, 0.0
+    t0 = time.time()
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
     refapi.set_threads(threads)
     refapi.seed(20261017)
-    paths = workload_files(REF_SAMPLE_MARKERS, "ref")
+    paths = workload_files(n_markers, "ref")
     r = refapi.Ref(*paths, lodscores=N_LOD)
     names = r.person_names()
     index = dict((n, i) for i, n in enumerate(names))
     order = [index[str(n)] for n in load_order()["order"]]
     assert r.set_peel(order), "reference rejected the committed elimination order"
-    r.sequential_imputation(1)            # the reference's own start state: one sequential-imputation run
-    scale = float(N_MARKERS) / REF_SAMPLE_MARKERS
-    times = []
+    r.sequential_imputation(1)
+    return r, threads, cores, time.time() - t0
+
+
+def reference_chain_steps(r, n_markers, steps, warmup, target_step_s):
+    """Times `warmup + steps` steps of MarkovChain::run's loop (markov_chain.cc:335-390: mix draw, L- or M-sweep,
+    scoring after every SCORING_PERIOD iterations) over the reference's own samplers and peelers.  A step is a BOUNDED
+    sample of the bench step (SCORING_PERIOD iterations + 1 scoring pass): `it` iterations and a scoring pass over
+    it / SCORING_PERIOD of the intervals, i.e. the same work per iteration, with `it` sized from the first step's pace.
+    Returns (iterations/s over the timed steps, info)."""
+    # pace: one iteration of each kind, one scheduler trial of every kind (optimal_num_lgroups, markov_chain.cc:269-311)
+    t, lgroups, counts = r.bench_chain(2, 2, LSAMPLER_PROB, max(1, (n_markers - 1) * 2 // SCORING_PERIOD), 1)
+    it_step = int(min(SCORING_PERIOD, max(2, round(target_step_s / max(t / 2.0, 1e-6)))))
+    lod_int = max(1, int(round((n_markers - 1) * it_step / float(SCORING_PERIOD))))
+    times, kinds = [], [0, 0, 0]
     for s in range(warmup + steps):
-        t_old = r.bench_lsweeps(1, -1)
-        t_grp = r.bench_lsweeps(1, 4) if threads > 1 else t_old
-        t_sweep = min(t_old, t_grp)       # the reference picks the faster scheduler itself (markov_chain.cc:269-311)
-        t_lod = r.bench_lodpasses(1)
-        t_ms = r.bench_msweeps(1)
+        t, _, counts = r.bench_chain(it_step, it_step, LSAMPLER_PROB, lod_int, 0 if lgroups < 0 else -lgroups)
         if s >= warmup:
-            times.append((t_sweep, t_lod, t_ms))
-    t_sweep = float(np.mean([t[0] for t in times])) * scale
-    t_lod = float(np.mean([t[1] for t in times])) * float(N_MARKERS - 1) / (REF_SAMPLE_MARKERS - 1)
-    t_msweep = float(np.mean([t[2] for t in times])) * scale
-    t_iter = LSAMPLER_PROB * t_sweep + (1.0 - LSAMPLER_PROB) * t_msweep + t_lod / SCORING_PERIOD
-    info = dict(cores=threads, host_cores=cores, sweep_s_at_10k=t_sweep, msweep_s_at_10k=t_msweep, lod_pass_s_at_10k=t_lod,
-                locus_updates_per_s=N_MARKERS / t_sweep,
-                trait_positions_per_s=(N_MARKERS - 1) * N_LOD / t_lod,
-                sample="reference LocusSampler sweep, MeiosisSampler sweep and Peeler::process pass over the first %d of "
-                       "%d SNPs of the same pedigree, %d OpenMP threads, x%d linear extrapolation in M, iteration = "
-                       "0.5 L-sweep + 0.5 M-sweep + 1/100 scoring pass" %
-                       (REF_SAMPLE_MARKERS, N_MARKERS, threads, int(scale)))
+            times.append(t)
+            for k in range(3):
+                kinds[k] += counts[k]
+    secs = float(np.sum(times))
+    info = dict(iterations_per_step=it_step, lod_intervals_per_step=lod_int, lgroups=lgroups, seconds=secs,
+                l_sweeps=kinds[0], m_sweeps=kinds[1], scoring_passes=kinds[2], ms_per_step=1e3 * secs / max(steps, 1))
+    return steps * it_step / secs, info
+
+
+def reference_measure(steps, warmup, n_markers=REF_SAMPLE_MARKERS, target_step_s=5.0):
+    """Times the reference's own CPU path on the first n_markers SNPs of the bench pedigree.  Returns
+    (iterations/s at that marker count, info); the caller states the sample."""
+    r, threads, cores, t_setup = reference_open(n_markers)
+    if r is None:
+        return None, dict(error="oracle/_ref/libswiftref.so not built")
+    value, info = reference_chain_steps(r, n_markers, steps, warmup, target_step_s)
+    # the three components alone, for the per-kernel comparisons (trait positions/s, locus updates/s)
+    t_old = r.bench_lsweeps(1, -1)
+    t_grp = r.bench_lsweeps(1, 4) if threads > 1 else t_old
+    t_sweep = min(t_old, t_grp)
+    t_lod = r.bench_lodpasses(1) if n_markers <= 2000 else None       # a full pass at 10k SNPs takes tens of seconds
+    t_ms = r.bench_msweeps(1)
+    info.update(cores=threads, host_cores=cores, n_markers=n_markers, setup_s=t_setup, l_sweep_s=t_sweep, m_sweep_s=t_ms,
+                lod_pass_s=t_lod, locus_updates_per_s=n_markers / t_sweep,
+                trait_positions_per_s=((n_markers - 1) * N_LOD / t_lod) if t_lod else None)
     r.close()
-    return 1.0 / t_iter, info
+    return value, info
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     t0 = time.time()
-    value, info = reference_measure(args.steps, args.warmup)
+    value, info = reference_measure(args.steps, args.warmup, N_MARKERS, target_step_s=args.ref_step_seconds)
     if value is None:
         print(json.dumps({"impl": "reference", "unavailable": info["error"]}))
         return
-    t_iter = 1.0 / value
+    sample = ("UNMODIFIED reference (oracle/_ref/libswiftref.so) on the full workload (%d members x %d SNPs), %d OpenMP threads: "
+              "the loop of MarkovChain::run over its own LocusSampler / MeiosisSampler / Peeler objects; one step = %d "
+              "iterations (L-sweep w.p. 0.5 with the scheduler its own timing picks, else M-sweep) + a scoring pass over "
+              "%d of the %d intervals, i.e. the bench step's work per iteration (scoring every %dth) on a bounded sample; "
+              "timed steps held %d L-sweeps, %d M-sweeps, %d scoring passes; set-up %.0f s not timed" %
+              (N_MEMBERS, N_MARKERS, info["cores"], info["iterations_per_step"], info["lod_intervals_per_step"],
+               N_MARKERS - 1, SCORING_PERIOD, info["l_sweeps"], info["m_sweeps"], info["scoring_passes"], info["setup_s"]))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_iter * SCORING_PERIOD, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": STEP_DESC,
-                   "n_members": N_MEMBERS, "n_markers": N_MARKERS, "n_lod": N_LOD},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "reference", "sample": info["sample"]},
+        "config": bench_config(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "detail": {k: info[k] for k in ("sweep_s_at_10k", "msweep_s_at_10k", "lod_pass_s_at_10k", "locus_updates_per_s",
-                                        "trait_positions_per_s", "host_cores")},
+        "detail": {k: info[k] for k in ("iterations_per_step", "lod_intervals_per_step", "lgroups", "l_sweeps", "m_sweeps",
+                                        "scoring_passes", "l_sweep_s", "m_sweep_s", "locus_updates_per_s", "host_cores",
+                                        "setup_s")},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(line))
+
+
+def bench_config():
+    """the `config` object both arms print"""
+    return {"workload": WORKLOAD, "step": STEP_DESC, "lsampler_prob": LSAMPLER_PROB,
+            "n_members": N_MEMBERS, "n_markers": N_MARKERS, "n_lod": N_LOD}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -504,14 +539,23 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = reference_measure(1, 0)
+            v, info = reference_measure(2, 1, REF_SAMPLE_MARKERS, target_step_s=4.0)
             if v is not None:
-                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "reference",
-                                        "sample": info["sample"],
-                                        "trait_positions_per_s": info["trait_positions_per_s"],
-                                        "locus_updates_per_s": info["locus_updates_per_s"],
-                                        "l_sweep_s": info["sweep_s_at_10k"], "m_sweep_s": info["msweep_s_at_10k"],
-                                        "lod_pass_s": info["lod_pass_s_at_10k"]}
+                scale = float(REF_SAMPLE_MARKERS) / N_MARKERS
+                line["cpu_baseline"] = {
+                    "value": v * scale, "unit": UNIT, "cores": info["cores"], "kind": "reference",
+                    "sample": "UNMODIFIED reference (oracle/_ref/libswiftref.so), %d OpenMP threads, the loop of MarkovChain::run "
+                              "(mix draw, L- or M-sweep, scoring every %dth iteration) on the first %d of the %d SNPs of the same "
+                              "pedigree: 2 timed steps of %d iterations + scoring of %d intervals; per-locus cost does not depend "
+                              "on M (checked at 1k / 2k / 10k SNPs), value = measured / %d; `bench.py --impl reference` runs the "
+                              "full 10k-SNP workload" % (info["cores"], SCORING_PERIOD, REF_SAMPLE_MARKERS, N_MARKERS,
+                                                         info["iterations_per_step"], info["lod_intervals_per_step"],
+                                                         int(round(1.0 / scale))),
+                    "measured_at_sample": v,
+                    "trait_positions_per_s": info["trait_positions_per_s"],
+                    "locus_updates_per_s": info["locus_updates_per_s"],
+                    "l_sweep_s_at_sample": info["l_sweep_s"], "m_sweep_s_at_sample": info["m_sweep_s"],
+                    "lod_pass_s_at_sample": info["lod_pass_s"]}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": info["error"]}
         except Exception as e:                                       # the baseline must not take the bench line down
@@ -533,6 +577,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-step-seconds", type=float, default=5.0,
+                    help="--impl reference: size of the bounded sample one step times (seconds of CPU work, approximately)")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="also time this many replicate chains in flight on one GPU (derived.replicates_in_flight; 1 = skip)")
     args = ap.parse_args()

@@ -40,6 +40,7 @@
 #include <omp.h>
 #include <istream>
 #include <math.h>
+#include <float.h>
 #include <stdio.h>
 #include <unistd.h>
 #include <fcntl.h>
@@ -681,4 +682,80 @@ double ref_bench_lodpasses(void* h, int reps) {
     return t1 - t0;
 }
 
+/* The loop of MarkovChain::run (markov_chain.cc:335-390) over the reference's own LocusSampler / MeiosisSampler /
+   Peeler objects, for `iterations` iterations: each an L-sweep with probability lsampler_prob (scheduler chosen as
+   optimal_num_lgroups would, from `sched_trials` timed sweeps of each kind instead of its 100: lgroups_out reports
+   it; sched_trials = -g forces g stride groups, 0 the old sampler), else an M-sweep over the shuffled m_ordering; after every `scoring_period` iterations one scoring pass over
+   the first `lod_intervals` intervals (all M-1 if <= 0; a bounded sample keeps a bench step short, the cost per
+   interval does not depend on how many are scored).  Returns the seconds of the loop alone (set-up and scheduler
+   trials excluded, as the driver's own clock excludes the reference's start-up); counts[0..2] = L-sweeps, M-sweeps,
+   scoring passes. */
+double ref_bench_chain(void* h, int iterations, int scoring_period, double lsampler_prob, int lod_intervals,
+                       int sched_trials, int* lgroups_out, int* counts) {
+    RefCtx* c = (RefCtx*) h;
+    Quiet q(quiet_mode());
+    struct mcmc_options o = c->opt;
+    o.burnin = 0; o.iterations = iterations; o.scoring_period = scoring_period; o.lsampler_prob = lsampler_prob;
+    o.sex_linked = c->dm.is_sexlinked();
+    MarkovChain chain(c->ped, &c->map, c->psg, o, 0);
+    DescentGraph& dg = *c->dg;
+    int num_lgroups = -1;
+    if(sched_trials < 0) num_lgroups = -sched_trials;          /* the caller's earlier choice */
+    else if(get_max_threads() > 1 && sched_trials > 0) {
+        /* markov_chain.cc:269-311 with fewer trials */
+        double best = DBL_MAX;
+        for(int g = 2; g <= 10; ++g) {
+            if(g == 2) {
+                double t0 = omp_get_wtime();
+                for(int k = 0; k < sched_trials; ++k) chain.run_old_lsampler(dg);
+                best = omp_get_wtime() - t0;
+                continue;
+            }
+            std::vector<int> groups;
+            for(int i = 0; i < g; ++i) groups.push_back(i);
+            double t0 = omp_get_wtime();
+            for(int k = 0; k < sched_trials; ++k) chain.run_scalable_lsampler(dg, groups, g);
+            double t = omp_get_wtime() - t0;
+            if(t < best) { best = t; num_lgroups = g; }
+        }
+    }
+    if(lgroups_out) *lgroups_out = num_lgroups;
+    std::vector<int> lgroups;
+    for(int i = 0; i < num_lgroups; ++i) lgroups.push_back(i);
+    const int n_int = (lod_intervals > 0 && lod_intervals < int(c->map.num_markers() - 1)) ? lod_intervals : int(c->map.num_markers() - 1);
+    int nl = 0, nm = 0, ns = 0;
+    double t0 = omp_get_wtime();
+    for(int i = 0; i < iterations; ++i) {
+        if(get_random() < lsampler_prob) {
+            if(num_lgroups == -1) chain.run_old_lsampler(dg);
+            else chain.run_scalable_lsampler(dg, lgroups, num_lgroups);
+            ++nl;
+        }
+        else {
+            random_shuffle(chain.m_ordering.begin(), chain.m_ordering.end());
+            chain.msampler.reset(dg, chain.m_ordering[0]);
+            for(unsigned int j = 0; j < chain.m_ordering.size(); ++j) chain.msampler.step(dg, chain.m_ordering[j]);
+            ++nm;
+        }
+        if(((i + 1) % scoring_period) == 0) {
+            int thread_num = 0;
+            #pragma omp parallel private(thread_num)
+            {
+                thread_num = get_thread_num();
+                #pragma omp for
+                for(int j = 0; j < n_int; ++j) {
+                    chain.peelers[thread_num]->set_locus(j);
+                    chain.peelers[thread_num]->process(&dg);
+                }
+            }
+            ++ns;
+        }
+    }
+    double t1 = omp_get_wtime();
+    if(counts) { counts[0] = nl; counts[1] = nm; counts[2] = ns; }
+    delete chain.lod;
+    return t1 - t0;
+}
+
 } // extern "C"
+

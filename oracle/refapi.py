@@ -32,7 +32,7 @@ def lib():
         L.ref_peel_cost.restype = C.c_uint
         for name in ("ref_dg_likelihood", "ref_dg_recombination_prob", "ref_dg_marker_transmission",
                      "ref_chain_run", "ref_ls_forward", "ref_calc_trait_prob", "ref_bench_lsweeps",
-                     "ref_bench_lodpasses", "ref_fag", "ref_fag_flipped", "ref_bench_msweeps", "ref_elod"):
+                     "ref_bench_lodpasses", "ref_fag", "ref_fag_flipped", "ref_bench_msweeps", "ref_elod", "ref_bench_chain"):
             getattr(L, name).restype = C.c_double
         _lib = L
     return _lib
@@ -282,3 +282,11 @@ class Ref(object):
 
     def bench_lodpasses(self, reps):
         return float(self.L.ref_bench_lodpasses(self.h, int(reps)))
+
+    def bench_chain(self, iterations, scoring_period, lsampler_prob, lod_intervals=0, sched_trials=1):
+        """MarkovChain::run's loop over the reference's own objects; returns (seconds, lgroups, [L-sweeps, M-sweeps, scorings])"""
+        lg = C.c_int(0)
+        counts = np.zeros(3, np.int32)
+        t = float(self.L.ref_bench_chain(self.h, int(iterations), int(scoring_period), C.c_double(lsampler_prob),
+                                         int(lod_intervals), int(sched_trials), C.byref(lg), _p(counts, C.c_int32)))
+        return t, int(lg.value), [int(x) for x in counts]

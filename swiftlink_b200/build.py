@@ -40,6 +40,16 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in src + hdr + [os.path.join(CSRC, "host", "swift_main.cc")])
 
 
+def build_variant(name, defs):
+    """an A/B variant of the library (kernel tuning only): swiftlink_b200/libslk_<name>.so built with extra -D flags"""
+    src, _ = sources()
+    out = os.path.join(HERE, "libslk_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + list(defs) + ["-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                           "-I", os.path.join(CSRC, "host"), "-o", out] + src)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

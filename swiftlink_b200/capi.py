@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswiftlink_b200.so")
+# SLK_LIB: an alternative build of the same library (A/B timing of kernel variants; tools/gpu/*.sh)
+LIB_PATH = os.environ.get("SLK_LIB") or os.path.join(HERE, "libswiftlink_b200.so")
 
 MAX_CUTSET, MAX_PREV, MAX_CHILDREN = 10, 8, 10
 

@@ -15,6 +15,7 @@
 #include "swiftlink_b200.h"
 #include "slk_plan.h"
 #include "slk_kernels.cuh"
+#include "slk_geometry.h"
 #include "slk_msampler.cuh"
 
 namespace {
@@ -87,11 +88,20 @@ struct slk_chain {
 
 namespace {
 
-template<int T> void launch_ls(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    slk_lsampler_kernel<T, false><<<grid, cta, smem, s>>>(L);
-}
-template<int T> void launch_lod(const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    slk_lodscore_kernel<T, false><<<grid, cta, smem, s>>>(L);
+typedef void (*PeelKernel)(const SlkLaunch);
+struct PeelGeom { int team, max_cta; PeelKernel ls, lod; };
+#define SLK_X(T, C) { T, C, slk_lsampler_kernel<T, C, false>, slk_lodscore_kernel<T, C, false> },
+const PeelGeom kGeoms[] = { SLK_GEOMETRIES(SLK_X) };
+#undef SLK_X
+
+// the instantiation for a team size with the smallest CTA bound that holds `cta` threads (most registers per thread)
+const PeelGeom* find_geom(int team, int cta) {
+    const PeelGeom* best = 0;
+    for(size_t i = 0; i < sizeof(kGeoms) / sizeof(kGeoms[0]); ++i) {
+        const PeelGeom& g = kGeoms[i];
+        if(g.team == team && g.max_cta >= cta && (!best || g.max_cta < best->max_cta)) best = &g;
+    }
+    return best;
 }
 
 // parity hooks: one team of 128 threads whatever the plan's production geometry (the team size
@@ -100,62 +110,47 @@ const int kDebugTeam = 128;
 cudaError_t prep_debug(int, int) {
     // the attribute belongs to the function, not to a plan: always allow the maximum so that
     // plans of different sizes can coexist in one process
-    cudaError_t e = cudaFuncSetAttribute(slk_lsampler_kernel<kDebugTeam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    cudaError_t e = cudaFuncSetAttribute(slk_lsampler_kernel<kDebugTeam, 384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
     if(e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(slk_lodscore_kernel<kDebugTeam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+    return cudaFuncSetAttribute(slk_lodscore_kernel<kDebugTeam, 384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
 }
 void launch_ls_debug(const SlkLaunch& L, int smem, cudaStream_t s) {
-    slk_lsampler_kernel<kDebugTeam, true><<<1, kDebugTeam, smem, s>>>(L);
+    slk_lsampler_kernel<kDebugTeam, 384, true><<<1, kDebugTeam, smem, s>>>(L);
 }
 void launch_lod_debug(const SlkLaunch& L, int grid, int smem, cudaStream_t s) {
-    slk_lodscore_kernel<kDebugTeam, true><<<grid, kDebugTeam, smem, s>>>(L);
+    slk_lodscore_kernel<kDebugTeam, 384, true><<<grid, kDebugTeam, smem, s>>>(L);
 }
 
-template<int T> cudaError_t prep_kernels(int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
+cudaError_t prep_by_team(int team, int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
     cudaError_t e;
     if(ls) {
-        e = cudaFuncSetAttribute(slk_lsampler_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+        const PeelGeom* g = find_geom(team, ls_cta);
+        if(!g) return cudaErrorInvalidConfiguration;
+        e = cudaFuncSetAttribute(g->ls, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
         if(e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ls_occ, slk_lsampler_kernel<T, false>, ls_cta, ls_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ls_occ, g->ls, ls_cta, ls_smem);
         if(e != cudaSuccess) return e;
     }
     if(lod) {
-        e = cudaFuncSetAttribute(slk_lodscore_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
+        const PeelGeom* g = find_geom(team, lod_cta);
+        if(!g) return cudaErrorInvalidConfiguration;
+        e = cudaFuncSetAttribute(g->lod, cudaFuncAttributeMaxDynamicSharedMemorySize, slk::kSmemPerBlockMax);
         if(e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(lod_occ, slk_lodscore_kernel<T, false>, lod_cta, lod_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(lod_occ, g->lod, lod_cta, lod_smem);
         if(e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-cudaError_t prep_by_team(int team, int ls_smem, int lod_smem, int ls_cta, int lod_cta, int* ls_occ, int* lod_occ, bool ls, bool lod) {
-    switch(team) {
-        case 32:  return prep_kernels<32>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
-        case 64:  return prep_kernels<64>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
-        case 128: return prep_kernels<128>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
-        case 256: return prep_kernels<256>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
-        default:  return prep_kernels<512>(ls_smem, lod_smem, ls_cta, lod_cta, ls_occ, lod_occ, ls, lod);
-    }
-}
-
+// a single-team launch (sequential imputation, P(T)) uses the same instantiation as the full CTA
 void launch_ls_by_team(int team, const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    switch(team) {
-        case 32:  launch_ls<32>(L, grid, cta, smem, s); break;
-        case 64:  launch_ls<64>(L, grid, cta, smem, s); break;
-        case 128: launch_ls<128>(L, grid, cta, smem, s); break;
-        case 256: launch_ls<256>(L, grid, cta, smem, s); break;
-        default:  launch_ls<512>(L, grid, cta, smem, s); break;
-    }
+    const PeelGeom* g = find_geom(team, std::max(cta, L.plan.ls.cta_threads));
+    g->ls<<<grid, cta, smem, s>>>(L);
 }
 
 void launch_lod_by_team(int team, const SlkLaunch& L, int grid, int cta, int smem, cudaStream_t s) {
-    switch(team) {
-        case 32:  launch_lod<32>(L, grid, cta, smem, s); break;
-        case 64:  launch_lod<64>(L, grid, cta, smem, s); break;
-        case 128: launch_lod<128>(L, grid, cta, smem, s); break;
-        case 256: launch_lod<256>(L, grid, cta, smem, s); break;
-        default:  launch_lod<512>(L, grid, cta, smem, s); break;
-    }
+    const PeelGeom* g = find_geom(team, std::max(cta, L.plan.lod.cta_threads));
+    g->lod<<<grid, cta, smem, s>>>(L);
 }
 
 int grid_for(int nunits, int teams_per_cta, int blocks_per_sm, int sm_count) {
@@ -265,6 +260,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
         dp = hp.layout;
         if(e == cudaSuccess) e = upload(hp.blob, &dp.blob, p->owned);
     }
+    UP(dbg, h.ls.dbg);
     UP(ms.seq, h.ms_seq); UP(ms.typed, h.ms_typed); UP(ms.obsT, h.ms_obsT); UP(ms.minor, h.ms_minor);
     UP(ms.lnmajor, h.ms_lnmajor); UP(ms.lnminor, h.ms_lnminor);
     UP(ms.desc_mask, h.ms_desc_mask); UP(ms.typed_index, h.ms_typed_index);

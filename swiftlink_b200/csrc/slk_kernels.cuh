@@ -29,10 +29,8 @@
 #ifndef SLK_KERNELS_CUH
 #define SLK_KERNELS_CUH
 
-#ifndef SLK_LS_MAXTHREADS
-#define SLK_LS_MAXTHREADS 768
-#endif
-
+// The kernels are compiled for a fixed list of (team threads, CTA threads) geometries (slk_geometry.h); the CTA
+// size fixes the register budget of a thread (65536 / CTA threads, one CTA per SM).
 #include <stdint.h>
 #include <float.h>
 
@@ -130,6 +128,7 @@ __device__ __forceinline__ SlkEnv make_env(const SlkLaunch& L) {
     E.male = L.plan.male;
     E.dump_mat = L.dump_mat;
     E.dump_pre = L.dump_pre;
+    E.dbg = L.plan.dbg;
     return E;
 }
 
@@ -143,11 +142,13 @@ __device__ __forceinline__ void forward_levels(const SlkLaunch& L, const SlkEnv&
                                                const SlkTeam& tm, int team, int tid, bool tracing, int& tstamp) {
     for(int lv = 0; lv < pr.n_flevels; ++lv) {
         const uint32_t items = pg.flevel_items[lv];
-        const uint16_t* map = pg.imap + pg.flevel_map[lv];
-        for(uint32_t q = tid; q < items; q += T) {
-            const uint32_t op = map[q >> 2];
-            const uint32_t qstart = pg.stream[4u * pg.op_start[op] + 2u];
-            slk_forward_tile<TRAIT, DBG>(E, pg, tm, op, q - qstart);
+        const uint32_t mw = pg.flevel_map[lv];
+        const uint16_t* map = pg.imap + (mw & ~SLK_LEVEL_FINE);
+        if(mw & SLK_LEVEL_FINE) {
+            for(uint32_t q = tid; q < items; q += T) slk_forward_item<TRAIT, DBG>(E, pg, tm, map, true, q);
+        }
+        else {
+            for(uint32_t q = tid; q < items; q += T) slk_forward_item<TRAIT, DBG>(E, pg, tm, map, false, q);
         }
         team_sync<T>(team);
         if(tracing) L.trace[tstamp++] = clock64();
@@ -158,8 +159,8 @@ __device__ __forceinline__ void forward_levels(const SlkLaunch& L, const SlkEnv&
 // L-sampler: LocusSampler::set_locus_minimal + step (locus_sampler2.cc:128-181) for every locus
 // of one window class.  Replaces lsampler_kernel (cuda_lsampler.cu:403-449).
 // ============================================================================================
-template<int T, bool DBG>
-__global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(const SlkLaunch L) {
+template<int T, int MAXCTA, bool DBG>
+__global__ void __launch_bounds__(MAXCTA, 1) slk_lsampler_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
     const SlkProgram& pr = P.ls;
@@ -301,8 +302,8 @@ __global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lsampler_kernel(cons
 // LOD scoring: Peeler::process (peeler.cc:79-103) with one team per (interval, position).
 // Replaces lodscore_kernel (cuda_lodscore.cu:389-467).
 // ============================================================================================
-template<int T, bool DBG>
-__global__ void __launch_bounds__(SLK_LS_MAXTHREADS, 1) slk_lodscore_kernel(const SlkLaunch L) {
+template<int T, int MAXCTA, bool DBG>
+__global__ void __launch_bounds__(MAXCTA, 1) slk_lodscore_kernel(const SlkLaunch L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
     const SlkProgram& pr = P.lod;

@@ -35,6 +35,7 @@ struct SlkEnv {
     // parity dumps (DBG instantiations only)
     double* dump_mat;            // dense matrices, reference cell order (pre-zeroed by the host)
     double* dump_pre;            // dense presum matrices
+    const uint32_t* dbg;         // [nops][3] dense offset, refpos
 };
 
 struct SlkProgView {             // CTA-shared (shared memory on the device)
@@ -53,7 +54,7 @@ struct SlkTeam {                 // per team
     double* arena;               // shared part of the arena
     double* garena;              // global part (arena offsets >= smem_doubles)
     int smem_doubles;
-    double* tables;              // (N-F) x 16 transmission tables (sampler) / (N-F) x 4 recombination weights (trait)
+    double* tables;              // (N-F) x 8 transmission tables (sampler) / (N-F) x 4 recombination weights (trait)
     double* scal;                // 48: thetas [0..4), class priors [16..36), founder priors of the locus [36..44)
     SlkOpLoc* oploc;             // [nops]
     double* ru;                  // [nops] genotype draws of the current locus (sampler)
@@ -158,26 +159,42 @@ SLK_DEV unsigned long long slk_full_lmw(int c) {
 }
 
 // row index of a consumed matrix: up to five runs of consecutive digits of the consumer's cell
+SLK_DEV uint32_t slk_run(uint32_t cell, uint32_t run) {
+    return ((cell >> (run & 31u)) & ((1u << ((run >> 10) & 31u)) - 1u)) << ((run >> 5) & 31u);
+}
+
 SLK_DEV uint32_t slk_gather(uint32_t cell, const uint32_t* pw) {
-    const uint32_t nruns = (pw[1] >> 8) & 0xffu;
-    uint32_t R = 0;
-    for(uint32_t r = 0; r < nruns; ++r) {
-        const uint32_t run = (r < 4u) ? ((pw[2 + (r >> 1)] >> (16u * (r & 1u))) & 0xffffu) : (pw[1] >> 16);
-        R |= ((cell >> (run & 31u)) & ((1u << (run >> 10)) - 1u)) << ((run >> 5) & 31u);
+    const uint32_t w1 = pw[1], w2 = pw[2];
+    const uint32_t nruns = (w1 >> 8) & 0xffu;
+    uint32_t R = slk_run(cell, w2);                     // an absent run is all zeros: no bits
+    if(nruns > 1u) {
+        R |= slk_run(cell, w2 >> 16);
+        if(nruns > 2u) {
+            const uint32_t w3 = pw[3];
+            R |= slk_run(cell, w3) | slk_run(cell, w3 >> 16) | slk_run(cell, w1 >> 16);
+        }
     }
     return R;
 }
 
-// sampler_rfunction.cc:350-419: one entry of the 64-entry transmission table, from the
-// per-child tables staged at the start of the locus: tb[2*pg + a] = P(maternal allele a | mother
-// genotype pg), tb[8 + 2*pg + a] the paternal one (sampler_rfunction.cc:102-157).  Under X
-// linkage a heterozygous father transmits nothing (both entries 0) and a son copies the
-// maternal allele (paternal entries of a homozygous father are 1, hetero kid genotypes are 0).
+// Per-child transmission tables (sampler_rfunction.cc:102-157), staged at the start of the locus: for each parent
+// (0 maternal, 1 paternal) the four entries that depend on the neighbouring meioses,
+//     tb[4 p + 0..1] = P(allele 0 / 1 | parent AU),  tb[4 p + 2..3] = P(allele 0 / 1 | parent UA);
+// a homozygous parent transmits its allele with certainty.  Under X linkage a heterozygous father transmits
+// nothing (entry 0) and a son takes nothing from his father (both paternal entries of a homozygous father are 1).
+SLK_DEV double slk_tb_entry(const double* tb, uint32_t parent, uint32_t pg, uint32_t a, bool xpat, bool xson) {
+    const double het = tb[4u * parent + 2u * (pg & 1u) + a];
+    const double hom = (a == pg || xson) ? 1.0 : 0.0;
+    return pg >= 2u ? (xpat ? 0.0 : het) : hom;
+}
+
+// sampler_rfunction.cc:350-419: one entry of the 64-entry transmission table = maternal entry x paternal entry;
+// a son is never heterozygous
 SLK_DEV double slk_trans_prob(bool sex_linked, bool male, uint32_t m, uint32_t f, uint32_t kg, const double* tb) {
     const uint32_t am = ((kg >> 1) ^ kg) & 1u;       // maternal allele of the kid: AA, AU carry A
     const uint32_t ap = kg & 1u;                     // paternal allele: AA, UA carry A
     if(sex_linked && male && kg >= 2u) return 0.0;
-    return tb[2u * m + am] * tb[8u + 2u * f + ap];
+    return slk_tb_entry(tb, 0u, m, am, false, false) * slk_tb_entry(tb, 1u, f, ap, sex_linked, sex_linked && male);
 }
 
 // rfunction.h:81-107
@@ -242,15 +259,17 @@ SLK_DEV void slk_stage_oploc(const SlkProgView& pg, const SlkTeam& tm, int op) {
     const uint32_t* rec = pg.stream + 4u * pg.op_start[op];
     const int c = (rec[0] >> 4) & 15u;
     const int peel = rec[0] >> 16;
+    const uint32_t* cw = rec + SLK_REC_HEADER;
     unsigned long long w = 0;
     uint32_t peel_lm;
     if(TRAIT) {
-        w = (unsigned long long) rec[13] | ((unsigned long long) rec[14] << 32);
-        peel_lm = rec[7] & 15u;
+        const uint32_t* lw = cw + ((c + 1) >> 1);
+        w = (unsigned long long) lw[0] | ((unsigned long long) lw[1] << 32);
+        peel_lm = (rec[3] >> 8) & 15u;
     }
     else {
         for(int d = 0; d < c; ++d) {
-            const uint32_t person = (rec[8 + (d >> 1)] >> (16 * (d & 1))) & 0xffffu;
+            const uint32_t person = (cw[d >> 1] >> (16 * (d & 1))) & 0xffffu;
             w |= (unsigned long long)(tm.gc[person] & 15u) << (4 * d);
         }
         peel_lm = (uint32_t) tm.gc[peel] & 15u;
@@ -266,13 +285,16 @@ SLK_DEV void slk_stage_oploc(const SlkProgView& pg, const SlkTeam& tm, int op) {
 //
 // TRAIT = false: SamplerRfunction::evaluate_element, TRAIT = true: TraitRfunction::evaluate_element
 // DBG adds the dense parity dumps (separate instantiation, keeps the hot kernels lean).
-template<bool TRAIT, bool DBG>
-SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkTeam& tm, uint32_t op, uint32_t row) {
-    const uint32_t* rec = pg.stream + 4u * pg.op_start[op];
+// NS = 4: the thread owns the whole tile (throughput mode, big levels); NS = 1: the thread owns slot s0 only
+// (latency mode: a level with few rows is spread over four times as many threads)
+template<bool TRAIT, bool DBG, int NS>
+SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkTeam& tm, const uint32_t* rec, uint32_t row,
+                              uint32_t s0) {
+    const uint32_t w0 = rec[0], matw = rec[1], w3 = rec[3];
+    const uint32_t op = w3 >> 16;
     const SlkOpLoc ol = tm.oploc[op];
     if(row >= ol.nrows) return;
     const bool sex_linked = E.sex_linked != 0;
-    const uint32_t w0 = rec[0];
     const int type = w0 & 7u, c = (w0 >> 4) & 15u, nprev = (w0 >> 8) & 15u, nkids = (w0 >> 12) & 15u;
     const int peel = w0 >> 16;
     const uint32_t lm0 = ol.misc & 15u, peel_lm = (ol.misc >> 4) & 15u;
@@ -280,30 +302,30 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
     const int ch = c > 0 ? c - 1 : 0;
     // digits 1..c-1 of this row, digit d at bits [2d, 2d+2); digit 0 is the slot axis
     const uint32_t cell = (lmw_hi == slk_full_lmw(ch)) ? (row << 2) : slk_decode_row(row, ol.lmw, c, pg.glist);
-    const uint32_t* pw = rec + SLK_REC_HEADER;
+    const uint32_t* pw = rec + SLK_REC_HEADER + ((c + 1) >> 1) + (TRAIT ? 2 : 0);
     const uint32_t* kw = pw + SLK_REC_PREV * nprev;
     const bool perm = TRAIT && type == SLK_CHILD_PEEL;
 
     double tc[4];
     slk_load_prior<TRAIT>(pg, tm, peel, tc);
-    if(!TRAIT && (rec[3] & 1u)) {
+    if(!TRAIT && (w3 & 1u)) {
         // a previous function keyed on the peel node is 0 wherever that genotype was eliminated (its cell is
         // not in valid_indices): the product is 0
 #pragma unroll
         for(int g = 0; g < 4; ++g) if(!((peel_lm >> g) & 1u)) tc[g] = 0.0;
     }
 
-    // digit value of sorted cutset position `pos` in slot s
-#define SLK_DIG(pos, s) (((pos) == 0u) ? (uint32_t)(s) : ((cell >> (2u * (pos))) & 3u))
+    // digit value of sorted cutset position `pos` in slot s of this thread
+#define SLK_DIG(pos, s) (((pos) == 0u) ? (s0 + (uint32_t)(s)) : ((cell >> (2u * (pos))) & 3u))
 
-    double t[4][4];
-    uint32_t gvp[4];
+    double t[NS][4];
+    uint32_t gvp[NS];
     // ---- initial factor: prior of the peel-node genotype (x transmission for a sampler child peel)
     const uint32_t k0 = (type == SLK_CHILD_PEEL) ? kw[0] : 0u;
     const uint32_t mpos0 = (k0 >> 20) & 15u, fpos0 = (k0 >> 24) & 15u;
     const bool male0 = (k0 >> 28) & 1u;
 #pragma unroll
-    for(int s = 0; s < 4; ++s) {
+    for(int s = 0; s < NS; ++s) {
         gvp[s] = 0xE4u;
         if(perm) {
             // variants are the four (maternal, paternal) transmitted-allele choices (trait_rfunction.cc:44-66)
@@ -318,26 +340,42 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
         else {
 #pragma unroll
             for(int v = 0; v < 4; ++v) t[s][v] = tc[v];
-            if(!TRAIT && type == SLK_CHILD_PEEL) {
-                const uint32_t m = SLK_DIG(mpos0, s), f = SLK_DIG(fpos0, s);
-                const double* tb = tm.tables + 16 * (peel - E.F);
+        }
+    }
+    if(!TRAIT && type == SLK_CHILD_PEEL) {
+        // T[m][f][v] = P(maternal allele of v | m) * P(paternal allele of v | f) (sampler_rfunction.cc:412-415); the
+        // four factors are the same in every slot unless a parent is cutset digit 0
+        const double* tb = tm.tables + 8 * (peel - E.F);
+        const bool xson = sex_linked && male0;
+        const bool dep_s = NS > 1 && (mpos0 == 0u || fpos0 == 0u);
+        double T[4];
 #pragma unroll
-                for(int v = 0; v < 4; ++v) t[s][v] *= slk_trans_prob(sex_linked, male0, m, f, (uint32_t) v, tb);
+        for(int s = 0; s < NS; ++s) {
+            if(s == 0 || dep_s) {
+                const uint32_t m = SLK_DIG(mpos0, s), f = SLK_DIG(fpos0, s);
+                const double m0 = slk_tb_entry(tb, 0u, m, 0u, false, false), m1 = slk_tb_entry(tb, 0u, m, 1u, false, false);
+                const double f0 = slk_tb_entry(tb, 1u, f, 0u, sex_linked, xson), f1 = slk_tb_entry(tb, 1u, f, 1u, sex_linked, xson);
+                T[SLK_UU] = m0 * f0;
+                T[SLK_AA] = m1 * f1;
+                T[SLK_AU] = xson ? 0.0 : m1 * f0;          // a son is never heterozygous
+                T[SLK_UA] = xson ? 0.0 : m0 * f1;
             }
+#pragma unroll
+            for(int v = 0; v < 4; ++v) t[s][v] *= T[v];
         }
     }
 
     // ---- previous functions, in the reference's order
     for(int jp = 0; jp < nprev; ++jp, pw += SLK_REC_PREV) {
-        const uint32_t offw = pw[0];
+        const uint32_t offw0 = pw[0];
         const uint32_t kind = pw[1] & 0xffu;
-        const bool pad = (offw & SLK_MAT_PAD) != 0u;
-        const uint32_t R = slk_gather(cell, pw);
-        const double* X = slk_mat_ptr(tm, offw);
+        const bool pad0 = (offw0 & SLK_MAT_PAD) != 0u;
+        const uint32_t R0 = slk_gather(cell, pw);
+        const double* p = slk_mat_ptr(tm, offw0) + (kind == SLK_KEY_VS ? (pad0 ? 18u * R0 : 16u * R0) + 4u * s0
+                                                    : kind == SLK_KEY_R ? slk_pidx(R0, pad0) : slk_pidx(4u * R0, pad0));
         if(kind == SLK_KEY_VS) {
-            const double* p = X + (pad ? 18u * R : 16u * R);
 #pragma unroll
-            for(int s = 0; s < 4; ++s) {
+            for(int s = 0; s < NS; ++s) {
                 double x[4];
                 slk_ld4(p + 4 * s, x);
 #pragma unroll
@@ -346,24 +384,25 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
         }
         else if(kind == SLK_KEY_V) {
             double x[4];
-            slk_ld4(X + slk_pidx(4u * R, pad), x);
+            slk_ld4(p, x);
 #pragma unroll
-            for(int s = 0; s < 4; ++s)
+            for(int s = 0; s < NS; ++s)
 #pragma unroll
                 for(int v = 0; v < 4; ++v) t[s][v] *= perm ? slk_sel4(x, (gvp[s] >> (2 * v)) & 3u) : x[v];
         }
         else if(kind == SLK_KEY_S) {
             double x[4];
-            slk_ld4(X + slk_pidx(4u * R, pad), x);
+            if(NS == 4) slk_ld4(p, x);
+            else x[0] = p[s0];
 #pragma unroll
-            for(int s = 0; s < 4; ++s)
+            for(int s = 0; s < NS; ++s)
 #pragma unroll
                 for(int v = 0; v < 4; ++v) t[s][v] *= x[s];
         }
         else {
-            const double x = X[slk_pidx(R, pad)];
+            const double x = p[0];
 #pragma unroll
-            for(int s = 0; s < 4; ++s)
+            for(int s = 0; s < NS; ++s)
 #pragma unroll
                 for(int v = 0; v < 4; ++v) t[s][v] *= x;
         }
@@ -374,30 +413,58 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
         double w[4];
         slk_ld4(tm.tables + 4 * (peel - E.F), w);
 #pragma unroll
-        for(int s = 0; s < 4; ++s)
+        for(int s = 0; s < NS; ++s)
 #pragma unroll
             for(int v = 0; v < 4; ++v) t[s][v] *= w[v];
     }
     else if(type == SLK_PARENT_PEEL) {
-        // child_prob = prod_k T_k (sampler_rfunction.cc:258-279 / trait_rfunction.cc:91-129), slot by slot to keep
-        // the live registers at one row of four
+        // child_prob = prod_k T_k (sampler_rfunction.cc:258-279 / trait_rfunction.cc:91-129).  When no child's own or
+        // other parent's digit is cutset digit 0, the four products (one per peel genotype) are the same in every slot
+        // and are evaluated once per tile.
         if(nkids > 0) {
-#pragma unroll
-            for(int s = 0; s < 4; ++s) {
-                double cp[4];
+            bool dep_s = false;
+            if(NS > 1) {
                 for(int k = 0; k < nkids; ++k) {
                     const uint32_t kd = kw[k];
                     const uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u, kp = (kd >> 16) & 15u;
-                    const bool male = (kd >> 28) & 1u;
-                    const double* tb = tm.tables + (TRAIT ? 4 : 16) * ((int)(kd & 0xffffu) - E.F);
-                    const uint32_t kg = SLK_DIG(kp, s);
+                    dep_s = dep_s || kp == 0u || (mp == SLK_POS_PEEL ? fp : mp) == 0u;
+                }
+            }
+            double cp[4];
 #pragma unroll
-                    for(int v = 0; v < 4; ++v) {
-                        const uint32_t m = (mp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(mp, s);
-                        const uint32_t f = (fp == SLK_POS_PEEL) ? (uint32_t) v : SLK_DIG(fp, s);
-                        const double T = TRAIT ? slk_trait_child_sum(sex_linked, male, m, f, kg, tb)
-                                               : slk_trans_prob(sex_linked, male, m, f, kg, tb);
-                        cp[v] = (k == 0) ? T : cp[v] * T;              // child_prob starts at 1.0: 1.0 * T == T
+            for(int s = 0; s < NS; ++s) {
+                if(s == 0 || dep_s) {
+                    for(int k = 0; k < nkids; ++k) {
+                        const uint32_t kd = kw[k];
+                        const uint32_t mp = (kd >> 20) & 15u, fp = (kd >> 24) & 15u, kp = (kd >> 16) & 15u;
+                        const bool male = (kd >> 28) & 1u;
+                        const double* tb = tm.tables + (TRAIT ? 4 : 8) * ((int)(kd & 0xffffu) - E.F);
+                        const bool peel_is_mother = mp == SLK_POS_PEEL;
+                        const uint32_t kg = SLK_DIG(kp, s), og = SLK_DIG(peel_is_mother ? fp : mp, s);   // the other parent is a cutset member
+                        double T[4];
+                        if(TRAIT) {
+#pragma unroll
+                            for(int v = 0; v < 4; ++v)
+                                T[v] = slk_trait_child_sum(sex_linked, male, peel_is_mother ? (uint32_t) v : og,
+                                                           peel_is_mother ? og : (uint32_t) v, kg, tb);
+                        }
+                        else {
+                            const uint32_t am = ((kg >> 1) ^ kg) & 1u, ap = kg & 1u;
+                            const bool xson = sex_linked && male;
+                            if(xson && kg >= 2u) { T[0] = T[1] = T[2] = T[3] = 0.0; }
+                            else if(peel_is_mother) {
+                                const double B = slk_tb_entry(tb, 1u, og, ap, sex_linked, xson);
+#pragma unroll
+                                for(int v = 0; v < 4; ++v) T[v] = slk_tb_entry(tb, 0u, (uint32_t) v, am, false, false) * B;
+                            }
+                            else {
+                                const double B = slk_tb_entry(tb, 0u, og, am, false, false);
+#pragma unroll
+                                for(int v = 0; v < 4; ++v) T[v] = B * slk_tb_entry(tb, 1u, (uint32_t) v, ap, sex_linked, xson);
+                            }
+                        }
+#pragma unroll
+                        for(int v = 0; v < 4; ++v) cp[v] = (k == 0) ? T[v] : cp[v] * T[v];   // child_prob starts at 1.0: 1.0 * T == T
                     }
                 }
 #pragma unroll
@@ -407,22 +474,26 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
     }
 
     // ---- the sum over the peel node; slots whose digit-0 genotype is illegal stay 0 as in the reference
-    double out[4];
+    double out[NS];
 #pragma unroll
-    for(int s = 0; s < 4; ++s) {
+    for(int s = 0; s < NS; ++s) {
         const double total = ((t[s][0] + t[s][1]) + t[s][2]) + t[s][3];
-        out[s] = ((lm0 >> s) & 1u) ? total : 0.0;
+        out[s] = ((lm0 >> (s0 + s)) & 1u) ? total : 0.0;
     }
-    const uint32_t matw = rec[1];
     double* Y = slk_mat_ptr(tm, matw);
-    if(c == 0) Y[0] = out[0];
-    else slk_st4(Y + slk_pidx(cell, (matw & SLK_MAT_PAD) != 0u), out);
+    const bool ypad = (matw & SLK_MAT_PAD) != 0u;
+    if(NS == 4) {
+        if(c == 0) Y[0] = out[0];
+        else slk_st4(Y + slk_pidx(cell, ypad), out);
+    }
+    else if(c > 0 || s0 == 0u) Y[slk_pidx(cell | s0, ypad)] = out[0];
 
     if(DBG) {
-        const int dense_off = (int) rec[4];
-        const unsigned long long refpos = (unsigned long long) rec[5] | ((unsigned long long) rec[6] << 32);
-        for(int s = 0; s < (c == 0 ? 1 : 4); ++s) {
-            if(!((lm0 >> s) & 1u)) continue;
+        const uint32_t* dbg = E.dbg + 3u * op;
+        const int dense_off = (int) dbg[0];
+        const unsigned long long refpos = (unsigned long long) dbg[1] | ((unsigned long long) dbg[2] << 32);
+        for(int s = 0; s < NS; ++s) {
+            if(!((lm0 >> (s0 + s)) & 1u)) continue;
             // the reference's cell index: sorted digit d sits at position refpos[d] of its cutset
             uint32_t ref = 0;
             for(int d = 0; d < c; ++d) ref |= SLK_DIG((uint32_t) d, s) << (2u * (uint32_t)((refpos >> (4 * d)) & 15u));
@@ -436,6 +507,30 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
 #undef SLK_DIG
 }
 
+// one item of a forward level: finds the op by the item map, runs the tile (whole, or one slot in a fine level)
+template<bool TRAIT, bool DBG>
+SLK_DEV void slk_forward_item(const SlkEnv& E, const SlkProgView& pg, const SlkTeam& tm, const uint16_t* map, bool fine, uint32_t q) {
+    const uint32_t ritem = fine ? (q >> 2) : q;
+    const uint32_t* rec = pg.stream + 4u * map[ritem >> 2];
+    const uint32_t row = ritem - rec[2];
+    if(fine) slk_forward_tile<TRAIT, DBG, 1>(E, pg, tm, rec, row, q & 3u);
+    else     slk_forward_tile<TRAIT, DBG, 4>(E, pg, tm, rec, row, 0u);
+}
+
+// the cell of a previous function at the sampled assignment `cell` of the consumer's cutset and genotype g of its peel node
+SLK_DEV const double* slk_backward_cell(const SlkTeam& tm, const uint32_t* pw, uint32_t cell, uint32_t s, uint32_t g) {
+    const uint32_t offw = pw[0];
+    const uint32_t kind = pw[1] & 0xffu;
+    const bool pad = (offw & SLK_MAT_PAD) != 0u;
+    const uint32_t R = slk_gather(cell & ~3u, pw);
+    uint32_t idx;
+    if(kind == SLK_KEY_VS)     idx = g + 4u * s + 16u * R;
+    else if(kind == SLK_KEY_V) idx = g + 4u * R;
+    else if(kind == SLK_KEY_S) idx = s + 4u * R;
+    else                       idx = R;
+    return slk_mat_ptr(tm, offw) + slk_pidx(idx, pad);
+}
+
 // ---- one term of the backward pass: presum(cell, g) of op recomputed (sampler only) --------
 // The presum matrix (rfunction.cc:20-21) is never stored; SamplerRfunction::sample (sampler_rfunction.cc:159-188)
 // reads it at the already sampled cutset assignment only, four values per op.
@@ -445,9 +540,10 @@ SLK_DEV double slk_backward_term(const SlkEnv& E, const SlkProgView& pg, const S
     const uint32_t w0 = rec[0];
     const int type = w0 & 7u, c = (w0 >> 4) & 15u, nprev = (w0 >> 8) & 15u, nkids = (w0 >> 12) & 15u;
     const int peel = w0 >> 16;
+    const uint32_t* cw = rec + SLK_REC_HEADER;
     uint32_t cell = 0;
     for(int d = 0; d < c; ++d) {
-        const uint32_t person = (rec[8 + (d >> 1)] >> (16 * (d & 1))) & 0xffffu;
+        const uint32_t person = (cw[d >> 1] >> (16 * (d & 1))) & 0xffffu;
         cell |= (uint32_t) tm.pmk[person] << (2 * d);
     }
     const uint32_t s = cell & 3u;
@@ -456,27 +552,16 @@ SLK_DEV double slk_backward_term(const SlkEnv& E, const SlkProgView& pg, const S
     slk_load_prior<false>(pg, tm, peel, tc);
     double t = slk_sel4(tc, g);
     if((rec[3] & 1u) && !((peel_lm >> g) & 1u)) t = 0.0;
-    const uint32_t* pw = rec + SLK_REC_HEADER;
+    const uint32_t* pw = cw + ((c + 1) >> 1);
     const uint32_t* kw = pw + SLK_REC_PREV * nprev;
 #define SLK_DIGC(pos) ((cell >> (2u * (pos))) & 3u)
     if(type == SLK_CHILD_PEEL) {
         const uint32_t k0 = kw[0];
         t *= slk_trans_prob(sex_linked, (k0 >> 28) & 1u, SLK_DIGC((k0 >> 20) & 15u), SLK_DIGC((k0 >> 24) & 15u), g,
-                            tm.tables + 16 * (peel - E.F));
+                            tm.tables + 8 * (peel - E.F));
     }
-    for(int jp = 0; jp < nprev; ++jp, pw += SLK_REC_PREV) {
-        const uint32_t offw = pw[0];
-        const uint32_t kind = pw[1] & 0xffu;
-        const bool pad = (offw & SLK_MAT_PAD) != 0u;
-        const uint32_t R = slk_gather(cell & ~3u, pw);
-        uint32_t idx;
-        if(kind == SLK_KEY_VS)     idx = g + 4u * s + 16u * R;
-        else if(kind == SLK_KEY_V) idx = g + 4u * R;
-        else if(kind == SLK_KEY_S) idx = s + 4u * R;
-        else                       idx = R;
-        // a genotype the elimination ruled out has t == 0 and an unwritten (stale but finite) cell: 0 * x == 0
-        t *= slk_mat_ptr(tm, offw)[slk_pidx(idx, pad)];
-    }
+    // a genotype the elimination ruled out has t == 0 and an unwritten (stale but finite) cell: 0 * x == 0
+    for(int jp = 0; jp < nprev; ++jp) t *= *slk_backward_cell(tm, pw + SLK_REC_PREV * jp, cell, s, g);
     if(type == SLK_PARENT_PEEL) {
         double cp = 1.0;
         for(int k = 0; k < nkids; ++k) {
@@ -485,7 +570,7 @@ SLK_DEV double slk_backward_term(const SlkEnv& E, const SlkProgView& pg, const S
             const uint32_t m = (mp == SLK_POS_PEEL) ? g : SLK_DIGC(mp);
             const uint32_t f = (fp == SLK_POS_PEEL) ? g : SLK_DIGC(fp);
             const uint32_t kg = SLK_DIGC((kd >> 16) & 15u);
-            cp *= slk_trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tm.tables + 16 * ((int)(kd & 0xffffu) - E.F));
+            cp *= slk_trans_prob(sex_linked, (kd >> 28) & 1u, m, f, kg, tm.tables + 8 * ((int)(kd & 0xffffu) - E.F));
         }
         t *= cp;
     }
@@ -517,7 +602,6 @@ SLK_DEV uint32_t slk_sample4(double dd[4], double r) {
 // per-child transmission tables (sampler_rfunction.cc:102-157): for parent genotype UU / AA the transmitted allele
 // is certain; for AU / UA it follows the neighbouring meioses.  q = 2 * (person - F) + parent.
 SLK_DEV void slk_stage_transmission(const SlkEnv& E, const SlkTeam& tm, int q, bool has_left, bool has_right) {
-    const bool sex_linked = E.sex_linked != 0;
     const int person = E.F + (q >> 1), parent = q & 1;
     double tmp0 = 0.5, tmp1 = 0.5;
     if(has_left) {
@@ -532,15 +616,9 @@ SLK_DEV void slk_stage_transmission(const SlkEnv& E, const SlkTeam& tm, int q, b
     }
     const double total = tmp0 + tmp1;
     const double u_au = tmp1 / total, u_ua = tmp0 / total;
-    double* tb = tm.tables + 16 * (person - E.F) + 8 * parent;
-    const bool xpat = sex_linked && parent == 1;
-    const bool son = sex_linked && E.male[person];
-    // homozygous parent
-    tb[2 * SLK_UU + 0] = 1.0; tb[2 * SLK_UU + 1] = (xpat && son) ? 1.0 : 0.0;
-    tb[2 * SLK_AA + 0] = (xpat && son) ? 1.0 : 0.0; tb[2 * SLK_AA + 1] = 1.0;
-    // heterozygous parent
-    tb[2 * SLK_AU + 0] = xpat ? 0.0 : u_au; tb[2 * SLK_AU + 1] = xpat ? 0.0 : 1.0 - u_au;
-    tb[2 * SLK_UA + 0] = xpat ? 0.0 : u_ua; tb[2 * SLK_UA + 1] = xpat ? 0.0 : 1.0 - u_ua;
+    double* tb = tm.tables + 8 * (person - E.F) + 4 * parent;
+    tb[0] = u_au; tb[1] = 1.0 - u_au;
+    tb[2] = u_ua; tb[3] = 1.0 - u_ua;
 }
 
 // trait_prob x recombination probability per child and (i, j) (trait_rfunction.cc:9-22); q = 4 * (person - F) + 2 i + j

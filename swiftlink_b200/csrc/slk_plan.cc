@@ -11,6 +11,7 @@
 //   * marker priors    = Person::populate_trait_prob_cache            (person.cc:224-299)
 #include "slk_plan.h"
 #include "slk_peel.h"
+#include "slk_geometry.h"
 
 #include <algorithm>
 #include <cmath>
@@ -193,7 +194,7 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     }
 
     // ---- geometry (needed before the arena: what stays in shared memory depends on it) ----
-    const int tpc_doubles = trait ? 4 : 16;
+    const int tpc_doubles = trait ? 4 : 8;
     pr.table_doubles_per_child = tpc_doubles;
     const int table_bytes = slk_team_layout(N, pb.n_founders, nops, 0, tpc_doubles).total;
     const long work = trait ? pr.valid_cells : hp.sum_cells;
@@ -208,17 +209,33 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     // small matrices (cutset <= 4, the ones hit by the many small latency-bound ops) stay in shared
     // memory and the few large ones go to the L2-resident global slab.
     const bool hybrid = (size_t) padded_total * 8 + table_bytes > 100 * 1024;
+    // Large plans: one warp per team and as many teams as shared memory holds.  A unit is a chain of ~50 dependent
+    // levels most of which hold a few dozen tiles, so what fills the SM is units in flight, not threads per unit; a
+    // one-warp team also needs no block-level barrier.  Measured on B200, 200-member pedigree, ms per L-sweep:
+    // 12 x 32 threads 3.05, 8 x 64 3.22, 6 x 64 3.58, 5 x 128 3.90, 3 x 128 4.38, 3 x 192 4.54, 3 x 256 5.23.
+    if(hybrid) team = 32;
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
-    if(team != 32 && team != 64 && team != 128 && team != 256 && team != 512) team = 128;
+    if(slk_max_cta(team) == 0) team = 128;
     pr.team_threads = team;
-    // the CTA holds a whole number of teams, at most SLK_LS_MAXTHREADS (768) threads and at most 15 teams
-    // (one named barrier each)
-    int cta = env_int(trait ? "SLK_LOD_CTA_THREADS" : "SLK_LS_CTA_THREADS", env_int("SLK_CTA_THREADS", hybrid ? 768 : 128));
-    cta = std::max(team, std::min(cta, 768));
+    // the CTA holds a whole number of teams and at most the thread count the kernels of this team size are
+    // compiled for (slk_geometry.h)
+    const int max_cta = slk_max_cta(team);
+    int cta = env_int(trait ? "SLK_LOD_CTA_THREADS" : "SLK_LS_CTA_THREADS", env_int("SLK_CTA_THREADS", hybrid ? max_cta : 128));
+    cta = std::max(team, std::min(cta, max_cta));
     cta = (cta / team) * team;
-    if(team > 32 && cta / team > 15) cta = 15 * team;
     pr.cta_threads = cta;
     const int teams_per_cta = pr.cta_threads / team;
+
+    // ---- record offsets ----
+    int stream_words = 0;
+    pr.op_start.assign(nops, 0);
+    for(int i = 0; i < nops; ++i) {
+        const slk_peel_op& op = pb.ops[i];
+        int nkids = (op.type == SLK_CHILD_PEEL) ? 1 : (op.type == SLK_PARENT_PEEL ? op.nchild : 0);
+        if(stream_words / 4 > 65535) { err = "peel program too large for 16-bit record offsets"; return false; }
+        pr.op_start[i] = (uint16_t)(stream_words / 4);
+        stream_words += round_up(SLK_REC_HEADER + ((op.ncut + 1) >> 1) + (trait ? 2 : 0) + SLK_REC_PREV * op.nprev + nkids, 4);
+    }
 
     // ---- forward schedule: ops per level, every op's rows padded to a multiple of four items ----
     pr.imap.clear(); pr.flevel_items.clear(); pr.flevel_map.clear();
@@ -234,15 +251,19 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         };
         std::stable_sort(ops_here.begin(), ops_here.end(), [&](int a, int b) { return shape(a) < shape(b); });
         uint32_t items = 0;
-        pr.flevel_map.push_back((uint32_t) pr.imap.size());
+        const uint32_t map0 = (uint32_t) pr.imap.size();
         for(size_t q = 0; q < ops_here.size(); ++q) {
             const int i = ops_here[q];
             qstart[i] = items;
             const uint32_t groups = (uint32_t)((nrows[i] + 3) / 4);
-            for(uint32_t g = 0; g < groups; ++g) pr.imap.push_back((uint16_t) i);
+            for(uint32_t g = 0; g < groups; ++g) pr.imap.push_back(pr.op_start[i]);
             items += 4 * groups;
         }
-        pr.flevel_items.push_back(items);
+        // a level with few rows is latency bound: one (row, slot) per thread spreads it over four times as
+        // many threads (SLK_LEVEL_FINE); items then count slots
+        const bool fine = items * 4u <= 2u * (uint32_t) team;
+        pr.flevel_map.push_back(map0 | (fine ? SLK_LEVEL_FINE : 0u));
+        pr.flevel_items.push_back(fine ? 4u * items : items);
     }
     if(pr.imap.empty()) pr.imap.push_back(0);
 
@@ -260,16 +281,6 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         pr.blevel_start.push_back((uint16_t) pr.bops.size());
     }
 
-    // ---- stream size (needed for the shared-memory budget) ----
-    int stream_words = 0;
-    pr.op_start.assign(nops, 0);
-    for(int i = 0; i < nops; ++i) {
-        const slk_peel_op& op = pb.ops[i];
-        int nkids = (op.type == SLK_CHILD_PEEL) ? 1 : (op.type == SLK_PARENT_PEEL ? op.nchild : 0);
-        if(stream_words / 4 > 65535) { err = "peel program too large for 16-bit record offsets"; return false; }
-        pr.op_start[i] = (uint16_t)(stream_words / 4);
-        stream_words += round_up(SLK_REC_HEADER + SLK_REC_PREV * op.nprev + nkids, 4);
-    }
     // CTA-shared copy of the program blob: stream, op_start, imap, level tables, genotype-list LUT, (trait)
     // disease probabilities, each at a 16-byte aligned offset
     SlkProgram& lay = pr.layout;
@@ -376,6 +387,7 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
 
     // ---- stream ----
     pr.stream.assign((size_t) stream_words, 0u);
+    pr.dbg.assign((size_t) nops * 3, 0u);
     for(int i = 0; i < nops; ++i) {
         const slk_peel_op& op = pb.ops[i];
         uint32_t* rec = &pr.stream[(size_t) pr.op_start[i] * 4];
@@ -391,17 +403,20 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
                  ((uint32_t) op.peelnode << 16);
         rec[1] = (uint32_t) pr.mat_off[i] | (pr.mat_pad[i] ? SLK_MAT_PAD : 0u);
         rec[2] = qstart[i];
-        rec[3] = peel_in_prev ? 1u : 0u;
-        rec[4] = (uint32_t) hp.dense_off[i];
+        rec[3] = (peel_in_prev ? 1u : 0u) | ((trait ? (uint32_t) dmask[op.peelnode] : 15u) << 8) | ((uint32_t) i << 16);
+        uint32_t* cw = rec + SLK_REC_HEADER;
+        for(int d = 0; d < c; ++d) cw[d >> 1] |= (uint32_t) scut[i][d] << (16 * (d & 1));
+        uint32_t* pw = cw + ((c + 1) >> 1);
+        if(trait) {
+            pw[0] = (uint32_t)(static_lmw[i] & 0xffffffffu);
+            pw[1] = (uint32_t)(static_lmw[i] >> 32);
+            pw += 2;
+        }
         uint64_t refpos = 0;
         for(int d = 0; d < c; ++d) refpos |= (uint64_t) find_pos(op, scut[i][d]) << (4 * d);
-        rec[5] = (uint32_t)(refpos & 0xffffffffu);
-        rec[6] = (uint32_t)(refpos >> 32);
-        rec[7] = trait ? (uint32_t) dmask[op.peelnode] : 15u;
-        for(int d = 0; d < c; ++d) rec[8 + (d >> 1)] |= (uint32_t) scut[i][d] << (16 * (d & 1));
-        rec[13] = (uint32_t)(static_lmw[i] & 0xffffffffu);
-        rec[14] = (uint32_t)(static_lmw[i] >> 32);
-        uint32_t* pw = rec + SLK_REC_HEADER;
+        pr.dbg[3 * (size_t) i + 0] = (uint32_t) hp.dense_off[i];
+        pr.dbg[3 * (size_t) i + 1] = (uint32_t)(refpos & 0xffffffffu);
+        pr.dbg[3 * (size_t) i + 2] = (uint32_t)(refpos >> 32);
         for(int j = 0; j < op.nprev; ++j, pw += SLK_REC_PREV) {
             const int x = op.prev[j];
             const std::vector<int>& xs = scut[x];
@@ -463,6 +478,7 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     memcpy(&pr.blob[lay.off_glist], kSlkGlist, 16);
     if(trait) memcpy(&pr.blob[lay.off_dprob], pb.disease_prob, (size_t) N * 32);
     lay.stream_words = stream_words;
+    lay.trait = trait ? 1 : 0;
     lay.imap_len = (int) pr.imap.size();
     lay.n_flevels = n_flevels;
     lay.n_blevels = n_blevels;

@@ -14,7 +14,8 @@ namespace slk {
 struct HostProgram {
     std::vector<uint32_t> stream;
     std::vector<uint16_t> op_start;  // record offset / 4
-    std::vector<uint16_t> imap;      // op of every group of four forward items
+    std::vector<uint16_t> imap;      // record offset / 4 of the op of every group of four forward rows
+    std::vector<uint32_t> dbg;       // [nops][3] dense offset, refpos (parity dumps)
     std::vector<uint32_t> flevel_items;
     std::vector<uint32_t> flevel_map;
     std::vector<uint16_t> bops;

@@ -43,13 +43,10 @@
 //  0  type[0:3) | c[4:8) | nprev[8:12) | nkids[12:16) | peelnode[16:32)
 //  1  arena offset of this op's matrix (doubles) | SLK_MAT_PAD if the matrix uses the padded layout
 //  2  first item of this op inside its forward level
-//  3  flags: bit0 = some previous function is keyed on the peel node
-//  4  dense offset (sum of 4^c of earlier ops, peel order)                     -- parity dumps only
-//  5,6  refpos: 4 bits per sorted digit = its position in the reference's cutset order -- parity dumps only
-//  7  static legal mask of the peel node (trait program: disease_prob != 0)
-//  8..12  sorted cutset, two 16-bit person ids per word
-//  13,14  static legal masks, 4 bits per sorted digit (trait program)
-//  15  reserved
+//  3  bit0 = some previous function is keyed on the peel node | static legal mask of the peel node [8:12)
+//     (trait program: disease_prob != 0) | op id [16:32)
+//  then ceil(c/2) words: the sorted cutset, two 16-bit person ids per word
+//  then (trait program only) 2 words: static legal masks, 4 bits per sorted digit
 //  then per previous function, in the reference's order (4 words):
 //        +0  arena offset of the consumed matrix | SLK_MAT_PAD
 //        +1  kind[0:8) (SLK_KEY_*) | nruns[8:16) | run 4 [16:32)
@@ -58,8 +55,12 @@
 //  then per child (CHILD_PEEL: the peel node itself; PARENT_PEEL: cutset members that are its
 //  offspring, in the reference's children order), one word:
 //        person[0:16) | kid_pos[16:20) | mat_pos[20:24) | pat_pos[24:28) | male[28]   (positions: sorted digits)
-#define SLK_REC_HEADER 16
+// The parity dumps need two more facts per op, kept out of the hot record in SlkDevPlan::dbg: the dense offset
+// (sum of 4^c of earlier ops, peel order) and `refpos`, 4 bits per sorted digit = its position in the reference's
+// cutset order.
+#define SLK_REC_HEADER 4
 #define SLK_REC_PREV   4
+#define SLK_LEVEL_FINE 0x80000000u // forward level with few rows: one slot per thread instead of a whole 4 x 4 tile
 #define SLK_MAT_PAD    0x80000000u
 #define SLK_OFF_MASK   0x7fffffffu
 
@@ -88,9 +89,10 @@ struct SlkProgram {
     int blob_bytes;                 // multiple of 16
     int off_stream;                 // uint32[stream_words]
     int off_op_start;               // uint16[nops] record offset / 4
-    int off_imap;                   // uint16[imap_len] op of every group of four forward items, level after level
+    int off_imap;                   // uint16[imap_len] record offset / 4 of the op of every group of four forward items, level after level
     int off_flevel_items;           // uint32[n_flevels] items of each level
-    int off_flevel_map;             // uint32[n_flevels] first imap entry of each level
+    int off_flevel_map;             // uint32[n_flevels] first imap entry of each level | SLK_LEVEL_FINE
+    int trait;                      // 1: trait program (records carry the static legal masks)
     int off_bops;                   // uint16[nops] ops in backward-level order
     int off_blevel_start;           // uint16[n_blevels + 1] into bops
     int off_glist;                  // uint8[16] genotype lists of the 16 legal masks
@@ -105,7 +107,7 @@ struct SlkProgram {
     int cta_threads;
     int prog_smem_bytes;            // == blob_bytes: CTA-shared copy of the program
     int team_smem_bytes;            // per team: arena prefix + tables
-    int table_doubles_per_child;    // 16 (sampler) or 4 (trait)
+    int table_doubles_per_child;    // 8 (sampler) or 4 (trait)
 };
 
 // M-sampler tables (slk_msampler.cuh)
@@ -136,6 +138,7 @@ struct SlkDevPlan {
     const double* partial;          // [M-1]
     const double* log_theta;        // [M-1] ln theta
     const double* log_1mtheta;      // [M-1] ln (1 - theta)
+    const uint32_t* dbg;            // [nops][3] dense offset, refpos (parity dumps only)
     double marker_transmission;     // descent_graph.cc:22,35
     SlkProgram ls;                  // sampler program
     SlkProgram lod;                 // trait program
@@ -146,7 +149,7 @@ struct SlkDevPlan {
 // launches and by the kernels to carve the slab.
 struct SlkTeamLayout {
     int arena;      // smem_doubles doubles
-    int tables;     // (N-F)*k doubles: sampler transmission tables (k = 16) / trait recombination weights (k = 4)
+    int tables;     // (N-F)*k doubles: sampler transmission tables (k = 8) / trait recombination weights (k = 4)
     int scal;       // 48 doubles: thetas [0..4), class priors [16..36), founder priors of the locus [36..44)
     int oploc;      // nops x SlkOpLoc (16 bytes)
     int ru;         // nops doubles: the genotype draws of the current locus (sampler)

@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libslk_emu.so")
 
 def build(force=False):
     src = [os.path.join(HERE, "slk_emu.cc"), os.path.join(CSRC, "slk_plan.cc")]
-    dep = src + [os.path.join(CSRC, f) for f in ("slk_peel.h", "slk_types.h", "slk_plan.h", "slk_philox.cuh")]
+    dep = src + [os.path.join(CSRC, f) for f in ("slk_peel.h", "slk_types.h", "slk_plan.h", "slk_philox.cuh", "slk_geometry.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(f) <= os.path.getmtime(LIB) for f in dep):
         return LIB
     # -ffp-contract=off: no fused multiply-add, as the kernels are compiled with -fmad=false

@@ -72,6 +72,7 @@ SlkEnv env_of(const slk::HostPlan& hp, double* dump_mat, double* dump_pre) {
     E.N = hp.N; E.F = hp.F; E.nops = hp.nops; E.sex_linked = hp.sex_linked;
     E.male = hp.male.data();
     E.dump_mat = dump_mat; E.dump_pre = dump_pre;
+    E.dbg = hp.ls.dbg.data();
     return E;
 }
 
@@ -84,12 +85,9 @@ template<bool TRAIT>
 void forward(const slk::HostProgram& pr, const SlkEnv& E, const SlkProgView& pg, const SlkTeam& tm) {
     for(int lv = 0; lv < pr.layout.n_flevels; ++lv) {
         const uint32_t items = pg.flevel_items[lv];
-        const uint16_t* map = pg.imap + pg.flevel_map[lv];
-        for(uint32_t q = 0; q < items; ++q) {
-            const uint32_t op = map[q >> 2];
-            const uint32_t qstart = pg.stream[4u * pg.op_start[op] + 2u];
-            slk_forward_tile<TRAIT, true>(E, pg, tm, op, q - qstart);
-        }
+        const uint32_t mw = pg.flevel_map[lv];
+        const uint16_t* map = pg.imap + (mw & ~SLK_LEVEL_FINE);
+        for(uint32_t q = 0; q < items; ++q) slk_forward_item<TRAIT, true>(E, pg, tm, map, (mw & SLK_LEVEL_FINE) != 0u, q);
     }
 }
 
