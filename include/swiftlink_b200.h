@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SLK_ABI_VERSION 3
+#define SLK_ABI_VERSION 4
 
 typedef enum {
     SLK_OK = 0,
@@ -102,6 +102,12 @@ typedef struct {
     int32_t disease_prior_locus_plus1;         /* 0 = none.  l + 1: at marker l every person's genotype prior is their
                                                   disease_prob (Person::copy_disease_probs, person.h:204-208) -- the
                                                   simulated trait locus of the ELOD calculation (elod.h:83) */
+    const double* person_prior;                /* [N][4] or NULL (ABI 4).  The genotype prior used at marker
+                                                  disease_prior_locus_plus1 - 1: what Person::copy_disease_probs copied, i.e. the
+                                                  disease probabilities AT THE TIME OF THE COPY.  The ELOD set-up copies before
+                                                  `-a` turns unaffected people into unknowns (elod.h:83-87), so the simulation uses
+                                                  the real phenotypes while the trait peel scores them as unknown.  NULL: the
+                                                  current disease_prob (identical unless affection changed after the copy). */
 } slk_problem;
 
 typedef struct slk_plan slk_plan;              /* device-resident flattened peel plan (shared, read-only) */

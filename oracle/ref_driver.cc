@@ -75,6 +75,9 @@
 #include "elod.h"
 #include "random.h"
 #include "omp_facade.h"
+#ifdef REF_WITH_GPU
+#include "gpu_lodscores.h"
+#endif
 #undef private
 #undef protected
 #undef class
@@ -580,8 +583,16 @@ double ref_bench_msweeps(void* h, int reps) {
 
 /* Elod(pedfile, options).run() (elod.h:33-107, elod.cc:19-85) with the reference's own generator
    (seeded from /dev/urandom by the constructor, then re-seeded here for reproducibility) */
+double ref_elod2(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
+                 int sex_linked, int affected_only, unsigned int seed);
 double ref_elod(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
                 int sex_linked, unsigned int seed) {
+    return ref_elod2(pedfile, frequency, penetrance, separation, replicates, sex_linked, 0, seed);
+}
+
+/* the same with --elod -a (options.affected_only, elod.h:85-87) */
+double ref_elod2(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,
+                 int sex_linked, int affected_only, unsigned int seed) {
     Quiet q(quiet_mode());
     struct mcmc_options o;
     o.elod = true;
@@ -590,6 +601,7 @@ double ref_elod(const char* pedfile, double frequency, const double* penetrance,
     o.elod_marker_separation = separation;
     o.elod_replicates = replicates;
     o.sex_linked = sex_linked != 0;
+    o.affected_only = affected_only != 0;
     o.peelopt_iterations = 20000;
     Elod e(pedfile, o);
     rng_ready = true;
@@ -757,5 +769,41 @@ double ref_bench_chain(void* h, int iterations, int scoring_period, double lsamp
     return t1 - t0;
 }
 
-} // extern "C"
+#ifdef REF_WITH_GPU
+/* The reference's own GPU path for LOD scoring (-g): GPULodscores::calculate / get_results (gpu_lodscores.cc:598-637)
+   driving lodscore_kernel (cuda_lodscore.cu:389-467), compiled for sm_100a by `make refgpu`.  Runs `reps` scoring
+   passes on the context's descent graph; returns the seconds per pass of calculate() + the final block_until_finished()
+   (the reference's synchronous pageable copy of the graph included, as in its own loop), writes the normalised LOD
+   table (lod_score.h:86-88) of those passes to lodout[(M-1)*n].  setup_s receives the constructor time (device mirror
+   of every (op, locus) R-function + its block-size autotune, gpu_lodscores.cc:396-596).
+   NOTE: ~GPULodscores calls cudaDeviceReset(): run this in a process of its own. */
+double ref_gpu_lod_bench(void* h, int reps, double* lodout, double* setup_s, int* threads_chosen) {
+    RefCtx* c = (RefCtx*) h;
+    need_samplers(c);
+    struct mcmc_options o = c->opt;
+    o.sex_linked = c->dm.is_sexlinked();
+    o.use_gpu = true;
+    const double tp = c->peeler->calc_trait_prob();
+    double t0 = omp_get_wtime();
+    GPULodscores* g = new GPULodscores(c->ped, &c->map, c->psg, o, tp);
+    g->block_until_finished();
+    if(setup_s) *setup_s = omp_get_wtime() - t0;
+    if(threads_chosen) *threads_chosen = g->num_lodscore_threads;
+    g->calculate(*c->dg);                     /* warm-up pass */
+    g->block_until_finished();
+    t0 = omp_get_wtime();
+    for(int k = 0; k < reps; ++k) g->calculate(*c->dg);
+    g->block_until_finished();
+    const double secs = (omp_get_wtime() - t0) / (reps > 0 ? reps : 1);
+    LODscores lod(&c->map);
+    g->get_results(&lod);
+    unsigned n = c->map.get_lodscore_count();
+    if(lodout)
+        for(unsigned l = 0; l + 1 < c->map.num_markers(); ++l)
+            for(unsigned k = 0; k < n; ++k) lodout[l * n + k] = lod.get(l, k);
+    /* the destructor resets the device; leak the object instead and let the process exit clean it up */
+    return secs;
+}
+#endif
 
+} // extern "C"

@@ -32,7 +32,7 @@ def lib():
         L.ref_peel_cost.restype = C.c_uint
         for name in ("ref_dg_likelihood", "ref_dg_recombination_prob", "ref_dg_marker_transmission",
                      "ref_chain_run", "ref_ls_forward", "ref_calc_trait_prob", "ref_bench_lsweeps",
-                     "ref_bench_lodpasses", "ref_fag", "ref_fag_flipped", "ref_bench_msweeps", "ref_elod", "ref_bench_chain"):
+                     "ref_bench_lodpasses", "ref_fag", "ref_fag_flipped", "ref_bench_msweeps", "ref_elod", "ref_elod2", "ref_bench_chain"):
             getattr(L, name).restype = C.c_double
         _lib = L
     return _lib
@@ -58,11 +58,12 @@ def seed(s):
     lib().ref_seed(C.c_uint(s))
 
 
-def elod(pedfile, frequency=1e-4, penetrance=(0.0, 0.0, 1.0), separation=0.05, replicates=10000, sex_linked=False, seed=1):
+def elod(pedfile, frequency=1e-4, penetrance=(0.0, 0.0, 1.0), separation=0.05, replicates=10000, sex_linked=False, seed=1,
+         affected_only=False):
     """the reference's Elod(pedfile, options).run()"""
     pen = np.ascontiguousarray(penetrance, np.float64)
-    return float(lib().ref_elod(pedfile.encode(), C.c_double(frequency), _dp(pen), C.c_double(separation), int(replicates),
-                                int(sex_linked), C.c_uint(seed)))
+    return float(lib().ref_elod2(pedfile.encode(), C.c_double(frequency), _dp(pen), C.c_double(separation), int(replicates),
+                                 int(sex_linked), int(affected_only), C.c_uint(seed)))
 
 
 def example(name):

@@ -52,7 +52,8 @@ class Problem(C.Structure):
                 ("theta", C.POINTER(C.c_double)), ("partial_theta", C.POINTER(C.c_double)),
                 ("elimination", C.POINTER(C.c_uint8)),
                 ("n_ops", C.c_int32), ("ops", C.POINTER(PeelOp)),
-                ("minor_freq", C.POINTER(C.c_double)), ("disease_prior_locus_plus1", C.c_int32)]
+                ("minor_freq", C.POINTER(C.c_double)), ("disease_prior_locus_plus1", C.c_int32),
+                ("person_prior", C.POINTER(C.c_double))]
 
 
 class SlkError(RuntimeError):
@@ -122,6 +123,7 @@ def make_problem(d):
                 getattr(arr[i], name)[j] = v
     keep["ops"] = arr
     keep["minor"] = None if d.get("minor") is None else np.ascontiguousarray(d["minor"], np.float64)
+    keep["person_prior"] = None if d.get("person_prior") is None else np.ascontiguousarray(d["person_prior"], np.float64)
     p = Problem(N, int(d["F"]), M, int(d["nlod"]), int(d["sex_linked"]),
                 _ptr(keep["mother"], C.c_int32), _ptr(keep["father"], C.c_int32),
                 _ptr(keep["sex"], C.c_int32), _ptr(keep["typed"], C.c_int32),
@@ -131,7 +133,8 @@ def make_problem(d):
                 _ptr(keep["theta"], C.c_double), _ptr(keep["partial"], C.c_double),
                 _ptr(keep["elim"], C.c_uint8), len(ops), arr,
                 _ptr(keep["minor"], C.c_double) if keep["minor"] is not None else None,
-                int(d.get("disease_prior_locus", -1)) + 1)
+                int(d.get("disease_prior_locus", -1)) + 1,
+                _ptr(keep["person_prior"], C.c_double) if keep["person_prior"] is not None else None)
     return p, keep
 
 

@@ -4,6 +4,7 @@
 // (gpu_lodscores.h:95-99) nothing here calls cudaDeviceReset(): several instances can coexist
 // in one process, one per GPU.
 #include "swiftlink_host.h"
+#include "slk_philox.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -79,7 +80,7 @@ double GPUMarkovChain::calc_trait_prob() {
 double GPUMarkovChain::sequential_imputation(DescentGraph& dg, int iterations) {
     const int M = (int) map->num_markers();
     if(iterations == 0) {
-        die_on(slk_lsampler_locus_by_locus(chain, 0), "sequential imputation (locus by locus)");
+        die_on(slk_lsampler_locus_by_locus(chain, SLK_SI_FIRST_RUN), "sequential imputation (locus by locus)");
         die_on(slk_dg_download(chain, dg.get_internal_ptr()), "sequential imputation (download)");
         return 0.0;
     }
@@ -90,7 +91,9 @@ double GPUMarkovChain::sequential_imputation(DescentGraph& dg, int iterations) {
     for(int run = 0; run < iterations; ++run) starts[run] = (int32_t) rng.uniform_int(M);
     std::vector<double> weights((size_t) iterations);
     int32_t best_run = -1;
-    die_on(slk_sequential_imputation_batch(chain, 0, iterations, starts.data(), weights.data(), &best_run), "sequential imputation");
+    // run numbers live in their own part of the Philox counter space (slk_philox.cuh): the MCMC iterations that
+    // follow never replay the draws that built the start graph, whatever the burn-in
+    die_on(slk_sequential_imputation_batch(chain, SLK_SI_FIRST_RUN, iterations, starts.data(), weights.data(), &best_run), "sequential imputation");
     const double best = best_run >= 0 ? weights[best_run] : -1e300;
     die_on(slk_dg_download(chain, dg.get_internal_ptr()), "sequential imputation (download)");
     printf("starting likelihood (log10) = %.3f\n", best / log(10.0));

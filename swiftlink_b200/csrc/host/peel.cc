@@ -591,6 +591,15 @@ void flatten_problem(Pedigree& ped, GeneticMap& map, PeelSequenceGenerator& psg,
     d.mother = out.mother.data(); d.father = out.father.data(); d.sex = out.sex.data(); d.typed = out.typed.data();
     d.prior_as_founder = real_founder_priors ? out.prior_as_founder.data() : 0;     // NULL: reference behaviour, see include/swiftlink_b200.h
     d.disease_prior_locus_plus1 = disease_prior_locus + 1;
+    if(disease_prior_locus >= 0) {
+        // what Person::copy_disease_probs stored at that marker -- NOT get_disease_prob(): make_unknown_affection may
+        // have re-run init_probs since the copy (elod.h:83-87)
+        out.person_prior.resize((size_t) N * 4);
+        for(int i = 0; i < N; ++i)
+            for(int g = 0; g < 4; ++g)
+                out.person_prior[(size_t) i * 4 + g] = ped.get_by_index(i)->get_trait_probability(disease_prior_locus, (enum phased_trait) g);
+        d.person_prior = out.person_prior.data();
+    }
     d.genotypes = out.genotypes.data(); d.disease_prob = out.disease_prob.data();
     d.marker_prob = out.marker_prob.data(); d.marker_xprob = out.marker_xprob.data();
     d.theta = out.theta.data(); d.partial_theta = out.partial_theta.data();

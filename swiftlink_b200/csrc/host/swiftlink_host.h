@@ -365,7 +365,7 @@ bool write_linkage_results(GeneticMap* map, const std::string& filename, std::ve
 struct FlatProblem {
     std::vector<int32_t> mother, father, sex, typed, prior_as_founder;
     std::vector<uint8_t> genotypes, elimination;
-    std::vector<double> disease_prob, marker_prob, marker_xprob, theta, partial_theta, minor_freq;
+    std::vector<double> disease_prob, marker_prob, marker_xprob, theta, partial_theta, minor_freq, person_prior;
     std::vector<slk_peel_op> ops;
     slk_problem desc;
 };

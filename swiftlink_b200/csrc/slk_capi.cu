@@ -251,7 +251,7 @@ int slk_plan_create(const slk_problem* problem, int device, slk_plan** out) {
     d.marker_transmission = h.marker_transmission;
     cudaError_t e = cudaSuccess;
 #define UP(field, vec) if(e == cudaSuccess) e = upload(vec, &d.field, p->owned)
-    UP(mother, h.mother); UP(father, h.father); UP(male, h.male); UP(disease_prob, h.disease_prob);
+    UP(mother, h.mother); UP(father, h.father); UP(male, h.male); UP(disease_prob, h.disease_prob); UP(person_prior, h.person_prior);
     UP(gcode, h.gcode); UP(fprior, h.fprior); UP(theta, h.theta); UP(partial, h.partial);
     UP(log_theta, h.log_theta); UP(log_1mtheta, h.log_1mtheta);
     for(int k = 0; k < 2; ++k) {

@@ -83,12 +83,29 @@ __device__ __forceinline__ void team_sync(int team) {
     else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(T) : "memory");
 }
 
-// copies the program blob into shared memory (whole CTA), returns the shared views
+// Brings the program blob into shared memory with ONE 1-D bulk copy (TMA: cp.async.bulk global -> shared, completion
+// counted in bytes on an mbarrier) issued by one thread; every thread then waits on the barrier's phase.  Returns
+// the shared views.  (blob and shared base are 16-byte aligned, blob_bytes is a multiple of 16.)
 __device__ __forceinline__ SlkProgView stage_program(const SlkProgram& p, const double* dprob_global, unsigned char* smem) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.blob);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for(int i = threadIdx.x; i < p.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
+    // the barrier lives in the dynamic allocation, right behind the blob (static shared memory would count
+    // against the 227 KB the dynamic part is allowed to ask for)
+    const uint32_t bar = (uint32_t) __cvta_generic_to_shared(smem + p.blob_bytes);
+    const uint32_t dst = (uint32_t) __cvta_generic_to_shared(smem);
+    if(threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t) p.blob_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(p.blob), "r"((uint32_t) p.blob_bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();                                       // the barrier is initialised before anybody polls it
+    {
+        uint32_t done = 0;
+        while(!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+    }
     SlkProgView g;
     g.stream = (const uint32_t*)(smem + p.off_stream);
     g.op_start = (const uint16_t*)(smem + p.off_op_start);
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(MAXCTA, 1) slk_lsampler_kernel(const SlkLaunch
     extern __shared__ __align__(16) unsigned char smem[];
     const SlkDevPlan& P = L.plan;
     const SlkProgram& pr = P.ls;
-    const SlkProgView pg = stage_program(pr, P.disease_prob, smem);
+    const SlkProgView pg = stage_program(pr, P.person_prior, smem);      // dprob: the SLK_PRIOR_PERSON class's prior
     const SlkEnv E = make_env(L);
 
     const int teams_per_cta = blockDim.x / T;
@@ -205,10 +222,23 @@ __global__ void __launch_bounds__(MAXCTA, 1) slk_lsampler_kernel(const SlkLaunch
         int tstamp = 0;
         if(tracing) L.trace[tstamp++] = clock64();
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
-        for(int i = tid; i < N; i += T) {
-            tm.gc[i] = P.gcode[(size_t) plocus * N + i];
-            tm.dgl[i] = has_left ? dgp[(size_t)(locus - 1) * N + i] : 0;
-            tm.dgr[i] = has_right ? dgp[(size_t)(locus + 1) * N + i] : 0;
+        if((N & 3) == 0) {
+            // rows are 4-byte aligned: word loads (one 200-byte row is two or three sectors)
+            const uint32_t* g4 = (const uint32_t*)(P.gcode + (size_t) plocus * N);
+            const uint32_t* l4 = (const uint32_t*)(dgp + (size_t)(has_left ? locus - 1 : locus) * N);
+            const uint32_t* r4 = (const uint32_t*)(dgp + (size_t)(has_right ? locus + 1 : locus) * N);
+            for(int i = tid; i < (N >> 2); i += T) {
+                ((uint32_t*) tm.gc)[i] = __ldg(g4 + i);
+                ((uint32_t*) tm.dgl)[i] = has_left ? l4[i] : 0u;
+                ((uint32_t*) tm.dgr)[i] = has_right ? r4[i] : 0u;
+            }
+        }
+        else {
+            for(int i = tid; i < N; i += T) {
+                tm.gc[i] = P.gcode[(size_t) plocus * N + i];
+                tm.dgl[i] = has_left ? dgp[(size_t)(locus - 1) * N + i] : 0;
+                tm.dgr[i] = has_right ? dgp[(size_t)(locus + 1) * N + i] : 0;
+            }
         }
         for(int i = tid; i < 28; i += T)
             tm.scal[16 + i] = (i < 20) ? kSlkClassPrior[i >> 2][i & 3] : P.fprior[(size_t) plocus * 8 + (i - 20)];
@@ -335,9 +365,16 @@ __global__ void __launch_bounds__(MAXCTA, 1) slk_lodscore_kernel(const SlkLaunch
 
         int ncross = 0;
         if(!L.no_dg) {
-            for(int i = tid; i < N; i += T) {
-                tm.dgl[i] = L.dgp[row_l * N + i];
-                tm.dgr[i] = L.dgp[row_r * N + i];
+            if((N & 3) == 0) {
+                const uint32_t* l4 = (const uint32_t*)(L.dgp + row_l * N);
+                const uint32_t* r4 = (const uint32_t*)(L.dgp + row_r * N);
+                for(int i = tid; i < (N >> 2); i += T) { ((uint32_t*) tm.dgl)[i] = l4[i]; ((uint32_t*) tm.dgr)[i] = r4[i]; }
+            }
+            else {
+                for(int i = tid; i < N; i += T) {
+                    tm.dgl[i] = L.dgp[row_l * N + i];
+                    tm.dgr[i] = L.dgp[row_r * N + i];
+                }
             }
             if(tid == 0) {
                 // trait_rfunction.h:50-56

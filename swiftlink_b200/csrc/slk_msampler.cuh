@@ -59,6 +59,9 @@
 #define SLK_SLOT_KIND     0x7ffffff2u
 #define SLK_SLOT_MEIOSIS  0x40000000u
 
+#ifndef SLK_MS_NODE_WALK
+#define SLK_MS_NODE_WALK 1           // 1: disjoint-set forest over the founder alleles themselves (ms_walk below)
+#endif
 #define SLK_MS_MAXSETS 3
 #define SLK_MS_REC_WORDS 448
 #define SLK_MS_MAXGROUPS 4095
@@ -156,7 +159,11 @@ __host__ __device__
 static inline MsLayout slk_ms_layout(int N, int F, int nt) {
     MsLayout L;
     L.wide = (2 * F > 255) ? 1 : 0;
+#if SLK_MS_NODE_WALK
+    L.G = 2 * F;                     // one union-find word per founder allele (ms_walk)
+#else
     L.G = nt < 2 * F ? nt : 2 * F;
+#endif
     if(L.G < 1) L.G = 1;
     const uint32_t E = L.wide ? 2u : 1u;
 #define r4(x) ((((uint32_t)(x)) + 3u) & ~3u)
@@ -170,7 +177,11 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
     L.grp = 0;
     L.cnt = L.grp + 4u * L.G;
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
+#if SLK_MS_NODE_WALK
+    const uint32_t c_bytes = L.fa;
+#else
     const uint32_t c_bytes = L.fa + r4(4u * F);
+#endif
     L.per_thread = L.ov + r4(a_bytes > c_bytes ? a_bytes : c_bytes);
     L.cta_tables = r8((uint32_t)(16 * (N - F) + 4 * nt + nt + 8));
 #undef r4
@@ -198,6 +209,162 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
 // fa entry (u16): bits 0..11 component + 1 (0 = none), bit 14 / 15 = candidate allele under
 // assignment 0 / 1 is HOMOZ_B (in the frame of that component).
 
+#if SLK_MS_NODE_WALK
+// The walk over the typed people (founder_allele_graph4.cc:34-424) shared by the two likelihood kernels, as a
+// disjoint-set forest over the FOUNDER ALLELES with parity bits.
+//
+// A typed person is an edge between the founder alleles its two alleles descend from.  A heterozygous genotype says
+// the two alleles differ, a homozygous one that both equal the observed allele; an assignment of A / B to the founder
+// alleles has probability prod p(allele), and the likelihood is the sum over the assignments consistent with every
+// edge.  It factorises over the connected components; a component is inconsistent (likelihood 0), or has one
+// consistent assignment (some homozygous edge fixed it), or exactly two, complementary ones (only heterozygous edges).
+// The reference keeps explicit component tables and relabels every founder allele on each merge
+// (combine_components, founder_allele_graph4.cc:504-546); here every founder allele is a node of a disjoint-set
+// forest: a word holds its parent, the parity to the parent ("my value is the opposite of my parent's") and, at a
+// root, whether the component is fixed and to which root value, and n0 / n1 = how many of its alleles have the root's
+// value / the opposite one.  A union is two stores; the counts play the role of the reference's two probability
+// products: fixed to root value x the component weighs p(x)^n0 p(!x)^n1, unfixed M^n0 m^n1 + m^n0 M^n1, so the kernel
+// returns ln L = A ln(major) + B ln(minor) + sum over unfixed components of ln(1 + (minor/major)^|n0-n1|): exact
+// integer bookkeeping, one rounding step at the end (checked against the oracle's explicit products on every test
+// pedigree).  An allele no typed person carries is a component of its own that sums to major + minor = 1.
+//
+// node word: bits 0..11 parent, bit 12 parity to parent, bits 13..14 state (0 unfixed, 1 / 2 fixed to root value
+// 0 / 1), bit 15 touched by an edge, bits 16..23 n0, 24..31 n1 (wide: n0, n1 16 bits each in a second word).
+// `src.next(k, g, mat, pat)` supplies the k-th typed person's observed genotype and founder-allele labels.
+template<bool WIDE, class Src>
+__device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint32_t o_cnt, uint32_t /*o_fa*/, int F, int nt,
+                                          const uint8_t* /*s_auto*/, Src& src, double lnM, double lnm, long long* tr) {
+    const int nn = 2 * F;
+    for(int i = 0; i < nn; ++i) {
+        if(WIDE) { ms_st32(ln.a32(o_grp, i), (uint32_t) i); ms_st32(ln.a32(o_cnt, i), 1u); }
+        else ms_st32(ln.a32(o_grp, i), (uint32_t) i | (1u << 16));
+    }
+    struct Node { uint32_t meta, n0, n1; };
+    auto node_ld = [&](uint32_t g) -> Node {
+        Node r;
+        const uint32_t w = ms_ld32(ln.a32(o_grp, g));
+        r.meta = w & 0xffffu;
+        if(WIDE) { const uint32_t c = ms_ld32(ln.a32(o_cnt, g)); r.n0 = c & 0xffffu; r.n1 = c >> 16; }
+        else { r.n0 = (w >> 16) & 0xffu; r.n1 = w >> 24; }
+        return r;
+    };
+    auto node_st = [&](uint32_t g, uint32_t meta, uint32_t n0, uint32_t n1) {
+        if(WIDE) { ms_st32(ln.a32(o_grp, g), meta); ms_st32(ln.a32(o_cnt, g), n0 | (n1 << 16)); }
+        else ms_st32(ln.a32(o_grp, g), meta | (n0 << 16) | (n1 << 24));
+    };
+    // root of node g (its entry e is passed in so that two first loads can be issued together): returns the root,
+    // its entry, and the parity of g to the root
+    auto find_from = [&](uint32_t g, Node e, Node& re, uint32_t& par) -> uint32_t {
+        const uint32_t g0 = g;
+        par = 0;
+        int hops = 0;
+        while((e.meta & 0xfffu) != g) {
+            par ^= (e.meta >> 12) & 1u;
+            g = e.meta & 0xfffu;
+            e = node_ld(g);
+            ++hops;
+        }
+        if(hops > 1) node_st(g0, g | (par << 12), 0u, 0u);           // path compression (a non-root's counts are dead)
+        re = e;
+        return g;
+    };
+
+    bool dead = false;
+    const int niter = src.iterations(nt);
+    for(int it = 0; it < niter && !dead; ++it) {
+        uint32_t g, mat, pat;
+        bool single;                                    // x-linked male: the maternal allele only
+        const int k = src.next(it, g, mat, pat, single);       // < 0: nobody to visit in this iteration
+        if(k < 0 || g == SLK_UNTYPED) continue;
+        const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
+        const bool het = g == SLK_HETERO;
+        const bool self = mat == pat || single;
+        if(self && het) { dead = true; break; }
+        const Node eu = node_ld(mat), ev = node_ld(self ? mat : pat);      // both loads in flight together
+        Node ru, rv; uint32_t pu, pv;
+        const uint32_t u = find_from(mat, eu, ru, pu);
+        uint32_t root = u, proot = pu;                   // the component's root after this edge, mat's parity to it
+        Node rr = ru;
+        if(!self) {
+            const uint32_t v = find_from(pat, ev, rv, pv);
+            const uint32_t pi = (het ? 1u : 0u) ^ pu ^ pv;        // required: value(root u) ^ value(root v)
+            if(u == v) {
+                if(pi) { dead = true; break; }
+            }
+            else {
+                // union by size: the smaller tree hangs under the larger one's root
+                const bool u_big = ru.n0 + ru.n1 >= rv.n0 + rv.n1;
+                const uint32_t big = u_big ? u : v, small = u_big ? v : u;
+                const Node rb = u_big ? ru : rv, rs = u_big ? rv : ru;
+                uint32_t sb = (rb.meta >> 13) & 3u;
+                const uint32_t ss = (rs.meta >> 13) & 3u;
+                if(ss) {
+                    const uint32_t xs = ((ss - 1u) ^ pi) + 1u;           // the small root's fixed value in the big root's frame
+                    if(sb == 0u) sb = xs;
+                    else if(sb != xs) { dead = true; break; }
+                }
+                rr.meta = big | (sb << 13) | 0x8000u;
+                rr.n0 = rb.n0 + (pi ? rs.n1 : rs.n0);
+                rr.n1 = rb.n1 + (pi ? rs.n0 : rs.n1);
+                node_st(small, big | (pi << 12), 0u, 0u);
+                root = big;
+                proot = u_big ? pu : (pu ^ pi);
+            }
+        }
+        uint32_t st = (rr.meta >> 13) & 3u;
+        if(!het) {
+            // homozygous: mat's allele is gB, i.e. the root's value is gB ^ parity(mat -> root)
+            const uint32_t x = (gB ^ proot) + 1u;
+            if(st == 0u) st = x;
+            else if(st != x) { dead = true; break; }
+        }
+        node_st(root, root | (st << 13) | 0x8000u, rr.n0, rr.n1);
+    }
+
+    if(tr) tr[5] = clock64();
+    double ret = -INFINITY;
+    if(!dead) {
+        uint32_t A = 0, B = 0;
+        const bool minor_smaller = lnm <= lnM;
+        const double rho = exp(-fabs(lnm - lnM));
+        double prod = 1.0;
+        for(int i0 = 0; i0 < nn; i0 += 4) {
+            // four table words in flight at a time (the loads are ordered asm statements: one per iteration would
+            // pay a shared-memory latency each)
+            Node eq[4];
+#pragma unroll
+            for(int j = 0; j < 4; ++j) {
+                if(i0 + j < nn) eq[j] = node_ld(i0 + j);
+                else { eq[j].meta = 0xfffu; eq[j].n0 = eq[j].n1 = 0u; }
+            }
+#pragma unroll
+            for(int j = 0; j < 4; ++j) {
+                const Node e = eq[j];
+                // roots that an edge touched only (an untouched allele sums to 1; a non-root is counted at its root)
+                if((e.meta & 0xfffu) != (uint32_t)(i0 + j) || !(e.meta & 0x8000u)) continue;
+                const uint32_t stt = (e.meta >> 13) & 3u;
+                uint32_t a, b;
+                if(stt == 0u) {
+                    // two complementary assignments: M^n0 m^n1 + m^n0 M^n1; keep the larger term, more factors of the
+                    // more frequent allele, and multiply up the (1 + rho^k) corrections
+                    const uint32_t hi = e.n0 > e.n1 ? e.n0 : e.n1, lo = e.n0 > e.n1 ? e.n1 : e.n0;
+                    uint32_t kk = hi - lo;
+                    if(minor_smaller) { a = hi; b = lo; } else { a = lo; b = hi; }
+                    double t = 1.0, sq = rho;
+                    while(kk) { if(kk & 1u) t *= sq; sq *= sq; kk >>= 1; }
+                    prod *= 1.0 + t;
+                }
+                else if(stt == 1u) { a = e.n0; b = e.n1; }       // root value 0 (allele A, the major allele's exponent first)
+                else               { a = e.n1; b = e.n0; }
+                A += a; B += b;
+            }
+        }
+        ret = ((double) A * lnM + (double) B * lnm) + log(prod);
+        if(!(ret > -1e290)) ret = -INFINITY;               // a zero allele frequency entered the product
+    }
+    return ret;
+}
+#else
 // The walk over the typed people (founder_allele_graph4.cc:34-424) shared by the two likelihood kernels.
 // `src.next(k, g, mat, pat)` supplies the k-th typed person's observed genotype and founder-allele labels.
 #define FA_LD(k)      ms_ld16(ln.a16(o_fa, (k)))
@@ -443,6 +610,7 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
 }
 #undef FA_LD
 #undef FA_ST
+#endif  // SLK_MS_NODE_WALK
 
 template<bool WIDE>
 __global__ void __launch_bounds__(32)
@@ -627,12 +795,20 @@ __host__ __device__
 static inline MsStepLayout slk_ms_step_layout(int N, int F, int nt, int W) {
     MsStepLayout L;
     L.wide = (2 * F > 255) ? 1 : 0;
+#if SLK_MS_NODE_WALK
+    L.G = 2 * F;
+#else
     L.G = nt < 2 * F ? nt : 2 * F;
+#endif
     if(L.G < 1) L.G = 1;
     L.grp = 0;
     L.cnt = L.grp + 4u * L.G;
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
+#if SLK_MS_NODE_WALK
+    L.hmask = L.fa;
+#else
     L.hmask = L.fa + ((4u * F + 3u) & ~3u);
+#endif
     L.per_thread = L.hmask + 4u * W;
     L.cta_tables = ((uint32_t)(4 * N + 2 * nt + nt + 4 + 4 * W + 2 * nt + 8 + 8) + 7u) & ~7u;
     return L;

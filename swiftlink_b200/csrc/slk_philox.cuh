@@ -18,6 +18,12 @@
 
 #define SLK_SLOT_PHASE 0x7ffffff0u
 
+// Partition of the `iteration` counter.  MCMC iterations count up from 0; the sequential-imputation runs that build
+// a chain's start graph (and the locus-by-locus fallback) are numbered from SLK_SI_FIRST_RUN, so the two never share
+// a (seed, chain, iteration, locus, slot) tuple -- with a common numbering a chain started with `-b 0` would redraw,
+// in its first sweeps, the uniforms that had produced its start graph.
+#define SLK_SI_FIRST_RUN (1ull << 62)
+
 #if defined(__CUDACC__)
 #define SLK_HD __host__ __device__ __forceinline__
 #else

@@ -299,7 +299,7 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
         if(trait) { lay.off_dprob = o; o += N * 32; }
         lay.blob_bytes = o;
     }
-    pr.prog_smem_bytes = lay.blob_bytes;
+    pr.prog_smem_bytes = lay.blob_bytes + 16;          // + the mbarrier of the bulk copy that stages the blob
 
     // ---- arena ----
     pr.mat_off.assign(nops, 0);
@@ -519,6 +519,8 @@ bool build_plan(const slk_problem& pb, HostPlan& hp, std::string& err) {
         hp.male[i] = pb.sex[i] == SLK_MALE;
     }
     hp.disease_prob.assign(pb.disease_prob, pb.disease_prob + 4 * N);
+    const double* pp = pb.person_prior ? pb.person_prior : pb.disease_prob;
+    hp.person_prior.assign(pp, pp + 4 * N);
 
     // ---- peel sequence sanity ----
     std::vector<int> seen(N, 0), used(N, 0);

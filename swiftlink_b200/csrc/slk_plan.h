@@ -40,6 +40,7 @@ struct HostPlan {
     std::vector<int16_t> mother, father;
     std::vector<uint8_t> male;
     std::vector<double> disease_prob;    // [N][4]
+    std::vector<double> person_prior;    // [N][4] prior of the SLK_PRIOR_PERSON class (ELOD's simulated trait locus)
     std::vector<uint8_t> gcode;          // [M][N]
     std::vector<double> fprior;          // [M][2][4]
     std::vector<double> theta, partial, log_theta, log_1mtheta;

@@ -105,7 +105,7 @@ struct SlkProgram {
     int smem_doubles;               // arena prefix kept in shared memory
     int team_threads;               // 32, 64, 128, 256 or 512
     int cta_threads;
-    int prog_smem_bytes;            // == blob_bytes: CTA-shared copy of the program
+    int prog_smem_bytes;            // blob_bytes + 16: CTA-shared copy of the program and the mbarrier of its bulk copy
     int team_smem_bytes;            // per team: arena prefix + tables
     int table_doubles_per_child;    // 8 (sampler) or 4 (trait)
 };
@@ -132,6 +132,7 @@ struct SlkDevPlan {
     const int16_t* father;          // [N]
     const uint8_t* male;            // [N]
     const double* disease_prob;     // [N][4]
+    const double* person_prior;     // [N][4] prior of the SLK_PRIOR_PERSON class
     const uint8_t* gcode;           // [M][N]: legal mask (trait encoding) | prior class << 4
     const double* fprior;           // [M][2][4] founder priors (autosomal/female, X male)
     const double* theta;            // [M-1]

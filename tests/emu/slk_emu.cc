@@ -138,7 +138,7 @@ double emu_ls_step(void* h, int32_t* dg, int locus, int ign_left, int ign_right,
     TeamMem t;
     carve(hp, pr, t);
     const SlkTeam& tm = t.tm;
-    const SlkProgView pg = view_of(pr, hp.disease_prob.data());
+    const SlkProgView pg = view_of(pr, hp.person_prior.data());
     const SlkEnv E = env_of(hp, matrices, presums);
     const bool has_left = locus != 0, has_right = locus != M - 1;
 

@@ -30,6 +30,12 @@ def main():
             for s in SEEDS]
     out["east_dominant"] = np.array(vals)
     print("east_dominant", vals)
+    # --elod -a on east with a reduced-penetrance model: unaffected people are simulated with their phenotype and scored
+    # as unknown (elod.h:83-87)
+    vals = [R.elod(R.example("east")[0], frequency=1e-3, penetrance=(0.01, 0.8, 0.8), separation=0.1, replicates=REPLICATES, seed=s,
+                   affected_only=True) for s in SEEDS]
+    out["east_dominant_affected_only"] = np.array(vals)
+    print("east_dominant_affected_only", vals)
     np.savez_compressed(os.path.join(OUT, "elod_ref.npz"), **out)
 
 

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_header_symbols():
     for name in declared:
         assert hasattr(L, name), "missing export: " + name
     assert sorted(capi.SYMBOLS) == declared
-    assert L.slk_abi_version() == 3
+    assert L.slk_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():

@@ -42,15 +42,17 @@ def test_replicates_match_oracle(name):
 
 
 @pytest.mark.skipif(not ref_available(), reason="example inputs live in oracle/_ref/examples")
-@pytest.mark.parametrize("case", ["east", "loop", "xlinked", "east_dominant"])
+@pytest.mark.parametrize("case", ["east", "loop", "xlinked", "east_dominant", "east_dominant_affected_only"])
 def test_elod_agrees_with_reference_within_mc_error(case):
     """swiftlink::Elod (fake map, genotype-free pedigree, peel search, batched replicates) vs the reference's Elod::run"""
     from oracle import refapi
     from swiftlink_b200 import host as H
     ref = np.load(os.path.join(GOLDEN, "elod_ref.npz"))
     kw = dict(replicates=400000, peel_iterations=20000, seed=77)
-    if case == "east_dominant":
-        total, per = H.elod(refapi.example("east")[0], frequency=1e-3, penetrance=(0.01, 0.8, 0.8), separation=0.1, **kw)
+    if case.startswith("east_dominant"):
+        # `-a`: the simulation keeps the real phenotypes (slk_problem.person_prior), the scoring treats unaffected people as unknown
+        total, per = H.elod(refapi.example("east")[0], frequency=1e-3, penetrance=(0.01, 0.8, 0.8), separation=0.1,
+                            affected_only=case.endswith("affected_only"), **kw)
     else:
         total, per = H.elod(refapi.example(case)[0], sex_linked=(case == "xlinked"), **kw)
     vals = ref[case]
