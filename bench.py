@@ -570,12 +570,227 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------------------------
+# the reference's example configurations (BASELINE.json configs[0], [1], [4]): --config east | loop | xlinked
+# ---------------------------------------------------------------------------------------------
+
+SMALL_CONFIGS = {
+    # name: replicates (-R), -X, iterations per bench step, reference CLI command
+    # ref_iterations: burn-in + iterations per replicate of the reference CLI run (its default is 100 000)
+    "east":    dict(runs=1, sex_linked=False, step_iterations=2000, ref_iterations=10000, cli="swift -p east.ped -m east.map -d east.dat"),
+    "loop":    dict(runs=10, sex_linked=False, step_iterations=2000, ref_iterations=100000, cli="swift -p loop.ped -m loop.map -d loop.dat -R 10"),
+    "xlinked": dict(runs=1, sex_linked=True, step_iterations=2000, ref_iterations=100000, cli="swift -p xlinked.ped -m xlinked.map -d xlinked.dat -X"),
+}
+SMALL_SCORING_PERIOD = 10                  # defaults.h: DEFAULT_MCMC_SCORING_PERIOD
+SMALL_SI_RUNS = 100
+
+
+def small_config_desc(name):
+    c = SMALL_CONFIGS[name]
+    return {"workload": "reference example %s (`%s`), default sampler mix (-l 0.5), LOD scoring (5 positions/interval) every "
+                        "%dth iteration, %d replicate chain(s)" % (name, c["cli"], SMALL_SCORING_PERIOD, c["runs"]),
+            "step": "%d MCMC iterations of each of the %d replicate(s), scoring passes included" % (c["step_iterations"], c["runs"]),
+            "lsampler_prob": LSAMPLER_PROB, "n_lod": N_LOD, "replicates": c["runs"], "sex_linked": c["sex_linked"]}
+
+
+def reference_cli_best(name):
+    """the reference CLI with one thread and with every host core (`-c`): on the tiny examples its OpenMP loops lose to one
+    thread; the faster of the two is the baseline, with the thread count it used"""
+    its = SMALL_CONFIGS[name]["ref_iterations"]
+    cores = min(os.cpu_count() or 1, 64)
+    # (the all-core run is given a fifth of the iterations: on these inputs it is the slower one by far)
+    runs = [reference_cli_rate(name, th, its if th == 1 else max(its // 5, 1000)) for th in sorted(set([1, cores]))]
+    v, info = max(runs, key=lambda r: r[0])
+    info["all_runs"] = [dict(threads=i["threads"], iterations_per_s=r, setup_s=i["setup_s"], run_s=i["run_s"]) for r, i in runs]
+    return v, info
+
+
+def reference_cli_rate(name, threads, iterations):
+    """the reference's own `swift` (oracle/_ref/swift, unmodified, built by oracle/Makefile) on the example: wall time of
+    the run minus the wall time of the same command with `-b 0 -i 1` (set-up: parsing, peel-sequence search,
+    sequential imputation), as BASELINE.md section 3.2 defines the end-to-end rate"""
+    from oracle import refapi
+    exe = os.path.join(refapi.REF_DIR, "swift")
+    c = SMALL_CONFIGS[name]
+    ped, mp, dat = refapi.example(name)
+    d = tempfile.mkdtemp(prefix="slk_refcli_")
+    base = [exe, "-p", ped, "-m", mp, "-d", dat, "-c", str(threads), "-o", os.path.join(d, "out.txt")]
+    if c["runs"] > 1:
+        base += ["-R", str(c["runs"])]
+    if c["sex_linked"]:
+        base += ["-X"]
+
+    def wall(burnin, iters):
+        t0 = time.perf_counter()
+        p = subprocess.run(base + ["-b", str(burnin), "-i", str(iters)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("reference swift failed: " + p.stderr[-300:])
+        return time.perf_counter() - t0
+    t_setup = wall(0, 1)
+    t_run = wall(iterations // 2, iterations - iterations // 2)
+    its = c["runs"] * iterations
+    return its / max(t_run - t_setup, 1e-9), dict(setup_s=t_setup, run_s=t_run, iterations=its, threads=threads,
+                                                  command=" ".join(["swift"] + base[1:7] + base[9:]) + " -b %d -i %d" % (iterations // 2, iterations - iterations // 2))
+
+
+def run_small_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import refapi
+    name = args.config
+    if not (refapi.available() and os.path.exists(os.path.join(refapi.REF_DIR, "swift"))):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/swift not built"}))
+        return
+    best, info = reference_cli_best(name)
+    threads = info["threads"]
+    line = {"impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * SMALL_CONFIGS[name]["runs"] * SMALL_CONFIGS[name]["step_iterations"] / best,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference example files",
+            "config": small_config_desc(name),
+            "cpu_baseline": {"value": best, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": "UNMODIFIED reference CLI `%s`: wall time minus the wall time of the same command with "
+                                       "-b 0 -i 1 (set-up %.2f s)" % (info["command"], info["setup_s"])},
+            "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "detail": info}
+    print(json.dumps(line))
+
+
+def run_small_ours(args, rank, world, local_rank):
+    """one of the reference's example pedigrees through the host API the `swift` command line drives
+    (swiftlink::run_replicates, csrc/host/gpu.cc): every replicate chain on the device, all of them in flight at once"""
+    import torch
+    from oracle import refapi                       # example input files only (they live in oracle/_ref/examples)
+    from swiftlink_b200 import build, capi, host as H
+    build.build()
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    name = args.config
+    cfg = SMALL_CONFIGS[name]
+    files = refapi.example(name)
+    hst = H.Host(*files, sex_linked=cfg["sex_linked"], lodscores=N_LOD)
+    hst.build_peel(100000)
+    S, R = cfg["step_iterations"], cfg["runs"]
+
+    def call(iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lod = hst.run_replicates(R, R, 0, iters, scoring_period=SMALL_SCORING_PERIOD, seed=20261017 + rank, device=local_rank,
+                                 lsampler_prob=LSAMPLER_PROB, si_iterations=SMALL_SI_RUNS)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, lod
+    for _ in range(max(args.warmup, 1)):
+        call(S // 10)
+    setups = sorted(call(1)[0] for _ in range(3))
+    t_setup = setups[1]
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    secs, lod = 0.0, None
+    for _ in range(args.steps):
+        t, lod = call(S)
+        secs += max(t - t_setup, 1e-9)
+    clock_info = clocks.stop()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    value = world * R * S * args.steps / secs
+
+    # ---- the LOD kernel alone on one descent graph, next to the reference's own GPU kernel and its CPU peeler ----
+    derived = {"setup_s_per_call": t_setup, "lod_max": float(np.max(lod)),
+               "note": "value = replicates x iterations / (wall time of swiftlink::run_replicates - wall time of the same call "
+                       "with 1 iteration); host buffers in and out, so value and e2e are the same measurement"}
+    plan = H.PlanFromHost(hst, device=local_rank)
+    chain = capi.Chain(plan, seed=1)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    chain.set_stream(stream.cuda_stream)
+    chain.sequential_imputation(run=0, start_locus=hst.M // 2)
+    for it in range(1, 20):
+        chain.lsampler_sweep(it)
+    chain.sync()
+
+    def kernel_ms(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+    positions = (hst.M - 1) * N_LOD
+    lod_ms = kernel_ms(chain.lodscore_accumulate, 200)
+    ctr = [100]
+
+    def lsweep():
+        chain.lsampler_sweep(ctr[0]); ctr[0] += 1
+
+    def msweep():
+        chain.msampler_sweep(ctr[0]); ctr[0] += 1
+    ls_ms = kernel_ms(lsweep, 200)
+    ms_ms = kernel_ms(msweep, 50)
+    derived.update({"lod_pass_ms": lod_ms, "trait_positions_per_s_kernel": positions / (lod_ms * 1e-3), "l_sweep_ms": ls_ms,
+                    "m_sweep_ms": ms_ms, "meioses_per_m_sweep": len(plan.msampler_ordering()),
+                    "n_members": hst.N, "n_markers": hst.M})
+    stats = plan.stats()
+    fp64_peak = capi.measure_fp64_peak(local_rank)
+    lod_tflops = stats["flops_lod"] * positions / (lod_ms * 1e-3) / 1e12
+    roofline = {"kernel": "slk_lodscore_kernel", "bound": "tensor", "unit": "TFLOP/s", "achieved": lod_tflops, "peak": fp64_peak,
+                "frac": lod_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "FP64 FMA microbenchmark run in this process (the kernel is FP64 CUDA-core work, not tensor-core work; "
+                               "MEASURED_PEAKS.json has no FP64 figure)",
+                "launch_ms": lod_ms, "units_per_launch": positions,
+                "note": "%d positions per launch: a launch of this size is launch-latency bound, not pipe bound" % positions}
+    chain.close(); plan.close()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "reference example files", "config": small_config_desc(name),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": R * hst.M * hst.N * 8,
+                    "d2h_bytes_per_step": R * hst.M * hst.N * 8 + positions * 8, "ms_per_step": 1e3 * secs / args.steps},
+            "gpu_launches": None, "clocks": clock_info, "roofline": roofline, "derived": derived}
+    # launches of a step, counted from the sweep kinds the chains draw: L-sweep 2, M-sweep 1 + 2 ceil(n / 2), scoring 1
+    n_me = derived["meioses_per_m_sweep"]
+    line["gpu_launches"] = int(args.steps * R * (S * (0.5 * 2 + 0.5 * (1 + 2 * ((n_me + 1) // 2))) + S // SMALL_SCORING_PERIOD))
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import refgpu
+            if refgpu.available() and not cfg["sex_linked"]:         # the reference refuses -g with -X (main.cc:534-537)
+                out = os.path.join(tempfile.gettempdir(), "slk_refgpu_%s_%d.npz" % (name, os.getpid()))
+                rg = refgpu.run_in_subprocess(name, 50, out)
+                derived["reference_gpu_kernel"] = {
+                    "kernel": "lodscore_kernel (cuda_lodscore.cu:389-467) via GPULodscores::calculate, compiled for sm_100a",
+                    "ms_per_pass": 1e3 * float(rg["secs_per_pass"]), "trait_positions_per_s": positions / float(rg["secs_per_pass"]),
+                    "block_threads": int(rg["block_threads"]), "setup_s": float(rg["setup_s"]),
+                    "reference_cpu_1_thread_trait_positions_per_s": positions / float(rg["cpu_secs_per_pass_1thread"]),
+                    "note": "calculate() includes the reference's synchronous copy of the descent graph, as its own loop does"}
+            v, info = reference_cli_best(name)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "reference", "runs": info["all_runs"],
+                                    "sample": "UNMODIFIED reference CLI `%s`: wall time minus the wall time of the same command "
+                                              "with -b 0 -i 1 (set-up %.2f s)" % (info["command"], info["setup_s"])}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+    hst.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="synth200", choices=["synth200", "east", "loop", "xlinked"],
+                    help="synth200 (default): BASELINE.json configs[2], the configuration the metric is quoted on; "
+                         "east / loop / xlinked: the reference's example pedigrees (configs[0], [1], [4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0,
                     help="--impl reference: size of the bounded sample one step times (seconds of CPU work, approximately)")
@@ -585,7 +800,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.config != "synth200":
+        if args.impl == "reference":
+            run_small_reference(args, rank)
+        else:
+            run_small_ours(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank)
     else:
         run_ours(args, rank, world, local_rank)

@@ -1,0 +1,36 @@
+"""slk_lodscore_kernel against the reference's OWN GPU kernel (lodscore_kernel, cuda_lodscore.cu:389-467, driven by
+GPULodscores::calculate / get_results, gpu_lodscores.cc:598-637) built for sm_100a by `make -C oracle refgpu`: the same
+descent graph, the same elimination order, the normalised LOD table of both.  The reference runs in a process of its own
+(oracle/refgpu.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import ref_available
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["east", "loop"])
+def test_lod_table_matches_reference_gpu_kernel(case, tmp_path):
+    from oracle import refapi, refgpu
+    from swiftlink_b200 import capi, host as H
+    if not (ref_available() and refgpu.available()):
+        pytest.skip("oracle/_ref/libswiftref_gpu.so not built")
+    reps = 3
+    ref = refgpu.run_in_subprocess(case, reps, str(tmp_path / "refgpu.npz"))
+    hst = H.Host(*refapi.example(case), lodscores=5)
+    assert hst.set_peel(ref["order"])
+    plan = H.PlanFromHost(hst)
+    chain = capi.Chain(plan, seed=1)
+    chain.dg_upload(ref["dg"])
+    chain.lodscore_init()
+    for _ in range(reps + 1):                     # the reference's run: one warm-up pass + reps passes of the same graph
+        chain.lodscore_accumulate()
+    tp = plan.trait_likelihood()
+    assert abs(tp - float(ref["trait_prob"])) <= 1e-12 * abs(tp)
+    lod = chain.lodscore_normalise(tp).reshape(ref["lod"].shape)
+    scale = max(1.0, float(np.abs(ref["lod"]).max()))
+    assert np.abs(lod - ref["lod"]).max() <= 1e-9 * scale
+    chain.close(); plan.close(); hst.close()
