@@ -656,6 +656,21 @@ def run_small_reference(args, rank):
     print(json.dumps(line))
 
 
+class quiet_stdout(object):
+    """the host classes print what the reference prints (starting likelihood, P(T), ...) on file descriptor 1; the bench
+    line must be the only thing on stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved); os.close(self.null)
+
+
 def run_small_ours(args, rank, world, local_rank):
     """one of the reference's example pedigrees through the host API the `swift` command line drives
     (swiftlink::run_replicates, csrc/host/gpu.cc): every replicate chain on the device, all of them in flight at once"""
@@ -676,8 +691,9 @@ def run_small_ours(args, rank, world, local_rank):
     def call(iters):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        lod = hst.run_replicates(R, R, 0, iters, scoring_period=SMALL_SCORING_PERIOD, seed=20261017 + rank, device=local_rank,
-                                 lsampler_prob=LSAMPLER_PROB, si_iterations=SMALL_SI_RUNS)
+        with quiet_stdout():
+            lod = hst.run_replicates(R, R, 0, iters, scoring_period=SMALL_SCORING_PERIOD, seed=20261017 + rank, device=local_rank,
+                                     lsampler_prob=LSAMPLER_PROB, si_iterations=SMALL_SI_RUNS)
         torch.cuda.synchronize()
         return time.perf_counter() - t0, lod
     for _ in range(max(args.warmup, 1)):

@@ -78,6 +78,24 @@ int slk_host_run_mc3(slk_host* h, int device, uint64_t seed, uint32_t chain_id, 
                      const double* temperatures, int burnin, int iterations, int scoring_period, double lsampler_prob,
                      int si_iterations, double* lod_out, int32_t* swap_success, int32_t* swap_failure);
 double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures);
+
+/* One device's share of a `-R` job (LinkageProgram::run_pedigree's replicate loop, linkage_program.cc:96-108): the
+   replicates `replicate_ids` (their chain ids; a job of R replicates over W processes places replicate r on process
+   r mod W), each a plain chain (mc3_chains <= 1) or a Metropolis-coupled ladder of mc3_chains chains (mc3.cc:81-200),
+   all resident on `device` at once.  create() builds the chains and their sequential-imputation start states;
+   advance() runs the next n iterations of every replicate (ladders: whole spurts of the exchange period) and returns
+   how many were run; results() merges the replicates' RAW log-sum accumulators and counts as LODscores::merge_results
+   does (lod_score.h:98-105) -- raw[(M-1)*n_lod], LOG_ZERO (-DBL_MAX) where nothing was scored -- so that tables of
+   different processes can be merged the same way (max / sum-exp / sum all-reduces, swiftlink_b200/dist.py), and sums
+   the ladders' swap counters into swap_success / swap_failure [n_swap]. */
+typedef struct slk_host_job slk_host_job;
+slk_host_job* slk_host_job_create(slk_host* h, int device, uint64_t seed, const int32_t* replicate_ids, int n_replicates,
+                                  int mc3_chains, int exchange_period, const double* temperatures, int burnin, int iterations,
+                                  int scoring_period, double lsampler_prob, int si_iterations);
+int slk_host_job_advance(slk_host_job* job, int n_iterations);
+int slk_host_job_results(slk_host_job* job, double* raw, int32_t* count, double* trait_prob, int32_t* swap_success,
+                         int32_t* swap_failure, int n_swap);
+void slk_host_job_destroy(slk_host_job* job);
 /* Elod(pedfile, options).run() (elod.h:33-107, elod.cc:19-85): expected LOD of every pedigree of the file by
    simulation on the device; per_pedigree[cap] receives the individual values, the total is returned */
 double slk_host_elod(const char* pedfile, double frequency, const double* penetrance, double separation, int replicates,

@@ -238,6 +238,52 @@ double slk_host_elod(const char* pedfile, double frequency, const double* penetr
     return total;
 }
 
+struct slk_host_job {
+    slk_host* host;
+    ReplicateJob* job;
+};
+
+slk_host_job* slk_host_job_create(slk_host* h, int device, uint64_t seed, const int32_t* replicate_ids, int n_replicates,
+                                  int mc3_chains, int exchange_period, const double* temperatures, int burnin, int iterations,
+                                  int scoring_period, double lsampler_prob, int si_iterations) {
+    if(!h || !h->psg || n_replicates < 0 || (n_replicates > 0 && !replicate_ids)) return 0;
+    struct mcmc_options o;
+    o.burnin = burnin; o.iterations = iterations; o.scoring_period = scoring_period; o.si_iterations = si_iterations;
+    o.lsampler_prob = lsampler_prob; o.sex_linked = h->dm.is_sexlinked(); o.seed = seed; o.device = device;
+    o.mc3 = mc3_chains > 1; o.mc3_number_of_chains = mc3_chains > 1 ? mc3_chains : 1; o.mc3_exchange_period = exchange_period;
+    if(temperatures && mc3_chains > 1) o.mc3_temperatures.assign(temperatures, temperatures + mc3_chains);
+    slk_host_job* j = new slk_host_job();
+    j->host = h;
+    j->job = new ReplicateJob(h->ped, &h->map, h->psg, o, std::vector<int>(replicate_ids, replicate_ids + n_replicates));
+    return j;
+}
+
+int slk_host_job_advance(slk_host_job* j, int n_iterations) {
+    return j ? j->job->advance(n_iterations) : 0;
+}
+
+int slk_host_job_results(slk_host_job* j, double* raw, int32_t* count, double* trait_prob, int32_t* swap_success, int32_t* swap_failure,
+                         int n_swap) {
+    if(!j) return SLK_ERR_INVALID;
+    std::vector<int> ok, bad;
+    LODscores* lod = j->job->results(&ok, &bad);
+    if(raw) for(unsigned i = 0; i < lod->num_lodscores(); ++i) raw[i] = lod->get_count() > 0 ? lod->get_raw(i) : LOG_ZERO;
+    if(count) *count = (int32_t) lod->get_count();
+    if(trait_prob) *trait_prob = lod->get_trait_prob();
+    for(int i = 0; i < n_swap; ++i) {
+        if(swap_success) swap_success[i] = i < (int) ok.size() ? ok[i] : 0;
+        if(swap_failure) swap_failure[i] = i < (int) bad.size() ? bad[i] : 0;
+    }
+    delete lod;
+    return SLK_OK;
+}
+
+void slk_host_job_destroy(slk_host_job* j) {
+    if(!j) return;
+    delete j->job;
+    delete j;
+}
+
 double slk_host_mc3_temperature(int chain_index, int n_chains, const double* temperatures) {
     struct mcmc_options o;
     o.mc3 = true; o.mc3_number_of_chains = n_chains;

@@ -26,7 +26,7 @@ double mc3_temperature(int i, const struct mcmc_options& options) {
 }
 
 Mc3::Mc3(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num) :
-    ped(ped), map(map), psg(psg), options(options), seq_num(sequence_num) {
+    ped(ped), map(map), psg(psg), options(options), seq_num(sequence_num), period(10), spurts_done(0), rng(0) {
     if(options.mc3_number_of_chains < 1) { fprintf(stderr, "error: number of Markov chains must be greater than zero\n"); abort(); }
     if(!options.mc3_temperatures.empty() && (int) options.mc3_temperatures.size() != options.mc3_number_of_chains) {
         fprintf(stderr, "error: %d temperatures given for %d chains\n", (int) options.mc3_temperatures.size(), options.mc3_number_of_chains);
@@ -46,7 +46,9 @@ Mc3::~Mc3() {
     for(size_t i = 0; i < chains.size(); ++i) delete chains[i];
 }
 
-LODscores* Mc3::run() {
+// Mc3::run in four parts, so that a caller can keep several ladders in flight on one device (ReplicateJob, job.cc):
+// enqueue_spurt only enqueues work on the chains' streams; exchange is where the host waits for the device.
+void Mc3::start() {
     // start states (mc3.cc:91-102): sequential imputation with the cold chain's plan
     for(size_t j = 0; j < chains.size(); ++j) {
         DescentGraph tmp(ped, map, options.sex_linked);
@@ -56,28 +58,37 @@ LODscores* Mc3::run() {
         starter.sequential_imputation(tmp, options.si_iterations);
         chains[j]->upload(tmp);
     }
-    int period = options.mc3_exchange_period;
+    period = options.mc3_exchange_period;
     if(!options.mc3 || chains.size() == 1) period = 10;                   // mc3.cc:108-110
-    const int spurts = (options.burnin + options.iterations) / period;
-    HostRng rng(options.seed ^ (0x4d4333ull << 32) ^ (uint64_t) seq_num);
-    for(int i = 0; i < spurts; ++i) {
-        for(size_t j = 0; j < chains.size(); ++j) chains[j]->step(i * period, period);
-        if(options.mc3 && chains.size() > 1) {
-            const int r = (int)((chains.size() - 1) * rng.uniform());
-            slk_chain* a = chains[r]->get_chain();
-            slk_chain* b = chains[r + 1]->get_chain();
-            const double xx = chains[r]->get_likelihood(), yy = chains[r + 1]->get_likelihood();
-            if(slk_dg_swap(a, b) != SLK_OK) { fprintf(stderr, "error: Mc3 swap: %s\n", slk_last_error()); abort(); }
-            const double xy = chains[r]->get_likelihood(), yx = chains[r + 1]->get_likelihood();
-            const double ratio = (xy + yx) - (xx + yy);
-            const double u = rng.uniform();
-            if(u == 0.0 || log(u) < std::min(0.0, ratio)) swap_success[r] += 1;
-            else {
-                swap_failure[r] += 1;
-                if(slk_dg_swap(a, b) != SLK_OK) { fprintf(stderr, "error: Mc3 swap: %s\n", slk_last_error()); abort(); }
-            }
-        }
+    spurts_done = 0;
+    rng = HostRng(options.seed ^ (0x4d4333ull << 32) ^ (uint64_t) seq_num);
+}
+
+int Mc3::total_spurts() const { return (options.burnin + options.iterations) / period; }
+
+void Mc3::enqueue_spurt() {
+    for(size_t j = 0; j < chains.size(); ++j) chains[j]->step(spurts_done * period, period);
+}
+
+void Mc3::exchange() {
+    ++spurts_done;
+    if(!(options.mc3 && chains.size() > 1)) return;
+    const int r = (int)((chains.size() - 1) * rng.uniform());
+    slk_chain* a = chains[r]->get_chain();
+    slk_chain* b = chains[r + 1]->get_chain();
+    const double xx = chains[r]->get_likelihood(), yy = chains[r + 1]->get_likelihood();
+    if(slk_dg_swap(a, b) != SLK_OK) { fprintf(stderr, "error: Mc3 swap: %s\n", slk_last_error()); abort(); }
+    const double xy = chains[r]->get_likelihood(), yx = chains[r + 1]->get_likelihood();
+    const double ratio = (xy + yx) - (xx + yy);
+    const double u = rng.uniform();
+    if(u == 0.0 || log(u) < std::min(0.0, ratio)) swap_success[r] += 1;
+    else {
+        swap_failure[r] += 1;
+        if(slk_dg_swap(a, b) != SLK_OK) { fprintf(stderr, "error: Mc3 swap: %s\n", slk_last_error()); abort(); }
     }
+}
+
+LODscores* Mc3::finish() {
     if(options.mc3) {
         if(!options.exchange_filename.empty()) {
             FILE* ef = fopen(options.exchange_filename.c_str(), "w");
@@ -97,6 +108,16 @@ LODscores* Mc3::run() {
         return tmp;
     }
     return chains[0]->get_result();
+}
+
+LODscores* Mc3::run() {
+    start();
+    const int spurts = total_spurts();
+    for(int i = 0; i < spurts; ++i) {
+        enqueue_spurt();
+        exchange();
+    }
+    return finish();
 }
 
 }  // namespace swiftlink

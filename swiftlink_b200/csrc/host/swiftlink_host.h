@@ -475,12 +475,45 @@ class Mc3 {
     std::vector<GPUMarkovChain*> chains;
     std::vector<int> swap_success, swap_failure;
     int seq_num;
+    int period, spurts_done;
+    HostRng rng;
  public:
     Mc3(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options, int sequence_num = 0);
     ~Mc3();
     LODscores* run();                           // mc3.cc:81-200; the caller deletes the result
+    // run() = start(); total_spurts() x { enqueue_spurt(); exchange(); }; finish()
+    void start();                               // start states, one sequential-imputation state per chain
+    int total_spurts() const;
+    int exchange_period() const { return period; }
+    void enqueue_spurt();                       // `period` iterations of every chain (asynchronous)
+    void exchange();                            // the Metropolis swap test of one adjacent pair (waits for the device)
+    LODscores* finish();                        // the cold chain's table
+    LODscores* cold_result() { return chains[0]->get_result(); }
     const std::vector<int>& get_swap_success() const { return swap_success; }
     const std::vector<int>& get_swap_failure() const { return swap_failure; }
+};
+
+// One device's share of a `-R` job (job.cc): the replicates placed on this device, plain chains or MC3 ladders,
+// all resident at once and advanced in turn; results() merges their tables as LODscores::merge_results does.
+class ReplicateJob {
+    Pedigree* ped;
+    GeneticMap* map;
+    PeelSequenceGenerator* psg;
+    struct mcmc_options options;
+    std::vector<int> ids;
+    bool ladder;
+    std::vector<GPUMarkovChain*> chains;
+    std::vector<DescentGraph*> dgs;
+    std::vector<Mc3*> ladders;
+    int next_iteration;
+ public:
+    ReplicateJob(Pedigree* ped, GeneticMap* map, PeelSequenceGenerator* psg, struct mcmc_options options,
+                 const std::vector<int>& replicate_ids);
+    ~ReplicateJob();
+    int total_iterations() const;
+    int done_iterations() const { return next_iteration; }
+    int advance(int n);
+    LODscores* results(std::vector<int>* swap_success, std::vector<int>* swap_failure);
 };
 
 }  // namespace swiftlink

@@ -768,7 +768,9 @@ static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
 // to wait for eight SMs to drain.
 static void ms_launch_chain(slk_chain* c, const SlkMsLaunch& L) {
     static const char* force = getenv("SLK_MS_CHAIN_EXCLUSIVE");     // tuning aid: "0" / "1"
-    const bool exclusive = force ? force[0] == '1' : g_ms_chains <= 1;
+    // (with two likelihood launches in flight the kernel must become resident next to the running one: it is what
+    // releases the next launch)
+    const bool exclusive = force ? force[0] == '1' : (g_ms_chains <= 1 && L.run_ahead != 2);
     const size_t smem = exclusive ? (size_t)(slk::kSmemPerBlockMax - 4096) : (size_t) c->plan->ms_chain_smem;
     ms_launch_overlapped((const void*) slk_ms_chain_kernel, SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, smem, c->stream, L);
 }
@@ -787,14 +789,19 @@ static int g_ms_tl_slot = 0;
 
 // (q0, q1): the meioses of the chain kernel that precedes this launch on the stream (the previous pair of the
 // sweep; q1 < 0: a single step), q0 < 0 when the predecessor is anything else
-static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -1, int q1 = -1) {
+// run_ahead 2: (r0, r1) are the meioses of the pair before that one (< 0: none): the chain kernel of (q0, q1) and the
+// likelihood launch of (q0, q1), which refreshes the label pairs (r0, r1) invalidated, may both still be running
+static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -1, int q1 = -1, int run_ahead = 1, int r0 = -1, int r1 = -1) {
     const SlkDevPlan& d = c->plan->dev;
     SlkMsLaunch L = ms_launch(c);
     L.iteration = iteration;
     L.prev_n = -1;
+    L.run_ahead = run_ahead;
     if(q0 >= 0) {
-        L.prev_n = 1; L.prev_person[0] = d.F + q0 / 2; L.prev_parent[0] = q0 % 2;
-        if(q1 >= 0) { L.prev_n = 2; L.prev_person[1] = d.F + q1 / 2; L.prev_parent[1] = q1 % 2; }
+        const int prev[4] = { q0, q1, run_ahead == 2 ? r0 : -1, run_ahead == 2 ? r1 : -1 };
+        L.prev_n = 0;
+        for(int j = 0; j < 4; ++j)
+            if(prev[j] >= 0) { L.prev_person[L.prev_n] = d.F + prev[j] / 2; L.prev_parent[L.prev_n] = prev[j] % 2; ++L.prev_n; }
     }
     const int p0 = d.F + m0 / 2, a0 = m0 % 2;
     L.set_n[0] = 1; L.set_person[0][0] = p0; L.set_parent[0][0] = a0;
@@ -909,11 +916,13 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     const int tl_words = 8 * (n + 2) + 2 * 3 * c->plan->ms_grid;
     if(timeline) { CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * tl_words)); CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * tl_words, c->stream)); }
     g_ms_timeline = tl;
-    int q0 = -1, q1 = -1;
+    static const int run_ahead = getenv("SLK_MS_RUN_AHEAD") ? atoi(getenv("SLK_MS_RUN_AHEAD")) : 2;   // tuning aid: 1 = one launch in flight
+    int q0 = -1, q1 = -1, r0 = -1, r1 = -1;
     for(int j = 0; j < n && rc == SLK_OK; j += 2) {
         const int m0 = order[j], m1 = j + 1 < n ? order[j + 1] : -1;
         g_ms_tl_slot = j;
-        rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1);
+        rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1, (no_overlap || run_ahead != 2) ? 1 : 2, r0, r1);
+        r0 = q0; r1 = q1;
         q0 = m0; q1 = m1;
     }
     g_ms_timeline = 0;

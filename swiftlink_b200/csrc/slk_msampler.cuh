@@ -84,9 +84,10 @@ struct SlkMsLaunch {
     // likelihood kernel: hypotheses.  set s flips set_n[s] indicators; a set with no flip writes lncur.
     int nsets;
     int refresh_set;             // step kernel: the hypothesis set whose threads also bring te up to date (the lighter one)
-    int prev_n;                  // step kernel: the predecessor on the stream is the chain kernel of these prev_n (0-2)
-    int prev_person[2];          //   meioses (-1: the predecessor is something else, nothing may run ahead of it)
-    int prev_parent[2];
+    int prev_n;                  // step kernel: the chain kernels that may still be running when this launch starts sample
+    int prev_person[4];          //   these prev_n (0-4) meioses (-1: the predecessor is something else, nothing may run
+    int prev_parent[4];          //   ahead of it)
+    int run_ahead;               // 2: two likelihood launches in flight (see slk_ms_step_kernel); else one
     int set_n[SLK_MS_MAXSETS];
     int set_person[SLK_MS_MAXSETS][2];
     int set_parent[SLK_MS_MAXSETS][2];
@@ -835,7 +836,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     MS_TL(0);
     if(L.timeline && L.tl_cta_off > 0 && t == 0) L.timeline[L.tl_cta_off + 2 * blockIdx.x] = ms_globaltimer() & 0xffffffffffffull;
 
-    ms_launch_dependents();
+    // Run-ahead 1: the successor (this pair's chain kernel) may become resident at once.  Run-ahead 2: only after this
+    // launch's own predecessor has completed (in sync()), which is what bounds the pipeline to two likelihood launches.
+    const bool deep = L.run_ahead == 2;
+    if(!deep) ms_launch_dependents();
     int16_t* s_mo = (int16_t*) ms_smem;                    // [N]
     int16_t* s_fa = s_mo + N;                              // [N]
     uint16_t* s_typed = (uint16_t*)(s_fa + N);             // [nt]
@@ -931,13 +935,14 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         const MsLane& ln; uint32_t o_hm; const uint8_t* row; const int16_t* s_mo; const int16_t* s_fa; const uint16_t* s_typed;
         const uint16_t* s_ord; int n0;
         const void* te; const uint8_t* obs; const uint32_t* stale; uint8_t* bits_out; int M, l, F, nt, W, p0, a0, p1, a1;
-        bool synced; unsigned long long* tl;
+        bool synced; unsigned long long* tl; bool deep;
         uint32_t hw_next;
         uint32_t qk[4], qp[4], qg[4];    // the next four people of the order: index, label pair, genotype (loads in flight)
         __device__ __forceinline__ int iterations(int n) const { return n; }
         __device__ __forceinline__ void sync() {
             if(tl) tl[2] = ms_globaltimer();
             ms_wait_for_predecessor();
+            if(deep) ms_launch_dependents();
             if(tl) tl[3] = ms_globaltimer();
             synced = true;
             for(int w = 0; w < W; ++w) {
@@ -970,6 +975,10 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         __device__ __forceinline__ int next(int it, uint32_t& g, uint32_t& mat, uint32_t& pat, bool& single) {
             if(it == n0) {                               // uniform: every lane of the launch is at the same iteration
                 sync();
+                // run-ahead 2: the previous likelihood launch was still refreshing the label pairs of the people
+                // visited from here on when the queue read them ahead: read them again (after the wait, which makes
+                // the completed grids' writes visible to this one)
+                if(deep) { for(int j = 0; j < 4; ++j) fetch(it + j, j); }
                 hw_next = ms_ld32(ln.a32(o_hm, (qk[0] & 0x7fffu) >> 4));
             }
             // Four-deep queues in registers (shifted, so every index is a compile-time constant; a ring indexed by
@@ -996,7 +1005,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     } src = { ln, o_hm, row, s_mo, s_fa, s_typed, s_ord, *s_n0, L.te, L.ms.obsT + l, L.stale,
               (p0 >= 0 && set < 2) ? L.bits + (size_t) set * M + l : (uint8_t*) 0,
               M, l, F, nt, W, p0, a0, p1, a1, false,
-              (L.timeline && blockIdx.x == 0 && t == 0) ? L.timeline + 8 * L.tl_slot : (unsigned long long*) 0,
+              (L.timeline && blockIdx.x == 0 && t == 0) ? L.timeline + 8 * L.tl_slot : (unsigned long long*) 0, deep,
               0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
     const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
     // predecessor unknown (the reset kernel, which writes te, or anything else): nothing is read ahead of it
@@ -1112,6 +1121,9 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     if(tr) tr[0] = clock64();
     const int W = L.ms.W;
     MS_TL(0);
+    // Run-ahead 2: the next pair's likelihood launch may start now, next to the launch this kernel waits for: it
+    // visits nobody this kernel's or the previous chain kernel's meioses can affect before this kernel has completed.
+    if(L.run_ahead == 2) ms_launch_dependents();
     // everything that does not depend on the likelihoods is done while the likelihood kernel is still running
     for(int i = cta_lo + t; i < cta_hi; i += T) {
         s_theta[i - cta_lo] = i > 0 ? L.theta[i - 1] : 0.5;
@@ -1121,9 +1133,9 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
     MS_TL(1);
     ms_wait_for_predecessor();                             // ln L of the hypotheses, the stale masks' last readers
     MS_TL(2);
-    // only now: the next step kernel reads te while it waits for this kernel, and the step kernel that has just
-    // completed was still refreshing te
-    ms_launch_dependents();
+    // run-ahead 1, only now: the next step kernel reads te while it waits for this kernel, and the step kernel that has
+    // just completed was still refreshing te (run-ahead 2 keeps the refreshed entries out of that launch's first phase)
+    if(L.run_ahead != 2) ms_launch_dependents();
     for(int i = cta_lo + t; i < cta_hi; i += T) {
         s_lncur[i - cta_lo] = L.lncur[i]; s_changed[i - cta_lo] = 0;
         for(int w = 0; w < W; ++w) L.stale[(size_t) i * W + w] = 0u;       // the likelihood launch brought te up to date

@@ -212,6 +212,15 @@ SLK_DEV uint32_t slk_phased_trait(bool sex_linked, bool male, uint32_t m, uint32
     return pa ? SLK_UA : SLK_UU;
 }
 
+// the four values of slk_phased_trait(m, f, i, j), (i, j) = (0,0), (0,1), (1,0), (1,1), packed two bits each: one
+// byte per (m, f), looked up in four 32-bit constants (byte f of word m) generated from the function above
+SLK_DEV uint32_t slk_phased_trait4(bool sex_linked, bool male, uint32_t m, uint32_t f) {
+    uint32_t w;
+    if(sex_linked && male) w = (m == 0u) ? 0x00000000u : (m == 1u) ? 0x55555555u : (m == 2u) ? 0x05050505u : 0x50505050u;
+    else                   w = (m == 0u) ? 0xcc33ff00u : (m == 1u) ? 0x669955aau : (m == 2u) ? 0xc639f50au : 0x6c935fa0u;
+    return (w >> (8u * f)) & 0xffu;
+}
+
 // trait_rfunction.cc:106-127: sum, in (i, j) order, of the recombination weights of the
 // transmitted-allele choices that produce the kid's genotype.  The choices factorise: the kid's
 // genotype fixes whether the maternal (paternal) allele must be the A allele, and the parent's
@@ -304,7 +313,6 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
     const uint32_t cell = (lmw_hi == slk_full_lmw(ch)) ? (row << 2) : slk_decode_row(row, ol.lmw, c, pg.glist);
     const uint32_t* pw = rec + SLK_REC_HEADER + ((c + 1) >> 1) + (TRAIT ? 2 : 0);
     const uint32_t* kw = pw + SLK_REC_PREV * nprev;
-    const bool perm = TRAIT && type == SLK_CHILD_PEEL;
 
     double tc[4];
     slk_load_prior<TRAIT>(pg, tm, peel, tc);
@@ -318,29 +326,19 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
     // digit value of sorted cutset position `pos` in slot s of this thread
 #define SLK_DIG(pos, s) (((pos) == 0u) ? (s0 + (uint32_t)(s)) : ((cell >> (2u * (pos))) & 3u))
 
+    // t[s][v]: the product chain of slot s and peel-node GENOTYPE v.  In a trait child peel the reference's four chains
+    // are the (maternal, paternal) transmitted-allele choices (trait_rfunction.cc:44-66); a choice's chain depends on
+    // the choice only through the kid's genotype it implies, factor by factor, so the four genotype chains are run
+    // instead (same factors, same order: bit-identical values) and the choices pick theirs at the end.
     double t[NS][4];
-    uint32_t gvp[NS];
     // ---- initial factor: prior of the peel-node genotype (x transmission for a sampler child peel)
     const uint32_t k0 = (type == SLK_CHILD_PEEL) ? kw[0] : 0u;
     const uint32_t mpos0 = (k0 >> 20) & 15u, fpos0 = (k0 >> 24) & 15u;
     const bool male0 = (k0 >> 28) & 1u;
 #pragma unroll
     for(int s = 0; s < NS; ++s) {
-        gvp[s] = 0xE4u;
-        if(perm) {
-            // variants are the four (maternal, paternal) transmitted-allele choices (trait_rfunction.cc:44-66)
-            const uint32_t m = SLK_DIG(mpos0, s), f = SLK_DIG(fpos0, s);
-            uint32_t g = 0;
 #pragma unroll
-            for(uint32_t ij = 0; ij < 4; ++ij) g |= slk_phased_trait(sex_linked, male0, m, f, ij >> 1, ij & 1u) << (2 * ij);
-            gvp[s] = g;
-#pragma unroll
-            for(int v = 0; v < 4; ++v) t[s][v] = slk_sel4(tc, (g >> (2 * v)) & 3u);
-        }
-        else {
-#pragma unroll
-            for(int v = 0; v < 4; ++v) t[s][v] = tc[v];
-        }
+        for(int v = 0; v < 4; ++v) t[s][v] = tc[v];
     }
     if(!TRAIT && type == SLK_CHILD_PEEL) {
         // T[m][f][v] = P(maternal allele of v | m) * P(paternal allele of v | f) (sampler_rfunction.cc:412-415); the
@@ -379,7 +377,7 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
                 double x[4];
                 slk_ld4(p + 4 * s, x);
 #pragma unroll
-                for(int v = 0; v < 4; ++v) t[s][v] *= perm ? slk_sel4(x, (gvp[s] >> (2 * v)) & 3u) : x[v];
+                for(int v = 0; v < 4; ++v) t[s][v] *= x[v];
             }
         }
         else if(kind == SLK_KEY_V) {
@@ -388,7 +386,7 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
 #pragma unroll
             for(int s = 0; s < NS; ++s)
 #pragma unroll
-                for(int v = 0; v < 4; ++v) t[s][v] *= perm ? slk_sel4(x, (gvp[s] >> (2 * v)) & 3u) : x[v];
+                for(int v = 0; v < 4; ++v) t[s][v] *= x[v];
         }
         else if(kind == SLK_KEY_S) {
             double x[4];
@@ -410,12 +408,18 @@ SLK_DEV void slk_forward_tile(const SlkEnv& E, const SlkProgView& pg, const SlkT
 
     // ---- transmission to the children / recombination weights
     if(TRAIT && type == SLK_CHILD_PEEL) {
+        // choice (i, j) takes the chain of the genotype it implies, times its recombination weight
         double w[4];
         slk_ld4(tm.tables + 4 * (peel - E.F), w);
 #pragma unroll
-        for(int s = 0; s < NS; ++s)
+        for(int s = 0; s < NS; ++s) {
+            const uint32_t g4 = slk_phased_trait4(sex_linked, male0, SLK_DIG(mpos0, s), SLK_DIG(fpos0, s));
+            double u[4];
 #pragma unroll
-            for(int v = 0; v < 4; ++v) t[s][v] *= w[v];
+            for(int v = 0; v < 4; ++v) u[v] = slk_sel4(t[s], (g4 >> (2 * v)) & 3u) * w[v];
+#pragma unroll
+            for(int v = 0; v < 4; ++v) t[s][v] = u[v];
+        }
     }
     else if(type == SLK_PARENT_PEEL) {
         // child_prob = prod_k T_k (sampler_rfunction.cc:258-279 / trait_rfunction.cc:91-129).  When no child's own or

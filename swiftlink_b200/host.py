@@ -12,6 +12,7 @@ SYMBOLS = [
     "slk_host_disease_model", "slk_host_elim_masks", "slk_host_build_peel", "slk_host_set_peel",
     "slk_host_num_ops", "slk_host_peel_cost", "slk_host_op_info", "slk_host_random_descentgraph",
     "slk_host_problem", "slk_host_write_results", "slk_host_run_chain", "slk_host_run_replicates", "slk_host_run_mc3", "slk_host_mc3_temperature", "slk_host_elod",
+    "slk_host_job_create", "slk_host_job_advance", "slk_host_job_results", "slk_host_job_destroy",
 ]
 
 
@@ -180,6 +181,44 @@ class Host(object):
         if rc != 0:
             raise capi.SlkError(rc, self.L.slk_last_error().decode())
         return dict(lod=lod.reshape(self.M - 1, self.nlod), swap_success=ok[:n_chains - 1], swap_failure=bad[:n_chains - 1])
+
+
+class Job(object):
+    """One device's share of a `-R` job (swiftlink::ReplicateJob, csrc/host/job.cc): the given replicates -- plain chains or
+    MC3 ladders of `mc3_chains` chains -- resident on `device` at once.  advance(n) runs the next n iterations of every
+    replicate; results() returns the RAW merged log-sum accumulators, the count of scoring passes, ln P(T) and the summed
+    swap counters, ready for the cross-rank merge of swiftlink_b200.dist."""
+
+    def __init__(self, host, replicate_ids, burnin, iterations, scoring_period=10, seed=1, device=0, lsampler_prob=0.5,
+                 si_iterations=10, mc3_chains=1, exchange_period=10, temperatures=None):
+        self.host, self.L = host, host.L
+        self.L.slk_host_job_create.restype = C.c_void_p
+        ids = np.ascontiguousarray(replicate_ids, np.int32)
+        t = None if temperatures is None else np.ascontiguousarray(temperatures, np.float64)
+        self.mc3_chains = max(int(mc3_chains), 1)
+        h = self.L.slk_host_job_create(host.h, int(device), C.c_uint64(seed), _ip(ids), int(len(ids)), int(mc3_chains),
+                                       int(exchange_period), _dp(t) if t is not None else None, int(burnin), int(iterations),
+                                       int(scoring_period), C.c_double(lsampler_prob), int(si_iterations))
+        if not h:
+            raise RuntimeError("slk_host_job_create failed")
+        self.h = C.c_void_p(h)
+
+    def advance(self, n):
+        return int(self.L.slk_host_job_advance(self.h, int(n)))
+
+    def results(self):
+        n = (self.host.M - 1) * self.host.nlod
+        raw = np.zeros(n); cnt = C.c_int32(0); tp = C.c_double(0)
+        ok = np.zeros(self.mc3_chains, np.int32); bad = np.zeros(self.mc3_chains, np.int32)
+        rc = self.L.slk_host_job_results(self.h, _dp(raw), C.byref(cnt), C.byref(tp), _ip(ok), _ip(bad), int(self.mc3_chains))
+        if rc != 0:
+            raise capi.SlkError(rc, self.L.slk_last_error().decode())
+        return dict(raw=raw, count=int(cnt.value), trait_prob=float(tp.value), swap_success=ok, swap_failure=bad)
+
+    def close(self):
+        if self.h:
+            self.L.slk_host_job_destroy(self.h)
+            self.h = None
 
 
 def elod(pedfile, frequency=1e-4, penetrance=(0.0, 0.0, 1.0), separation=0.05, replicates=1000000, sex_linked=False,

@@ -285,3 +285,75 @@ def test_msampler_fallback_paths(env):
                          timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "passed" in out.stdout
+
+
+def _bench_problem(markers, tag):
+    import sys
+    from common import ROOT
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    from oracle import orcapi
+    from swiftlink_b200 import capi, host as H
+    hst = H.Host(*bench.workload_files(markers, tag), lodscores=bench.N_LOD)
+    assert hst.set_peel_by_names(bench.load_order()["order"])
+    d = hst.problem_dict()
+    return hst, orcapi.Problem(d), capi.Plan(d)
+
+
+def _check_lod_sample(ch, orc, dg, intervals):
+    """the production scoring kernel (slk_lodscore_kernel<T, CTA, false>, the instantiation bench.py times) over ALL
+    positions, compared with the oracle's Peeler::process at a sample of intervals"""
+    ch.lodscore_init()
+    ch.lodscore_accumulate()
+    raw, count = ch.lodscore_read()
+    assert count == 1
+    for l in intervals:
+        prob = orc.lod_interval(dg, int(l))[1]
+        assert np.abs(raw[l] - prob).max() <= 1e-12 * np.abs(prob).max(), l
+    ch.lodscore_accumulate()                           # LODscores::add: log_sum of the same value twice = value + ln 2
+    raw2, count = ch.lodscore_read()
+    assert count == 2
+    assert np.abs(raw2 - (raw + np.log(2.0))).max() <= 1e-12 * np.abs(raw).max()
+
+
+def test_bench_pedigree_lod_pass_matches_oracle():
+    """bench pedigree, first 1 500 SNPs: a scoring pass of the hot (non-debug) kernel at the production team geometry
+    against the oracle (1e-12 relative), after L-sweeps of the hot sampler kernel that the oracle reproduces bit for bit"""
+    hst, orc, plan = _bench_problem(1500, "t_lod")
+    ch = capi_chain(plan, 77, 3)
+    ch.sequential_imputation(0, hst.M // 2)
+    ref = ch.dg_download()
+    for it in (1, 2, 3):                              # several L-sweeps at the production geometry
+        assert orc.ls_sweep(ref, 77, 3, it) == 0
+        ch.lsampler_sweep(it)
+        assert (ch.dg_download() == ref).all(), it
+    _check_lod_sample(ch, orc, ref, np.linspace(0, hst.M - 2, 40).astype(int))
+    ch.close(); plan.close(); hst.close()
+
+
+@pytest.mark.slow
+def test_bench_workload_full_size_matches_oracle():
+    """the bench workload itself (200 members x 10 000 SNPs): one M-sweep, two L-sweeps and a scoring pass of the
+    production kernels against the oracle -- graphs bit for bit, ln L(graph) and sampled LOD terms at 1e-12"""
+    hst, orc, plan = _bench_problem(10000, "t_full")
+    ch = capi_chain(plan, 20261017, 0)
+    ch.sequential_imputation(0, hst.M // 2)
+    ref = ch.dg_download()
+    for it, kind in ((1, "M"), (2, "L"), (3, "L")):
+        if kind == "L":
+            assert orc.ls_sweep(ref, 20261017, 0, it) == 0
+            ch.lsampler_sweep(it)
+        else:
+            assert orc.ms_sweep(ref, 20261017, 0, it) == 0
+            ch.msampler_sweep(it)
+        assert (ch.dg_download() == ref).all(), (it, kind)
+    want = orc.dg_likelihood(ref)
+    assert abs(ch.dg_likelihood() - want) <= TOL * abs(want)
+    _check_lod_sample(ch, orc, ref, np.linspace(0, hst.M - 2, 24).astype(int))
+    ch.close(); plan.close(); hst.close()
+
+
+def capi_chain(plan, seed, chain_id):
+    from swiftlink_b200 import capi
+    return capi.Chain(plan, seed=seed, chain_id=chain_id)
