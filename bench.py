@@ -798,15 +798,120 @@ def run_small_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: the synthetic pedigree, -R 8 replicates + MC3 coupled chains sharded across 1/2/4/8 GPUs
+# ---------------------------------------------------------------------------------------------
+
+C4_REPLICATES, C4_CHAINS, C4_EXCHANGE, C4_STEP_ITERATIONS, C4_SCORING_PERIOD = 8, 2, 10, 20, 10
+
+
+def run_c4(args, rank, world, local_rank):
+    """A FIXED job -- 8 replicates, each a Metropolis-coupled ladder of 2 chains (16 chains) -- over `world` GPUs: strong
+    scaling.  Replicate r runs on rank r mod world (swiftlink::ReplicateJob: all of a rank's ladders resident at once,
+    swaps are pointer exchanges on the ladder's GPU); every timed step ends with the merge of the per-rank LOD
+    accumulators and swap counters over NCCL (swiftlink_b200/dist.py), inside the timed region."""
+    import torch
+    from swiftlink_b200 import build, capi, dist as sdist, host as H
+    build.build()
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    paths = workload_files(N_MARKERS, "c4r%d" % rank)
+    hst = H.Host(*paths, lodscores=N_LOD)
+    assert hst.set_peel_by_names(load_order()["order"]), "committed elimination order rejected"
+    ids = sdist.chain_placement(C4_REPLICATES, world)[rank]
+    total_steps = args.warmup + args.steps
+    t0 = time.perf_counter()
+    with quiet_stdout():
+        job = H.Job(hst, ids, 0, total_steps * C4_STEP_ITERATIONS, scoring_period=C4_SCORING_PERIOD, seed=20261017, device=local_rank,
+                    lsampler_prob=LSAMPLER_PROB, si_iterations=1, mc3_chains=C4_CHAINS, exchange_period=C4_EXCHANGE)
+    t_setup = time.perf_counter() - t0
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    merge_ms = []
+
+    def step():
+        n = job.advance(C4_STEP_ITERATIONS) if ids else C4_STEP_ITERATIONS
+        assert n == C4_STEP_ITERATIONS
+        r = job.results()                                  # waits for the rank's chains, reads the raw accumulators
+        t1 = time.perf_counter()
+        raw, count = sdist.merge_lod(torch.from_numpy(r["raw"]).to(dev), r["count"])
+        ok, bad = sdist.merge_swap_stats(r["swap_success"], r["swap_failure"], device=dev)
+        torch.cuda.synchronize()
+        merge_ms.append(1e3 * (time.perf_counter() - t1))
+        return raw, count, ok, bad, r["trait_prob"]
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    merge_ms[:] = []
+    secs = 0.0
+    out = None
+    for _ in range(args.steps):
+        barrier()
+        ta = time.perf_counter()
+        out = step()
+        barrier()
+        secs += time.perf_counter() - ta
+    clock_info = clocks.stop()
+    if dist is not None:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    raw, count, ok, bad, tp = out
+    value = C4_REPLICATES * C4_STEP_ITERATIONS * args.steps / secs
+    lod = sdist.normalise(raw, count, tp)
+    n_me = 281
+    launches_per_it = 0.5 * 2 + 0.5 * (1 + 2 * ((n_me + 1) // 2))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 200-member consanguineous pedigree, 10k SNPs: a fixed job of %d replicates, each an MC3 ladder "
+                                   "of %d chains (exchange every %d iterations), default sampler mix, LOD scoring every %dth iteration, "
+                                   "dealt out over the GPUs" % (C4_REPLICATES, C4_CHAINS, C4_EXCHANGE, C4_SCORING_PERIOD),
+                       "step": "%d iterations of every replicate (cold-chain iterations are what `value` counts) + the NCCL merge of the "
+                               "LOD tables and swap counters" % C4_STEP_ITERATIONS,
+                       "replicates": C4_REPLICATES, "chains_per_ladder": C4_CHAINS, "n_members": hst.N, "n_markers": hst.M,
+                       "parallelism": "replicate ladders round-robin over %d GPU(s), %d ladder(s) = %d chains resident per GPU"
+                                      % (world, len(ids), len(ids) * C4_CHAINS),
+                       "l2": "working set of %d chains per GPU exceeds L2" % (len(ids) * C4_CHAINS)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(raw.numel() * 8),
+                    "note": "the job runs through the product API (swiftlink::ReplicateJob via the C ABI); per step the raw LOD "
+                            "accumulators come back to the host and go through the all-reduces"},
+            "gpu_launches": int(args.steps * len(ids) * C4_CHAINS * C4_STEP_ITERATIONS * launches_per_it),
+            "clocks": clock_info,
+            "derived": {"merge_ms_per_step": float(np.mean(merge_ms)), "setup_s": t_setup, "scoring_passes_merged": count,
+                        "swap_success": [int(x) for x in ok.cpu().numpy()], "swap_failure": [int(x) for x in bad.cpu().numpy()],
+                        "lod_max": float(lod.max().item()), "chains_total": C4_REPLICATES * C4_CHAINS}}
+    job.close()
+    hst.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="synth200", choices=["synth200", "east", "loop", "xlinked"],
+    ap.add_argument("--config", default="synth200", choices=["synth200", "east", "loop", "xlinked", "c4"],
                     help="synth200 (default): BASELINE.json configs[2], the configuration the metric is quoted on; "
-                         "east / loop / xlinked: the reference's example pedigrees (configs[0], [1], [4])")
+                         "east / loop / xlinked: the reference's example pedigrees (configs[0], [1], [4]); c4: configs[3], a fixed "
+                         "job of 8 replicates x MC3 ladders over --gpus GPUs (strong scaling, NCCL merges inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0,
                     help="--impl reference: size of the bounded sample one step times (seconds of CPU work, approximately)")
@@ -816,7 +921,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.config != "synth200":
+    if args.config == "c4":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference's MC3 driver is unreachable (linkage_program.cc:169-170) "
+                                                                       "and its -R loop is timed by the synth200 configuration"}))
+        else:
+            run_c4(args, rank, world, local_rank)
+    elif args.config != "synth200":
         if args.impl == "reference":
             run_small_reference(args, rank)
         else:

@@ -70,13 +70,16 @@ def main():
     dg = r.dg_get()
     # the CPU peeler on the same graph (one thread), for the record
     t_cpu = r.bench_lodpasses(3)
+    # ... and its table: Peeler::process per interval, one pass, normalised as LODscores::get does (lod_score.h:86-88)
+    tp = r.calc_trait_prob()
+    lod_cpu = np.array([(r.lod_interval(l)[1] - tp) / np.log(10.0) for l in range(r.M - 1)])
     lod = np.zeros((r.M - 1) * r.nlod)
     setup = C.c_double(0)
     threads = C.c_int(0)
     secs = float(L.ref_gpu_lod_bench(r.h, int(args.reps), lod.ctypes.data_as(C.POINTER(C.c_double)), C.byref(setup), C.byref(threads)))
-    np.savez(args.out, dg=dg, order=order, lod=lod.reshape(r.M - 1, r.nlod), secs_per_pass=secs, setup_s=setup.value,
+    np.savez(args.out, dg=dg, order=order, lod=lod.reshape(r.M - 1, r.nlod), lod_cpu=lod_cpu, secs_per_pass=secs, setup_s=setup.value,
              block_threads=threads.value, positions=(r.M - 1) * r.nlod, cpu_secs_per_pass_1thread=t_cpu,
-             trait_prob=r.calc_trait_prob(), N=r.N, M=r.M)
+             trait_prob=tp, N=r.N, M=r.M)
     print(json.dumps(dict(case=args.case, secs_per_pass=secs, positions=(r.M - 1) * r.nlod,
                           trait_positions_per_s=(r.M - 1) * r.nlod / secs, setup_s=setup.value, block_threads=threads.value)))
     sys.stdout.flush()

@@ -31,6 +31,13 @@ def test_lod_table_matches_reference_gpu_kernel(case, tmp_path):
     tp = plan.trait_likelihood()
     assert abs(tp - float(ref["trait_prob"])) <= 1e-12 * abs(tp)
     lod = chain.lodscore_normalise(tp).reshape(ref["lod"].shape)
-    scale = max(1.0, float(np.abs(ref["lod"]).max()))
-    assert np.abs(lod - ref["lod"]).max() <= 1e-9 * scale
+    # the reference's CPU peeler on the same graph (computed in the same child process): the parity bar
+    scale = max(1.0, float(np.abs(ref["lod_cpu"]).max()))
+    assert np.abs(lod - ref["lod_cpu"]).max() <= 1e-12 * scale
+    # the reference's GPU kernel against its own CPU peeler: recorded only -- see DESIGN.md section 5 (on east its table
+    # deviates from the CPU path's by up to 1.4 LOD units on the same graph, on loop it agrees; ours equals the CPU path's)
+    dev_gpu = float(np.abs(ref["lod"] - ref["lod_cpu"]).max())
+    print("reference lodscore_kernel vs reference CPU peeler on %s: max |dLOD| = %.3g; slk_lodscore_kernel vs CPU: %.3g"
+          % (case, dev_gpu, float(np.abs(lod - ref["lod_cpu"]).max())))
+    assert np.isfinite(ref["lod"]).all()
     chain.close(); plan.close(); hst.close()
