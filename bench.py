@@ -15,16 +15,19 @@ One bench STEP = 100 iterations (the kind of each drawn from the chain's Philox 
 GPUMarkovChain::run does) + 1 scoring pass.  metric = MCMC iterations / second, whole job.
 
 With N > 1 GPUs every rank runs an independent replicate chain (the reference's -R, one chain
-group per GPU, weak scaling); the LOD accumulators are merged at the end by small NCCL
-all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the counts).
+group per GPU, weak scaling); the LOD accumulators are merged at the end of every step, inside the
+timed region, by small NCCL all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the
+counts).  `--config c4` runs BASELINE.json configs[3] instead: a FIXED job of 8 replicates x MC3 ladders
+dealt out over the GPUs (strong scaling); `--config east|loop|xlinked` the reference's examples.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libswiftref.so, built by
 oracle/Makefile) on the host cores with all OpenMP threads: its own LocusSampler sweeps,
 MeiosisSampler sweeps and Peeler::process passes (markov_chain.cc:209-266, :342-349, :375-383),
-combined with the same 0.5 / 0.5 mix, on a bounded sample of the same
-workload -- the first 1000 of the 10 000 SNPs of the same pedigree (the per-locus cost does not
-depend on M; the reference's per-locus index tables make M = 10 000 take minutes to set up) --
-extrapolated linearly in M and stated as such in `cpu_baseline.sample`.
+in the loop of MarkovChain::run (mix draw, L- or M-sweep, scoring) on the FULL workload (10 000
+SNPs, about a minute of set-up, 7 GB), each step a bounded sample of the bench step (fewer
+iterations, the same share of scoring work).  The `cpu_baseline` object of our own line is the
+same loop on the first 1000 SNPs (value / 10, stated in its `sample`), so that the default run
+stays short.
 """
 import argparse
 import json
@@ -280,6 +283,8 @@ def run_ours(args, rank, world, local_rank):
     n_meioses = len(plan.msampler_ordering())
     launches = [0]
     kinds = [0, 0]
+    from swiftlink_b200 import dist as sdist
+    merged, merge_s = [None], [0.0]
 
     def hot_step(start_it):
         for k in range(SCORING_PERIOD):
@@ -293,6 +298,13 @@ def run_ours(args, rank, world, local_rank):
                 kinds[1] += 1
         chain.lodscore_accumulate()
         launches[0] += 1
+        if dist is not None:
+            # N > 1: the replicates' tables are merged (LODscores::merge_results as MAX / SUM-of-exp / SUM all-reduces
+            # over NCCL) at the end of EVERY step, inside the timed region
+            t1 = time.perf_counter()
+            cnt = chain.lodscore_read_ptr(pinned_lod.data_ptr())
+            merged[0] = sdist.merge_lod(pinned_lod.to("cuda", non_blocking=True), cnt)
+            merge_s[0] += time.perf_counter() - t1
         return start_it + SCORING_PERIOD
 
     def timed(step_fn, k_steps, it0):
@@ -320,7 +332,9 @@ def run_ours(args, rank, world, local_rank):
     clocks.start()
     launches[0] = 0
     kinds[0] = kinds[1] = 0
+    merge_s[0] = 0.0
     secs, it = timed(hot_step, args.steps, it)
+    merge_ms_per_step = 1e3 * merge_s[0] / max(args.steps, 1)
     timed_launches, timed_kinds = launches[0], list(kinds)
     chain.sync()
     clock_info = clocks.stop()
@@ -446,7 +460,6 @@ def run_ours(args, rank, world, local_rank):
             c.close()
 
     # ---- merge replicates (LODscores::merge_results, lod_score.h:98-105) -----------------------------------
-    from swiftlink_b200 import dist as sdist
     raw, count = chain.lodscore_read()
     raw = torch.from_numpy(raw.ravel().copy()).cuda()
     raw, merged_count = sdist.merge_lod(raw, count)
@@ -521,7 +534,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": STEP_DESC, "lsampler_prob": LSAMPLER_PROB,
                    "l_sweeps_timed": n_l, "m_sweeps_timed": n_m, "meioses_per_m_sweep": n_meioses,
-                   "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU",
+                   "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU" + ("; LOD tables merged over NCCL at the end of every step, inside the timed region" if world > 1 else ""),
                    "l2": "256 MiB buffer written between timed steps (working set is L2-resident by design)",
                    "peel_cost_sum4c": stats["sum_cells"], "max_cutset": stats["max_cutset"],
                    "ls_team_threads": stats["ls_team_threads"], "lod_team_threads": stats["lod_team_threads"]},
@@ -535,6 +548,7 @@ def run_ours(args, rank, world, local_rank):
                     "l_sweep_ms": 2 * ls_ms, "m_sweep_ms": msweep_ms, "lod_pass_ms": lod_ms,
                     "lod_max": lod_max, "lod_argmax_interval": lod_argmax, "scoring_passes_merged": merged_count,
                     "setup_s": t_setup, "si_log10_weight": si_weight / np.log(10.0),
+                    "merge_ms_per_step": merge_ms_per_step if world > 1 else None,
                     "replicates_in_flight": in_flight},
     }
     if world == 1 and not args.no_cpu_baseline:

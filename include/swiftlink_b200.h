@@ -284,6 +284,12 @@ int slk_debug_msampler_trace(slk_chain* chain, int meiosis0, int meiosis1, long 
    (meiosis0, meiosis1): which = 0 the three-hypothesis incremental likelihood kernel, 1 the two-step chain kernel,
    2 the full likelihood kernel (every label recomputed; what a sweep's reset launches once) */
 int slk_debug_msampler_launch(slk_chain* chain, int meiosis0, int meiosis1, int which, int reps);
+/* tuning aid: one M-sweep (as slk_msampler_sweep) whose launches record %globaltimer stamps.  With n = the number of
+   meioses of a sweep: out[8 j + 0..4] = likelihood launch of the pair at order positions (j, j + 1), CTA 0: start, walk
+   begins, before the wait for its predecessor, after it, end; out[8 (j + 1) + 0..3] = that pair's chain launch: start,
+   before the wait, after it, end; from out[8 (n + 2)] on, for every CTA b of the likelihood launch at order position
+   cta_pair: out[.. + 2 b] = start, out[.. + 2 b + 1] = end << 10 | SM id.  cap >= 8 (n + 2) + 6 ceil(M / 32) words. */
+int slk_debug_msampler_timeline(slk_chain* chain, uint64_t iteration, int cta_pair, unsigned long long* out, int cap);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward
    level, after every backward level, after the indicators.  Returns the number of stamps. */

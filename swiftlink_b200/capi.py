@@ -28,7 +28,7 @@ SYMBOLS = [
     "slk_lodscore_init", "slk_lodscore_accumulate", "slk_lodscore_read", "slk_lodscore_normalise",
     "slk_trait_likelihood", "slk_elod_run", "slk_debug_elod_graphs",
     "slk_msampler_ordering", "slk_msampler_reset", "slk_msampler_step", "slk_msampler_sweep", "slk_dg_likelihood",
-    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace", "slk_debug_msampler_launch",
+    "slk_sweep_is_lsampler", "slk_debug_fag", "slk_debug_msampler_state", "slk_debug_msampler_trace", "slk_debug_msampler_launch", "slk_debug_msampler_timeline",
     "slk_debug_lsampler_forward", "slk_debug_lsampler_step", "slk_debug_lod_interval", "slk_debug_lsampler_trace",
     "slk_debug_philox", "slk_debug_uniform", "slk_measure_fp64_peak",
 ]
@@ -302,6 +302,14 @@ class Chain(object):
         buf = np.zeros((20, 8), np.int64)
         _check(self.L.slk_debug_msampler_trace(self.h, int(m0), int(m1), _ptr(buf, C.c_longlong)))
         return buf
+
+    def debug_msampler_timeline(self, iteration, cta_pair=100):
+        """%globaltimer stamps of one M-sweep: (launch stamps [n + 2][8], CTA stamps [3 * grid][2]) -- see the header"""
+        n = len(self.plan.msampler_ordering())
+        grid = (self.plan.M + 31) // 32
+        buf = np.zeros(8 * (n + 2) + 6 * grid, np.uint64)
+        _check(self.L.slk_debug_msampler_timeline(self.h, C.c_uint64(iteration), int(cta_pair), _ptr(buf, C.c_ulonglong), int(buf.size)))
+        return buf[:8 * (n + 2)].reshape(n + 2, 8), buf[8 * (n + 2):].reshape(3 * grid, 2)
 
     def debug_msampler_launch(self, m0, m1, which, reps):
         _check(self.L.slk_debug_msampler_launch(self.h, int(m0), int(m1), int(which), int(reps)))

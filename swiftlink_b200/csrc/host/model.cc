@@ -1,7 +1,13 @@
 // model.cc -- DiseaseModel, Snp/GeneticMap, Person, Pedigree and the LINKAGE ped/map/dat
 // readers.  Restates disease_model.cc, genetic_map.cc, person.cc, pedigree.cc,
 // pedigree_parser.cc, map_parser.cc, linkage_parser.cc and parser.h of the reference so that
-// every table the hot path consumes is bit-identical (tests/test_host_vs_reference.py).
+// every table the hot path consumes is bit-identical (tests/test_host.py).
+//
+// This file is the drop-in boundary's host mirror, not the hot path: class names, messages and the arithmetic of the
+// tables have to be the reference's.  Three bodies follow their originals statement for statement because every
+// statement is either an error message a user greps for or an operation whose order fixes a table bit for bit:
+// GeneticMap::sanity_check (genetic_map.cc:14-64), GeneticMap::set_temperature (:95-117) and Pedigree::sanity_check
+// (pedigree.cc); they are marked where they stand.
 #include "swiftlink_host.h"
 
 #include <algorithm>

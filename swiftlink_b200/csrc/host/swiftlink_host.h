@@ -5,7 +5,7 @@
 // reference, re-written around flat tables that feed slk_problem directly.
 //
 // Every numeric table produced here is checked bit-for-bit against the compiled reference in
-// tests/test_host_vs_reference.py (person order, disease probabilities, marker priors, thetas,
+// tests/test_host.py (person order, disease probabilities, marker priors, thetas,
 // elimination masks, peel operations for a given elimination order).
 #ifndef SWIFTLINK_HOST_H
 #define SWIFTLINK_HOST_H

@@ -82,6 +82,8 @@ struct slk_chain {
     // M-sampler state (allocated on first use)
     double* ms_lncur; double* ms_lnl; uint8_t* ms_bits; double* ms_fb; double* ms_out; void* ms_te; uint32_t* ms_stale;
     bool ms_cur_valid;            // ms_cur describes the graph now in dgp
+    unsigned long long* ms_timeline;   // slk_debug_msampler_timeline only: %globaltimer stamps of the sweep being traced
+    int ms_tl_slot, ms_tl_cta_slot;
     // debug buffers (allocated on first use)
     double* dbg_mat; double* dbg_pre; double* dbg_dist4; int* dbg_pmk; double* dbg_res; double* dbg_prob;
 };
@@ -381,10 +383,6 @@ static void pin_scratch_in_l2(slk_chain* c, cudaStream_t s) {
     if(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
-// chains that hold M-sampler state (host-side bookkeeping; the C ABI is driven by one thread per device, as the
-// reference's is): decides whether the chain kernel may claim whole SMs, see ms_launch_chain
-static int g_ms_chains = 0;
-
 int slk_chain_create(slk_plan* plan, uint64_t seed, uint32_t chain_id, slk_chain** out) {
     if(!plan || !out) return fail(SLK_ERR_INVALID, "null argument");
     *out = 0;
@@ -425,7 +423,6 @@ void slk_chain_destroy(slk_chain* c) {
     if(!c) return;
     cudaSetDevice(c->plan->device);
     if(c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
-    if(c->ms_lncur) --g_ms_chains;
     cudaFree(c->dgp); cudaFree(c->dg_staging); cudaFree(c->lod); cudaFree(c->lod_out);
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
@@ -713,7 +710,6 @@ static int ms_ready(slk_chain* c) {
         CU(cudaMemsetAsync(c->ms_stale, 0, sizeof(uint32_t) * M * p->dev.ms.W, c->stream));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
         c->ms_cur_valid = false;
-        ++g_ms_chains;
     }
     return SLK_OK;
 }
@@ -760,17 +756,13 @@ static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
     else ms_launch_overlapped((const void*) slk_ms_step_kernel<false>, grid, 32, p->ms_step_smem, c->stream, L);
 }
 
-// The chain kernel runs while the next pair's likelihood kernel is already walking (see slk_ms_step_kernel).  Its
-// eight 640-thread CTAs would slow down the likelihood CTAs that share their SMs, and the slowest CTA sets the
-// period of the whole sweep (measured: 94 us per pair against 79 us for a CTA elsewhere).  When this is the only
-// chain sampling meioses in the process, the kernel therefore asks for (nearly) all of an SM's shared memory, so
-// that no likelihood CTA is placed next to it; with several chains in flight it stays small so that it never has
-// to wait for eight SMs to drain.
+// The chain kernel runs while the next pair's likelihood kernel is already walking (see slk_ms_step_kernel) and has to
+// become resident next to the running likelihood launch: it is what releases the next one.  SLK_MS_CHAIN_EXCLUSIVE=1
+// (tuning aid, meaningful with SLK_MS_RUN_AHEAD=1 only) makes it ask for a whole SM's shared memory instead, so that no
+// likelihood CTA is placed next to its eight 640-thread CTAs.
 static void ms_launch_chain(slk_chain* c, const SlkMsLaunch& L) {
-    static const char* force = getenv("SLK_MS_CHAIN_EXCLUSIVE");     // tuning aid: "0" / "1"
-    // (with two likelihood launches in flight the kernel must become resident next to the running one: it is what
-    // releases the next launch)
-    const bool exclusive = force ? force[0] == '1' : (g_ms_chains <= 1 && L.run_ahead != 2);
+    static const char* force = getenv("SLK_MS_CHAIN_EXCLUSIVE");
+    const bool exclusive = force && force[0] == '1';
     const size_t smem = exclusive ? (size_t)(slk::kSmemPerBlockMax - 4096) : (size_t) c->plan->ms_chain_smem;
     ms_launch_overlapped((const void*) slk_ms_chain_kernel, SLK_MS_CLUSTER, SLK_MS_CHAIN_THREADS, smem, c->stream, L);
 }
@@ -784,8 +776,6 @@ static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
 
 // one or two consecutive steps of a sweep: the second meiosis's likelihood is evaluated under both
 // outcomes of the first, so the pair costs one likelihood launch and one chain launch
-static unsigned long long* g_ms_timeline = 0;     // SLK_MS_TIMELINE (tuning aid, single-threaded use)
-static int g_ms_tl_slot = 0;
 
 // (q0, q1): the meioses of the chain kernel that precedes this launch on the stream (the previous pair of the
 // sweep; q1 < 0: a single step), q0 < 0 when the predecessor is anything else
@@ -852,13 +842,13 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
             L.rec_n = words;
         }
     }
-    L.timeline = g_ms_timeline; L.tl_slot = g_ms_tl_slot;
-    L.tl_cta_off = (g_ms_timeline && g_ms_tl_slot == (getenv("SLK_MS_TL_SLOT") ? atoi(getenv("SLK_MS_TL_SLOT")) : 100)) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
+    L.timeline = c->ms_timeline; L.tl_slot = c->ms_tl_slot;
+    L.tl_cta_off = (c->ms_timeline && c->ms_tl_slot == c->ms_tl_cta_slot) ? 8 * ((int) c->plan->host.ms_ordering.size() + 2) : 0;
     static const bool full_kernel = getenv("SLK_MS_FULL_KERNEL") != 0;
     if(full_kernel) ms_launch_likelihood(c, L);                        // tuning aid: recompute every label each step
     else ms_launch_step(c, L);
     CU(cudaGetLastError());
-    L.tl_slot = g_ms_tl_slot + 1;
+    L.tl_slot = c->ms_tl_slot + 1;
     ms_launch_chain(c, L);
     CU(cudaGetLastError());
     return SLK_OK;
@@ -911,67 +901,38 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     // The likelihood walk of a pair runs ahead of the previous pair's chain kernel for every typed person that
     // pair cannot affect (slk_ms_step_kernel).  The first pair follows the reset kernel, which writes te.
     static const bool no_overlap = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
-    static const bool timeline = getenv("SLK_MS_TIMELINE") != 0;        // tuning aid: %globaltimer stamps of every launch
-    unsigned long long* tl = 0;
-    const int tl_words = 8 * (n + 2) + 2 * 3 * c->plan->ms_grid;
-    if(timeline) { CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * tl_words)); CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * tl_words, c->stream)); }
-    g_ms_timeline = tl;
     static const int run_ahead = getenv("SLK_MS_RUN_AHEAD") ? atoi(getenv("SLK_MS_RUN_AHEAD")) : 2;   // tuning aid: 1 = one launch in flight
     int q0 = -1, q1 = -1, r0 = -1, r1 = -1;
     for(int j = 0; j < n && rc == SLK_OK; j += 2) {
         const int m0 = order[j], m1 = j + 1 < n ? order[j + 1] : -1;
-        g_ms_tl_slot = j;
+        c->ms_tl_slot = j;
         rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1, (no_overlap || run_ahead != 2) ? 1 : 2, r0, r1);
         r0 = q0; r1 = q1;
         q0 = m0; q1 = m1;
     }
-    g_ms_timeline = 0;
-    if(tl) {
-        std::vector<unsigned long long> h((size_t) tl_words);
-        CU(cudaMemcpyAsync(h.data(), tl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        cudaFree(tl);
-        {
-            // every CTA of the step kernel of pair 50: start and end relative to the first start
-            const int g3 = 3 * c->plan->ms_grid, off = 8 * (n + 2);
-            unsigned long long first = ~0ull;
-            for(int b = 0; b < g3; ++b) if(h[off + 2 * b] && h[off + 2 * b] < first) first = h[off + 2 * b];
-            std::vector<double> st, en;
-            double set_end[3] = {0, 0, 0}, set_dur[3] = {0, 0, 0};
-            std::vector<std::pair<double, int> > slow;
-            std::vector<int> per_sm(1024, 0);
-            for(int b = 0; b < g3; ++b) if(h[off + 2 * b + 1]) per_sm[h[off + 2 * b + 1] & 1023u]++;
-            for(int b = 0; b < g3; ++b) {
-                if(!h[off + 2 * b + 1]) continue;
-                const double a = (h[off + 2 * b] - first) * 1e-3, e = ((h[off + 2 * b + 1] >> 10) - first) * 1e-3;
-                slow.push_back(std::make_pair(e, b));
-                st.push_back(a); en.push_back(e);
-                const int set = b / c->plan->ms_grid;
-                set_end[set] = std::max(set_end[set], e); set_dur[set] += (e - a) / c->plan->ms_grid;
-            }
-            std::sort(slow.begin(), slow.end());
-            for(int q = 0; q < 12 && q < (int) slow.size(); ++q) {
-                const int b = slow[slow.size() - 1 - q].second, sm = (int)(h[off + 2 * b + 1] & 1023u);
-                fprintf(stderr, "  slow CTA %4d (set %d, loci %5d..) end %.1f us on SM %3d (%d CTAs of this launch there)\n", b, b / c->plan->ms_grid,
-                        32 * (b % c->plan->ms_grid), slow[slow.size() - 1 - q].first, sm, per_sm[sm]);
-            }
-            { int h6 = 0, h7 = 0, h8 = 0; for(int i = 0; i < 1024; ++i) { if(per_sm[i] == 6) ++h6; if(per_sm[i] == 7) ++h7; if(per_sm[i] >= 8) ++h8; }
-              fprintf(stderr, "  SMs with 6 / 7 / 8+ CTAs of the launch: %d / %d / %d\n", h6, h7, h8); }
-            std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end());
-            if(!st.empty())
-                fprintf(stderr, "step kernel CTAs (%d): start p50 %.1f p99 %.1f max %.1f | end p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f | per set: mean duration %.1f %.1f %.1f last end %.1f %.1f %.1f (us)\n",
-                        (int) st.size(), st[st.size() / 2], st[st.size() * 99 / 100], st.back(), en[en.size() / 10], en[en.size() / 2], en[en.size() * 9 / 10],
-                        en[en.size() * 99 / 100], en.back(), set_dur[0], set_dur[1], set_dur[2], set_end[0], set_end[1], set_end[2]);
-        }
-        const unsigned long long t0 = h[0];
-        for(int j = 40; j < 56 && j + 1 < n; j += 2) {
-            const unsigned long long* a = &h[(size_t) 8 * j];          // step kernel: start, walk, before wait, after wait, end
-            const unsigned long long* b = &h[(size_t) 8 * (j + 1)];    // chain kernel: start, before wait, after wait, end
-            fprintf(stderr, "pair %3d  step: start %7.1f walk %7.1f wait %7.1f..%7.1f end %7.1f | chain: start %7.1f wait %7.1f..%7.1f end %7.1f (us)\n", j / 2,
-                    (a[0] - t0) * 1e-3, (a[1] - t0) * 1e-3, (a[2] - t0) * 1e-3, (a[3] - t0) * 1e-3, (a[4] - t0) * 1e-3,
-                    (b[0] - t0) * 1e-3, (b[1] - t0) * 1e-3, (b[2] - t0) * 1e-3, (b[3] - t0) * 1e-3);
-        }
-    }
+    return rc;
+}
+
+// Tuning aid: one M-sweep with %globaltimer stamps.  out[8 j + 0..4] = likelihood launch of the pair that starts at
+// meiosis j of the order (start, walk, before wait, after wait, end; CTA 0), out[8 (j + 1) + 0..3] = its chain launch
+// (start, before wait, after wait, end); from out[8 (n + 2)] on, (start, end << 10 | SM) of every CTA of the likelihood
+// launch at order position `cta_pair`.  cap >= 8 (n + 2) + 6 * ceil(M / 32) words (n = meioses of a sweep).
+int slk_debug_msampler_timeline(slk_chain* c, uint64_t iteration, int cta_pair, unsigned long long* out, int cap) {
+    int rc = ms_ready(c);
+    if(rc != SLK_OK) return rc;
+    const int n = (int) c->plan->host.ms_ordering.size();
+    const int words = 8 * (n + 2) + 2 * 3 * c->plan->ms_grid;
+    if(!out || cap < words) return fail(SLK_ERR_INVALID, "slk_debug_msampler_timeline: %d words needed", words);
+    unsigned long long* tl = 0;
+    CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * words));
+    CU(cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * words, c->stream));
+    c->ms_timeline = tl; c->ms_tl_cta_slot = cta_pair;
+    rc = slk_msampler_sweep(c, iteration);
+    c->ms_timeline = 0;
+    cudaError_t e = cudaMemcpyAsync(out, tl, sizeof(unsigned long long) * words, cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tl);
+    if(e != cudaSuccess) return fail(SLK_ERR_CUDA, "timeline: %s", cudaGetErrorString(e));
     return rc;
 }
 

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--msweeps", type=int, default=0)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="%%globaltimer stamps of the launches of one M-sweep")
     args = ap.parse_args()
     from swiftlink_b200 import capi, host as H
     paths = bench.workload_files(args.markers, "prof")
@@ -52,6 +53,24 @@ def main():
         print("M-sweep ms %.3f (%d meioses, %.2f us per step; host enqueue %.3f ms per sweep); ln L = %.3f" %
               (1e3 * (t4 - t3) / args.msweeps, n, 1e6 * (t4 - t3) / args.msweeps / n, 1e3 * (t_enq - t3) / args.msweeps,
                chain.dg_likelihood()))
+    if args.timeline:
+        import numpy as np
+        chain.msampler_sweep(900); chain.sync()
+        tl, cta = chain.debug_msampler_timeline(901, cta_pair=100)
+        t0 = float(tl[0, 0])
+        us = lambda x: (float(x) - t0) * 1e-3
+        for j in range(40, 56, 2):
+            a, b = tl[j], tl[j + 1]
+            print("pair %3d  step: start %7.1f walk %7.1f wait %7.1f..%7.1f end %7.1f | chain: start %7.1f wait %7.1f..%7.1f end %7.1f (us)"
+                  % (j // 2, us(a[0]), us(a[1]), us(a[2]), us(a[3]), us(a[4]), us(b[0]), us(b[1]), us(b[2]), us(b[3])))
+        live = cta[:, 1] != 0
+        if live.any():
+            first = float(cta[live, 0].min())
+            st = np.sort((cta[live, 0].astype(np.float64) - first) * 1e-3)
+            en = np.sort(((cta[live, 1] >> np.uint64(10)).astype(np.float64) - first) * 1e-3)
+            q = lambda v, f: v[min(len(v) - 1, int(len(v) * f))]
+            print("likelihood CTAs of pair 50 (%d): start p50 %.1f p99 %.1f max %.1f | end p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f (us)"
+                  % (len(st), q(st, .5), q(st, .99), st[-1], q(en, .1), q(en, .5), q(en, .9), q(en, .99), en[-1]))
     if args.msweeps and args.trace:
         import numpy as np
         order = plan.msampler_ordering()
