@@ -224,7 +224,7 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     cta = std::max(team, std::min(cta, max_cta));
     cta = (cta / team) * team;
     pr.cta_threads = cta;
-    const int teams_per_cta = pr.cta_threads / team;
+    int teams_per_cta = pr.cta_threads / team;
 
     // ---- record offsets ----
     int stream_words = 0;
@@ -305,6 +305,9 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     pr.mat_off.assign(nops, 0);
     pr.mat_pad.assign(nops, 0);
     const int budget = kSmemPerBlockMax - pr.prog_smem_bytes;           // one CTA per SM worst case
+    // as many teams as the CTA's shared memory holds (tables alone; the arena prefix takes what is left)
+    while(teams_per_cta > 1 && budget / teams_per_cta < table_bytes) --teams_per_cta;
+    pr.cta_threads = teams_per_cta * team;
     int per_team_budget = budget / teams_per_cta - table_bytes;
     if(per_team_budget < 0) per_team_budget = 0;
     int limit_doubles = per_team_budget / 8;
