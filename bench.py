@@ -476,11 +476,13 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
-            traffic = json.load(f)
-    except (IOError, ValueError):
-        pass
+    for tag in ("r2", "r1"):
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % tag)) as f:
+                traffic = json.load(f)
+            break
+        except (IOError, ValueError):
+            pass
     loci_per_launch = M / 2.0
     ls_flops = stats["flops_ls"] * loci_per_launch
     ls_tflops = ls_flops / (ls_ms * 1e-3) / 1e12
@@ -497,15 +499,30 @@ def run_ours(args, rank, world, local_rank):
     ms_bytes_per_eval = (2 * nf + 2 * n_typed) / 8.0 + 24.0
     ms_evals = 3 * M                                               # three hypotheses per locus per launch
     ms_bytes = ms_bytes_per_eval * ms_evals
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_hz = 1e6 * float(clock_info.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+
+    def issue_bound(kernel, launch_ms):
+        """instruction-issue roofline of a kernel: warp instructions per launch (ncu, smsp__inst_executed.sum of the committed
+        capture of the same launch shape) / live launch time, against 4 issue slots per SM per clock"""
+        n = traffic.get("_warp_inst_per_launch", {}).get(kernel)
+        if not n or not launch_ms:
+            return None
+        peak = 4.0 * sm_count * sm_hz
+        return {"bound": "issue slots", "achieved": n / (launch_ms * 1e-3), "peak": peak, "unit": "warp instructions/s",
+                "frac": n / (launch_ms * 1e-3) / peak, "warp_instructions_per_launch": n,
+                "ncu_issue_active_pct": traffic.get("_issue_active_pct", {}).get(kernel)}
     roofline = {
         "kernel": "slk_ms_step_kernel", "bound": "hbm", "achieved": ms_bytes / (ms_lik_ms * 1e-3) / 1e9, "peak": hbm_peak,
         "unit": "GB/s", "frac": ms_bytes / (ms_lik_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("slk_ms_step_kernel"),
         "traffic_source": traffic.get("_source"),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
         "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": ms_lik_ms, "units_per_launch": ms_evals,
-        "note": "latency-bound integer walk (one dependent chain per thread, 939 warps resident): neither HBM nor a math "
-                "pipe is the limiter; in a sweep the launch overlaps the previous pair's chain kernel (programmatic "
-                "dependent launch), launch_ms is the kernel timed alone; see DESIGN.md section 4",
+        "note": "latency-bound integer walk (one dependent chain per thread, 939 warps per launch): neither HBM nor a math "
+                "pipe is the limiter -- the bound that describes it is `issue` below; in a sweep two of these launches are in "
+                "flight and overlap the chain kernels (programmatic dependent launch), launch_ms is the kernel timed alone; "
+                "see DESIGN.md section 4",
+        "issue": issue_bound("slk_ms_step_kernel", ms_lik_ms),
         "ncu": {"issue_slots_busy_pct": traffic.get("_issue_active_pct", {}), "fp64_pipe_busy_pct": traffic.get("_fp64_pipe_pct", {}),
                 "source": traffic.get("_issue_source")},
         "ms_chain_kernel": {"launch_ms": ms_chain_ms, "steps_per_launch": 2, "traffic": traffic.get("slk_ms_chain_kernel")},
@@ -514,11 +531,12 @@ def run_ours(args, rank, world, local_rank):
             "frac": ls_tflops / fp64_peak if fp64_peak else None,
             "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
             "algorithmic_flops_per_launch": ls_flops, "launch_ms": ls_ms, "units_per_launch": loci_per_launch,
-            "traffic": traffic.get("slk_lsampler_kernel"),
+            "traffic": traffic.get("slk_lsampler_kernel"), "issue": issue_bound("slk_lsampler_kernel", ls_ms),
             "hbm": {"achieved": ls_bytes / (ls_ms * 1e-3) / 1e9, "frac": ls_bytes / (ls_ms * 1e-3) / 1e9 / hbm_peak,
                     "algorithmic_bytes_per_launch": ls_bytes}},
         "lodscore_kernel": {"bound": "fp64", "achieved": lod_tflops, "frac": lod_tflops / fp64_peak if fp64_peak else None,
                             "launch_ms": lod_ms, "algorithmic_flops_per_launch": lod_flops, "traffic": traffic.get("slk_lodscore_kernel"),
+                            "issue": issue_bound("slk_lodscore_kernel", lod_ms),
                             "trait_positions_per_s": (M - 1) * N_LOD / (lod_ms * 1e-3)},
         "msampler": {"sweep_ms": msweep_ms, "meioses_per_sweep": n_meioses, "us_per_meiosis_step": 1e3 * msweep_ms / max(n_meioses, 1),
                      "locus_likelihoods_per_s": 1.5 * n_meioses * M / (msweep_ms * 1e-3)},
