@@ -288,7 +288,7 @@ int slk_debug_msampler_launch(slk_chain* chain, int meiosis0, int meiosis1, int 
    meioses of a sweep: out[8 j + 0..4] = likelihood launch of the pair at order positions (j, j + 1), CTA 0: start, walk
    begins, before the wait for its predecessor, after it, end; out[8 (j + 1) + 0..3] = that pair's chain launch: start,
    before the wait, after it, end; from out[8 (n + 2)] on, for every CTA b of the likelihood launch at order position
-   cta_pair: out[.. + 2 b] = start, out[.. + 2 b + 1] = end << 10 | SM id.  cap >= 8 (n + 2) + 6 ceil(M / 32) words. */
+   cta_pair: out[.. + 2 b] = start, out[.. + 2 b + 1] = end << 10 | SM id.  cap >= 8 (n + 2) + 8 ceil(M / 32) words. */
 int slk_debug_msampler_timeline(slk_chain* chain, uint64_t iteration, int cta_pair, unsigned long long* out, int cap);
 /* tuning aid: one production L-sampler window launch (window 2, given offset) that also records
    clock64() stamps of the first team's first locus: start, after staging, after every forward

@@ -307,9 +307,9 @@ class Chain(object):
         """%globaltimer stamps of one M-sweep: (launch stamps [n + 2][8], CTA stamps [3 * grid][2]) -- see the header"""
         n = len(self.plan.msampler_ordering())
         grid = (self.plan.M + 31) // 32
-        buf = np.zeros(8 * (n + 2) + 6 * grid, np.uint64)
+        buf = np.zeros(8 * (n + 2) + 8 * grid, np.uint64)
         _check(self.L.slk_debug_msampler_timeline(self.h, C.c_uint64(iteration), int(cta_pair), _ptr(buf, C.c_ulonglong), int(buf.size)))
-        return buf[:8 * (n + 2)].reshape(n + 2, 8), buf[8 * (n + 2):].reshape(3 * grid, 2)
+        return buf[:8 * (n + 2)].reshape(n + 2, 8), buf[8 * (n + 2):].reshape(4 * grid, 2)
 
     def debug_msampler_launch(self, m0, m1, which, reps):
         _check(self.L.slk_debug_msampler_launch(self.h, int(m0), int(m1), int(which), int(reps)))

@@ -81,6 +81,7 @@ struct slk_chain {
     int32_t count;                // scoring passes (LODscores::count)
     // M-sampler state (allocated on first use)
     double* ms_lncur; double* ms_lnl; uint8_t* ms_bits; double* ms_fb; double* ms_out; void* ms_te; uint32_t* ms_stale;
+    uint32_t* ms_snap;            // two forest snapshots of slk_ms_snap_words(F) x M words (slk_ms_step_kernel)
     bool ms_cur_valid;            // ms_cur describes the graph now in dgp
     unsigned long long* ms_timeline;   // slk_debug_msampler_timeline only: %globaltimer stamps of the sweep being traced
     int ms_tl_slot, ms_tl_cta_slot;
@@ -427,7 +428,7 @@ void slk_chain_destroy(slk_chain* c) {
     cudaFree(c->gscratch); cudaFree(c->err);
     cudaFree(c->dbg_mat); cudaFree(c->dbg_pre); cudaFree(c->dbg_dist4); cudaFree(c->dbg_pmk);
     cudaFree(c->dbg_res); cudaFree(c->dbg_prob);
-    cudaFree(c->ms_lncur); cudaFree(c->ms_lnl); cudaFree(c->ms_bits); cudaFree(c->ms_te); cudaFree(c->ms_stale); cudaFree(c->ms_fb); cudaFree(c->ms_out);
+    cudaFree(c->ms_lncur); cudaFree(c->ms_lnl); cudaFree(c->ms_bits); cudaFree(c->ms_te); cudaFree(c->ms_stale); cudaFree(c->ms_snap); cudaFree(c->ms_fb); cudaFree(c->ms_out);
     delete c;
 }
 
@@ -707,6 +708,7 @@ static int ms_ready(slk_chain* c) {
         CU(cudaMalloc((void**) &c->ms_out, sizeof(double) * 4));
         CU(cudaMalloc((void**) &c->ms_te, (size_t) std::max(p->dev.ms.n_typed, 1) * M * 4));
         CU(cudaMalloc((void**) &c->ms_stale, sizeof(uint32_t) * M * p->dev.ms.W));
+        CU(cudaMalloc((void**) &c->ms_snap, sizeof(uint32_t) * 2 * (size_t) slk_ms_snap_words(p->dev.F) * M));
         CU(cudaMemsetAsync(c->ms_stale, 0, sizeof(uint32_t) * M * p->dev.ms.W, c->stream));
         CU(cudaMemsetAsync(c->ms_fb, 0, sizeof(double) * 2 * M, c->stream));
         c->ms_cur_valid = false;
@@ -724,6 +726,7 @@ static SlkMsLaunch ms_launch(slk_chain* c) {
     L.log_theta = d.log_theta; L.log_1mtheta = d.log_1mtheta;
     L.dgp = c->dgp; L.lncur = c->ms_lncur; L.lnl = c->ms_lnl; L.bits = c->ms_bits; L.fb = c->ms_fb; L.err = c->err;
     L.te = c->ms_te; L.stale = c->ms_stale;
+    L.snap = c->ms_snap; L.snap_use = -1; L.snap_build = -1;
     L.out = c->ms_out;
     L.nsets = 1;
     static const bool prev0 = getenv("SLK_MS_DEBUG_PREV0") != 0;  // timing aid for the debug launches only: results are invalid
@@ -751,7 +754,7 @@ static void ms_launch_overlapped(const void* kernel, int grid, int threads, size
 // the incremental kernel of a sweep's steps (te and the stale masks are valid: a reset has run)
 static void ms_launch_step(slk_chain* c, const SlkMsLaunch& L) {
     slk_plan* p = c->plan;
-    const int grid = p->ms_grid * L.nsets;
+    const int grid = p->ms_grid * (L.nsets + (L.snap_build >= 0 ? 1 : 0));        // the snapshot set comes last
     if(2 * p->dev.F > 255) ms_launch_overlapped((const void*) slk_ms_step_kernel<true>, grid, 32, p->ms_step_smem, c->stream, L);
     else ms_launch_overlapped((const void*) slk_ms_step_kernel<false>, grid, 32, p->ms_step_smem, c->stream, L);
 }
@@ -781,7 +784,17 @@ static void ms_launch_likelihood(slk_chain* c, const SlkMsLaunch& L) {
 // sweep; q1 < 0: a single step), q0 < 0 when the predecessor is anything else
 // run_ahead 2: (r0, r1) are the meioses of the pair before that one (< 0: none): the chain kernel of (q0, q1) and the
 // likelihood launch of (q0, q1), which refreshes the label pairs (r0, r1) invalidated, may both still be running
-static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -1, int q1 = -1, int run_ahead = 1, int r0 = -1, int r1 = -1) {
+// Forest snapshots of a launch (slk_ms_step_kernel): `use` / `build` = buffer (-1: none), the masks = te slots of the typed
+// people the snapshot does NOT hold (anybody one of the window's meioses can affect)
+struct MsSnapPlan {
+    int use, build;
+    const std::vector<uint32_t>* use_mask;
+    const std::vector<uint32_t>* build_mask;
+    MsSnapPlan() : use(-1), build(-1), use_mask(0), build_mask(0) {}
+};
+
+static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -1, int q1 = -1, int run_ahead = 1, int r0 = -1, int r1 = -1,
+                    const MsSnapPlan& snap = MsSnapPlan()) {
     const SlkDevPlan& d = c->plan->dev;
     SlkMsLaunch L = ms_launch(c);
     L.iteration = iteration;
@@ -828,16 +841,31 @@ static int ms_steps(slk_chain* c, uint64_t iteration, int m0, int m1, int q0 = -
             for(int s = 0; s < L.nsets; ++s) {
                 std::vector<uint32_t> hm((size_t) W, 0u);
                 for(int j = 0; j < L.set_n[s]; ++j) add(hm, L.set_person[s][j], L.set_parent[s][j]);
-                for(int w = 0; w < W; ++w) rec[1 + s * W + w] = hm[w];
+                for(int w = 0; w < W; ++w) rec[3 + s * W + w] = hm[w];
             }
-            uint16_t* ord = (uint16_t*)(rec + 1 + 3 * W);
+            auto touched = [&](const std::vector<uint32_t>& m, int k) { return ((m[k >> 4] >> (2 * (k & 15))) & 3u) != 0; };
+            // the hypothesis sets visit everybody the snapshot they start from does not hold: first the people the
+            // running chain kernels cannot affect, then the others
+            const bool use = L.prev_n >= 0 && snap.use >= 0 && snap.use_mask;
+            uint16_t* ord = (uint16_t*)(rec + 3 + 3 * W);
             int n = 0;
             for(int pass = 0; pass < 2; ++pass) {
                 for(int k = 0; k < nt; ++k) {
-                    const bool aff = ((prev[k >> 4] >> (2 * (k & 15))) & 3u) != 0;
-                    if(aff == (pass == 1)) ord[n++] = (uint16_t)(k | (hp.ms_typed_auto[k] ? 0x8000 : 0));
+                    if(use && !touched(*snap.use_mask, k)) continue;          // held by the snapshot
+                    if(touched(prev, k) == (pass == 1)) ord[n++] = (uint16_t)(k | (hp.ms_typed_auto[k] ? 0x8000 : 0));
                 }
                 if(pass == 0) rec[0] = (uint32_t) n;
+            }
+            rec[1] = (uint32_t) n;
+            if(use) L.snap_use = snap.use;
+            // the snapshot set visits the people its snapshot holds
+            if(snap.build >= 0 && snap.build_mask) {
+                uint16_t* bord = (uint16_t*)(rec + 3 + 3 * W + (nt + 1) / 2);
+                int nb = 0;
+                for(int k = 0; k < nt; ++k)
+                    if(!touched(*snap.build_mask, k)) bord[nb++] = (uint16_t)(k | (hp.ms_typed_auto[k] ? 0x8000 : 0));
+                rec[2] = (uint32_t) nb;
+                L.snap_build = snap.build;
             }
             L.rec_n = words;
         }
@@ -902,11 +930,41 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     // pair cannot affect (slk_ms_step_kernel).  The first pair follows the reset kernel, which writes te.
     static const bool no_overlap = getenv("SLK_MS_NO_PREFIX") != 0;      // tuning aid
     static const int run_ahead = getenv("SLK_MS_RUN_AHEAD") ? atoi(getenv("SLK_MS_RUN_AHEAD")) : 2;   // tuning aid: 1 = one launch in flight
+    // Forest snapshots (slk_ms_step_kernel): every K-th launch (a "leader", pair s) carries an extra set of CTAs that
+    // walks the typed people no meiosis of pairs s-2 .. s+K+1 can affect and saves the forest; launches s+2 .. s+K+1
+    // -- which start after the leader has completed -- begin their walks from it and visit the other people only.
+    // Two buffers alternate: the launches that read one have completed before the leader after next starts.
+    static const int snap_k = getenv("SLK_MS_SNAPSHOT") ? atoi(getenv("SLK_MS_SNAPSHOT")) : 4;    // tuning aid: 0 = off
+    const int np = (n + 1) / 2;
+    std::vector<MsSnapPlan> snaps((size_t) np);
+    std::vector<std::vector<uint32_t> > masks;
+    if(snap_k > 0 && run_ahead == 2 && !no_overlap) {
+        const slk::HostPlan& hp = c->plan->host;
+        const int W = hp.ms_W, nt = c->plan->dev.ms.n_typed, F = c->plan->dev.F;
+        masks.reserve((size_t) np / snap_k + 1);
+        for(int s = 0; s + 2 < np; s += snap_k) {
+            std::vector<uint32_t> m((size_t) W, 0u);
+            for(int j = std::max(0, s - 2); j <= std::min(np - 1, s + snap_k + 1); ++j)
+                for(int h = 0; h < 2 && 2 * j + h < n; ++h) {
+                    const int person = F + order[2 * j + h] / 2, parent = order[2 * j + h] % 2;
+                    for(int w = 0; w < W; ++w) m[w] |= hp.ms_desc_mask[(size_t)(person - F) * W + w];
+                    const int kk = hp.ms_typed_index[person];
+                    if(kk >= 0) m[(2 * kk + parent) >> 5] |= 1u << ((2 * kk + parent) & 31);
+                }
+            int held = 0;
+            for(int k = 0; k < nt; ++k) if(((m[k >> 4] >> (2 * (k & 15))) & 3u) == 0) ++held;
+            if(held < 8) continue;                                   // not worth a snapshot
+            masks.push_back(m);
+            const int buf = (s / snap_k) & 1;
+            snaps[s].build = buf; snaps[s].build_mask = &masks.back();
+            for(int j = s + 2; j <= std::min(np - 1, s + snap_k + 1); ++j) { snaps[j].use = buf; snaps[j].use_mask = &masks.back(); }
+        }
+    }
     int q0 = -1, q1 = -1, r0 = -1, r1 = -1;
     for(int j = 0; j < n && rc == SLK_OK; j += 2) {
         const int m0 = order[j], m1 = j + 1 < n ? order[j + 1] : -1;
         c->ms_tl_slot = j;
-        rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1, (no_overlap || run_ahead != 2) ? 1 : 2, r0, r1);
+        rc = ms_steps(c, iteration, m0, m1, no_overlap ? -1 : q0, q1, (no_overlap || run_ahead != 2) ? 1 : 2, r0, r1, snaps[j / 2]);
         r0 = q0; r1 = q1;
         q0 = m0; q1 = m1;
     }
@@ -916,12 +974,12 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
 // Tuning aid: one M-sweep with %globaltimer stamps.  out[8 j + 0..4] = likelihood launch of the pair that starts at
 // meiosis j of the order (start, walk, before wait, after wait, end; CTA 0), out[8 (j + 1) + 0..3] = its chain launch
 // (start, before wait, after wait, end); from out[8 (n + 2)] on, (start, end << 10 | SM) of every CTA of the likelihood
-// launch at order position `cta_pair`.  cap >= 8 (n + 2) + 6 * ceil(M / 32) words (n = meioses of a sweep).
+// launch at order position `cta_pair`.  cap >= 8 (n + 2) + 8 * ceil(M / 32) words (n = meioses of a sweep).
 int slk_debug_msampler_timeline(slk_chain* c, uint64_t iteration, int cta_pair, unsigned long long* out, int cap) {
     int rc = ms_ready(c);
     if(rc != SLK_OK) return rc;
     const int n = (int) c->plan->host.ms_ordering.size();
-    const int words = 8 * (n + 2) + 2 * 3 * c->plan->ms_grid;
+    const int words = 8 * (n + 2) + 2 * 4 * c->plan->ms_grid;          // up to four sets of CTAs (the fourth: a snapshot set)
     if(!out || cap < words) return fail(SLK_ERR_INVALID, "slk_debug_msampler_timeline: %d words needed", words);
     unsigned long long* tl = 0;
     CU(cudaMalloc((void**) &tl, sizeof(unsigned long long) * words));

@@ -59,9 +59,6 @@
 #define SLK_SLOT_KIND     0x7ffffff2u
 #define SLK_SLOT_MEIOSIS  0x40000000u
 
-#ifndef SLK_MS_NODE_WALK
-#define SLK_MS_NODE_WALK 1           // 1: disjoint-set forest over the founder alleles themselves (ms_walk below)
-#endif
 #define SLK_MS_MAXSETS 3
 #define SLK_MS_REC_WORDS 448
 #define SLK_MS_MAXGROUPS 4095
@@ -88,6 +85,9 @@ struct SlkMsLaunch {
     int prev_person[4];          //   these prev_n (0-4) meioses (-1: the predecessor is something else, nothing may run
     int prev_parent[4];          //   ahead of it)
     int run_ahead;               // 2: two likelihood launches in flight (see slk_ms_step_kernel); else one
+    // forest snapshots (step kernel, host record only): two buffers of slk_ms_snap_words(F) x M words
+    uint32_t* snap;
+    int snap_use, snap_build;    // buffer this launch starts its walks from / an extra set of CTAs fills (-1: none)
     int set_n[SLK_MS_MAXSETS];
     int set_person[SLK_MS_MAXSETS][2];
     int set_parent[SLK_MS_MAXSETS][2];
@@ -160,11 +160,7 @@ __host__ __device__
 static inline MsLayout slk_ms_layout(int N, int F, int nt) {
     MsLayout L;
     L.wide = (2 * F > 255) ? 1 : 0;
-#if SLK_MS_NODE_WALK
     L.G = 2 * F;                     // one union-find word per founder allele (ms_walk)
-#else
-    L.G = nt < 2 * F ? nt : 2 * F;
-#endif
     if(L.G < 1) L.G = 1;
     const uint32_t E = L.wide ? 2u : 1u;
 #define r4(x) ((((uint32_t)(x)) + 3u) & ~3u)
@@ -178,11 +174,7 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
     L.grp = 0;
     L.cnt = L.grp + 4u * L.G;
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
-#if SLK_MS_NODE_WALK
     const uint32_t c_bytes = L.fa;
-#else
-    const uint32_t c_bytes = L.fa + r4(4u * F);
-#endif
     L.per_thread = L.ov + r4(a_bytes > c_bytes ? a_bytes : c_bytes);
     L.cta_tables = r8((uint32_t)(16 * (N - F) + 4 * nt + nt + 8));
 #undef r4
@@ -192,25 +184,6 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
 
 // ---- (1) founder allele graph likelihood ---------------------------------------------------------
 //
-// The reference relabels every founder allele of the absorbed component on each merge
-// (combine_components, founder_allele_graph4.cc:504-546: a loop over all 2F alleles).  Here the
-// components form a disjoint-set forest: a founder allele remembers the component it first joined
-// and its two candidate alleles in that component's frame; a component that is merged away points at
-// its absorber with a parity bit ("my two assignments are swapped relative to yours").
-//
-// A component's two assignment probabilities are products of allele frequencies, so they are kept as
-// exponents (a, b): p = major^a * minor^b for the assignment the component is FIXED to, or for
-// assignment 0 if it is unfixed.  An unfixed component only ever contains heterozygous edges, so its
-// assignment 1 is the allele-wise complement of assignment 0 and p1 = major^b * minor^a: nothing else
-// needs storing (checked against the oracle's explicit prob[0], prob[1] on every test pedigree).
-//
-// grp word: bits 0..11 parent component, bit 12 parity to parent, bits 13..14 state (0 unfixed,
-// 1 fixed to assignment 0, 2 fixed to assignment 1), bit 15 merged away, bits 16..23 a, 24..31 b
-// (wide: a, b are 16 bits each in a second word).
-// fa entry (u16): bits 0..11 component + 1 (0 = none), bit 14 / 15 = candidate allele under
-// assignment 0 / 1 is HOMOZ_B (in the frame of that component).
-
-#if SLK_MS_NODE_WALK
 // The walk over the typed people (founder_allele_graph4.cc:34-424) shared by the two likelihood kernels, as a
 // disjoint-set forest over the FOUNDER ALLELES with parity bits.
 //
@@ -232,13 +205,38 @@ static inline MsLayout slk_ms_layout(int N, int F, int nt) {
 // node word: bits 0..11 parent, bit 12 parity to parent, bits 13..14 state (0 unfixed, 1 / 2 fixed to root value
 // 0 / 1), bit 15 touched by an edge, bits 16..23 n0, 24..31 n1 (wide: n0, n1 16 bits each in a second word).
 // `src.next(k, g, mat, pat)` supplies the k-th typed person's observed genotype and founder-allele labels.
+// Snapshots (step kernel, see there): `snap_in` = the forest after a set of typed people nobody touches for a while has
+// been walked, saved by an earlier launch -- the walk starts from it instead of from singletons; `snap_out` = save the
+// forest after this walk instead of finishing it.  Layout [word][M] (a lane is a locus: coalesced), words 0 .. nn - 1 the
+// nodes (wide: nn more with the counts), then one word that is non-zero if the saved forest is inconsistent.
 template<bool WIDE, class Src>
 __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint32_t o_cnt, uint32_t /*o_fa*/, int F, int nt,
-                                          const uint8_t* /*s_auto*/, Src& src, double lnM, double lnm, long long* tr) {
+                                          const uint8_t* /*s_auto*/, Src& src, double lnM, double lnm, long long* tr,
+                                          const uint32_t* snap_in = 0, uint32_t* snap_out = 0, size_t snap_stride = 0) {
     const int nn = 2 * F;
-    for(int i = 0; i < nn; ++i) {
-        if(WIDE) { ms_st32(ln.a32(o_grp, i), (uint32_t) i); ms_st32(ln.a32(o_cnt, i), 1u); }
-        else ms_st32(ln.a32(o_grp, i), (uint32_t) i | (1u << 16));
+    bool dead = false;
+    if(snap_in) {
+        // (L2 loads: the buffer was last written by another launch, this SM's L1 may still hold what it held before)
+        for(int i0 = 0; i0 < nn; i0 += 8) {
+            uint32_t w[8], c[8];
+#pragma unroll
+            for(int j = 0; j < 8; ++j) if(i0 + j < nn) {
+                w[j] = __ldcg(snap_in + (size_t)(i0 + j) * snap_stride);
+                if(WIDE) c[j] = __ldcg(snap_in + (size_t)(nn + i0 + j) * snap_stride);
+            }
+#pragma unroll
+            for(int j = 0; j < 8; ++j) if(i0 + j < nn) {
+                ms_st32(ln.a32(o_grp, i0 + j), w[j]);
+                if(WIDE) ms_st32(ln.a32(o_cnt, i0 + j), c[j]);
+            }
+        }
+        dead = __ldcg(snap_in + (size_t)(WIDE ? 2 * nn : nn) * snap_stride) != 0u;
+    }
+    else {
+        for(int i = 0; i < nn; ++i) {
+            if(WIDE) { ms_st32(ln.a32(o_grp, i), (uint32_t) i); ms_st32(ln.a32(o_cnt, i), 1u); }
+            else ms_st32(ln.a32(o_grp, i), (uint32_t) i | (1u << 16));
+        }
     }
     struct Node { uint32_t meta, n0, n1; };
     auto node_ld = [&](uint32_t g) -> Node {
@@ -270,7 +268,6 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
         return g;
     };
 
-    bool dead = false;
     const int niter = src.iterations(nt);
     for(int it = 0; it < niter && !dead; ++it) {
         uint32_t g, mat, pat;
@@ -323,6 +320,14 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
     }
 
     if(tr) tr[5] = clock64();
+    if(snap_out) {
+        for(int i = 0; i < nn; ++i) {
+            snap_out[(size_t) i * snap_stride] = ms_ld32(ln.a32(o_grp, i));
+            if(WIDE) snap_out[(size_t)(nn + i) * snap_stride] = ms_ld32(ln.a32(o_cnt, i));
+        }
+        snap_out[(size_t)(WIDE ? 2 * nn : nn) * snap_stride] = dead ? 1u : 0u;
+        return 0.0;
+    }
     double ret = -INFINITY;
     if(!dead) {
         uint32_t A = 0, B = 0;
@@ -365,253 +370,6 @@ __device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint
     }
     return ret;
 }
-#else
-// The walk over the typed people (founder_allele_graph4.cc:34-424) shared by the two likelihood kernels.
-// `src.next(k, g, mat, pat)` supplies the k-th typed person's observed genotype and founder-allele labels.
-#define FA_LD(k)      ms_ld16(ln.a16(o_fa, (k)))
-#define FA_ST(k, v)   ms_st16(ln.a16(o_fa, (k)), (v))
-template<bool WIDE, class Src>
-__device__ __forceinline__ double ms_walk(const MsLane& ln, uint32_t o_grp, uint32_t o_cnt, uint32_t o_fa, int F, int nt,
-                                          const uint8_t* s_auto, Src& src, double lnM, double lnm, long long* tr) {
-    for(int i = 0; i < F; ++i) ms_st32(ln.a32(o_fa, i), 0u);           // two u16 entries per word
-
-    // ---- phase C: founder_allele_graph4.cc:34-424 ---------------------------------------------------
-    struct Grp { uint32_t meta; uint32_t a, b; };       // meta = low 16 bits of the word
-    auto grp_ld = [&](uint32_t g) -> Grp {
-        Grp r;
-        const uint32_t w = ms_ld32(ln.a32(o_grp, g));
-        r.meta = w & 0xffffu;
-        if(WIDE) { const uint32_t c = ms_ld32(ln.a32(o_cnt, g)); r.a = c & 0xffffu; r.b = c >> 16; }
-        else { r.a = (w >> 16) & 0xffu; r.b = w >> 24; }
-        return r;
-    };
-    auto grp_st = [&](uint32_t g, uint32_t meta, uint32_t a, uint32_t b) {
-        if(WIDE) { ms_st32(ln.a32(o_grp, g), meta); ms_st32(ln.a32(o_cnt, g), a | (b << 16)); }
-        else ms_st32(ln.a32(o_grp, g), meta | (a << 16) | (b << 24));
-    };
-    // root of component g: returns the root id, its entry, the parity of g's frame to the root's
-    // (the entry of g is passed in: where two components are looked up, both first loads are issued together)
-    auto find_from = [&](uint32_t g, Grp e, Grp& re, uint32_t& par) -> uint32_t {
-        const uint32_t g0 = g;
-        par = 0;
-        int hops = 0;
-        while((e.meta & 0xfffu) != g) {
-            par ^= (e.meta >> 12) & 1u;
-            g = e.meta & 0xfffu;
-            e = grp_ld(g);
-            ++hops;
-        }
-        if(hops > 1) grp_st(g0, g | (par << 12) | 0x8000u, 0u, 0u);        // path compression
-        re = e;
-        return g;
-    };
-    auto find = [&](uint32_t g, Grp& re, uint32_t& par) -> uint32_t { return find_from(g, grp_ld(g), re, par); };
-    auto fixed_of = [](const Grp& e) -> int { return (int)((e.meta >> 13) & 3u) - 1; };   // -1 unfixed, 0, 1
-    // write root `g` with state f and exponents (a, b)
-    auto put = [&](uint32_t g, int f, uint32_t a, uint32_t b) { grp_st(g, g | ((uint32_t)(f + 1) << 13), a, b); };
-
-    int ngroups = 0;
-    bool dead = false;
-    // The likelihood does not depend on the order in which the typed people are visited (the exponents are
-    // integers; only the rounding of the unfixed components' product does, in the last bits).  The source decides
-    // the order: the full kernel visits everyone once, the step kernel in two phases (see slk_ms_step_kernel).
-    const int niter = src.iterations(nt);
-    for(int it = 0; it < niter && !dead; ++it) {
-        uint32_t g, mat, pat;
-        bool single;                                    // x-linked male: the maternal allele only
-        const int k = src.next(it, g, mat, pat, single);       // < 0: nobody to visit in this iteration
-        if(k < 0 || g == SLK_UNTYPED) continue;
-        const uint32_t gB = (g == SLK_HOMOZ_B) ? 1u : 0u;
-        const bool het = g == SLK_HETERO;
-        const uint32_t em = FA_LD(mat), ep = FA_LD(pat);        // both loads in flight together
-
-        if(mat == pat || single) {
-            if(het) { dead = true; break; }
-            if(em & 0xfffu) {
-                Grp re; uint32_t par;
-                const uint32_t g1 = find((em & 0xfffu) - 1u, re, par);
-                const int f1 = fixed_of(re);
-                const uint32_t x0 = (em >> (14 + par)) & 1u, x1 = (em >> (15 - par)) & 1u;    // root frame
-                if(f1 != -1) {
-                    if((f1 ? x1 : x0) != gB) { dead = true; break; }
-                }
-                else {
-                    if(x0 == gB)      put(g1, 0, re.a, re.b);
-                    else if(x1 == gB) put(g1, 1, re.b, re.a);
-                    else { dead = true; break; }
-                }
-            }
-            else {
-                FA_ST(mat, (uint32_t)(ngroups + 1) | (gB << 14));
-                put(ngroups, 0, gB ? 0u : 1u, gB ? 1u : 0u);
-                ++ngroups;
-            }
-            continue;
-        }
-
-        // legal(g, a1, a2) and get_other_allele(g, a1) on one-bit alleles (founder_allele_graph4.cc:427-455)
-#define LEGAL(x, y) (het ? ((x) != (y)) : ((x) == gB && (y) == gB))
-        if((em & 0xfffu) && (ep & 0xfffu)) {
-            Grp re1, re2; uint32_t par1, par2;
-            const uint32_t i1 = (em & 0xfffu) - 1u, i2 = (ep & 0xfffu) - 1u;
-            const Grp e1 = grp_ld(i1), e2 = grp_ld(i2);
-            const uint32_t g1 = find_from(i1, e1, re1, par1);
-            const uint32_t g2 = find_from(i2, e2, re2, par2);       // (a path compression of i1 leaves e2 a valid, longer route)
-            const uint32_t m0 = (em >> (14 + par1)) & 1u, m1 = (em >> (15 - par1)) & 1u;
-            const uint32_t q0 = (ep >> (14 + par2)) & 1u, q1 = (ep >> (15 - par2)) & 1u;
-            int f1 = fixed_of(re1);
-            if(g1 == g2) {
-                if(f1 != -1) {
-                    if(!LEGAL(f1 ? m1 : m0, f1 ? q1 : q0)) { dead = true; break; }
-                }
-                else {
-                    const bool l0 = LEGAL(m0, q0), l1 = LEGAL(m1, q1);
-                    if(l0) { if(!l1) put(g1, 0, re1.a, re1.b); }
-                    else {
-                        if(l1) put(g1, 1, re1.b, re1.a);
-                        else { dead = true; break; }
-                    }
-                }
-                continue;
-            }
-            int f2 = fixed_of(re2);
-            const bool was1 = f1 != -1, was2 = f2 != -1;
-            if(f1 != -1) {
-                const uint32_t am = f1 ? m1 : m0;
-                if(f2 != -1) {
-                    if(!LEGAL(am, f2 ? q1 : q0)) { dead = true; break; }
-                }
-                else {
-                    if(LEGAL(am, q0)) f2 = 0;
-                    else if(LEGAL(am, q1)) f2 = 1;
-                    else { dead = true; break; }
-                }
-            }
-            else if(f2 != -1) {
-                const uint32_t ap = f2 ? q1 : q0;
-                if(LEGAL(m0, ap)) f1 = 0;
-                else if(LEGAL(m1, ap)) f1 = 1;
-                else { dead = true; break; }
-            }
-            else {
-                const bool l0 = LEGAL(m0, q0), l1 = LEGAL(m1, q0), l2 = LEGAL(m0, q1), l3 = LEGAL(m1, q1);
-                if(!(l0 || l1 || l2 || l3)) { dead = true; break; }
-                if(l0 && !(l1 || l2 || l3))      { f1 = f2 = 0; }
-                else if(l1 && !(l0 || l2 || l3)) { f1 = 1; f2 = 0; }
-                else if(l2 && !(l0 || l1 || l3)) { f1 = 0; f2 = 1; }
-                else if(l3 && !(l0 || l1 || l2)) { f1 = f2 = 1; }
-                else if(l0 && l3 && !(l1 || l2)) { f1 = f2 = -1; }
-                else if(l1 && l2 && !(l0 || l3)) { f1 = f2 = -2; }
-                else                             { f1 = f2 = -1; }
-            }
-            // combine_components(group1, group2, flip) (:504-546).  s1 / s2: which assignment of each
-            // component goes into the product that is kept (assignment 0 of the merged component if it
-            // stays unfixed).  A fixed component stores the exponents of its fixed side, an unfixed one
-            // those of assignment 0 with assignment 1 = (b, a).
-            bool flip; int nf; int s1, s2;
-            if(f1 != f2)       { nf = f1; flip = true;  s1 = f1; s2 = f2; }
-            else if(f1 == -2)  { nf = -1; flip = true;  s1 = 0;  s2 = 1; }
-            else if(f1 == -1)  { nf = -1; flip = false; s1 = 0;  s2 = 0; }
-            else               { nf = f1; flip = false; s1 = f1; s2 = f1; }
-            const uint32_t a1v = (was1 || s1 == 0) ? re1.a : re1.b, b1v = (was1 || s1 == 0) ? re1.b : re1.a;
-            const uint32_t a2v = (was2 || s2 == 0) ? re2.a : re2.b, b2v = (was2 || s2 == 0) ? re2.b : re2.a;
-            put(g1, nf, a1v + a2v, b1v + b2v);
-            grp_st(g2, g1 | ((flip ? 1u : 0u) << 12) | 0x8000u, 0u, 0u);
-            continue;
-        }
-#undef LEGAL
-        if((em & 0xfffu) || (ep & 0xfffu)) {
-            // one allele already in a component, the other joins it (:286-384)
-            const bool mat_in = (em & 0xfffu) != 0;
-            const uint32_t eo = mat_in ? em : ep;
-            Grp re; uint32_t par;
-            const uint32_t grp = find((eo & 0xfffu) - 1u, re, par);
-            const uint32_t fa_new = mat_in ? pat : mat;
-            const uint32_t o0 = (eo >> (14 + par)) & 1u, o1 = (eo >> (15 - par)) & 1u;
-            const int fx = fixed_of(re);
-            uint32_t v0 = 0, v1 = 0;
-            // other allele under assignment w: valid iff het or o_w == gB; value = het ? !o_w : gB
-            if(fx != -1) {
-                const uint32_t o = fx ? o1 : o0;
-                if(!het && o != gB) { dead = true; break; }
-                const uint32_t v = het ? (o ^ 1u) : gB;
-                if(fx) v1 = v; else v0 = v;
-                put(grp, fx, re.a + (v ^ 1u), re.b + v);
-            }
-            else {
-                const bool ok0 = het || o0 == gB, ok1 = het || o1 == gB;
-                v0 = het ? (o0 ^ 1u) : gB; v1 = het ? (o1 ^ 1u) : gB;
-                if(ok0) {
-                    // both valid (heterozygous edge): assignment 1 gets the complementary factor, which
-                    // the (b, a) convention already encodes
-                    put(grp, ok1 ? -1 : 0, re.a + (v0 ^ 1u), re.b + v0);
-                }
-                else {
-                    if(ok1) put(grp, 1, re.b + (v1 ^ 1u), re.a + v1);
-                    else { dead = true; break; }
-                }
-            }
-            FA_ST(fa_new, (grp + 1u) | (v0 << 14) | (v1 << 15));
-            continue;
-        }
-        // neither allele seen before: a new component (:386-409)
-        if(het) {
-            FA_ST(mat, (uint32_t)(ngroups + 1) | (0u << 14) | (1u << 15));
-            FA_ST(pat, (uint32_t)(ngroups + 1) | (1u << 14) | (0u << 15));
-            put(ngroups, -1, 1u, 1u);
-        }
-        else {
-            FA_ST(mat, (uint32_t)(ngroups + 1) | (gB << 14));
-            FA_ST(pat, (uint32_t)(ngroups + 1) | (gB << 14));
-            put(ngroups, 0, gB ? 0u : 2u, gB ? 2u : 0u);
-        }
-        ++ngroups;
-    }
-
-    if(tr) tr[5] = clock64();
-    double ret = -INFINITY;
-    if(!dead) {
-        // an unfixed component contributes p0 + p1 = M^a m^b + M^b m^a = M^hi' m^lo' (1 + rho^|a-b|) with
-        // rho = min(m/M, M/m) <= 1 and (hi', lo') the exponents of the larger term: the exponents are summed as
-        // integers, the (1 + rho^k) factors (each in (1, 2]) multiplied up and logged once
-        uint32_t A = 0, B = 0;
-        const bool minor_smaller = lnm <= lnM;
-        const double rho = exp(-fabs(lnm - lnM));
-        double prod = 1.0;
-        for(int i0 = 0; i0 < ngroups; i0 += 4) {
-            // four table words in flight at a time (the loads are ordered asm statements: one per iteration would
-            // pay a shared-memory latency each)
-            Grp eq[4];
-#pragma unroll
-            for(int j = 0; j < 4; ++j) {
-                if(i0 + j < ngroups) eq[j] = grp_ld(i0 + j);
-                else { eq[j].meta = 0x8000u; eq[j].a = eq[j].b = 0u; }
-            }
-#pragma unroll
-            for(int j = 0; j < 4; ++j) {
-                const Grp e = eq[j];
-                if(e.meta & 0x8000u) continue;             // merged away (group_active false)
-                uint32_t a = e.a, b = e.b;
-                if(fixed_of(e) == -1) {
-                    // keep the larger of the two terms: more factors of the more frequent allele
-                    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
-                    uint32_t k = hi - lo;
-                    if(minor_smaller) { a = hi; b = lo; } else { a = lo; b = hi; }
-                    double t = 1.0, sq = rho;
-                    while(k) { if(k & 1u) t *= sq; sq *= sq; k >>= 1; }
-                    prod *= 1.0 + t;
-                }
-                A += a; B += b;
-            }
-        }
-        ret = ((double) A * lnM + (double) B * lnm) + log(prod);
-        if(!(ret > -1e290)) ret = -INFINITY;               // a zero allele frequency entered the product
-    }
-    return ret;
-}
-#undef FA_LD
-#undef FA_ST
-#endif  // SLK_MS_NODE_WALK
 
 template<bool WIDE>
 __global__ void __launch_bounds__(32)
@@ -796,33 +554,33 @@ __host__ __device__
 static inline MsStepLayout slk_ms_step_layout(int N, int F, int nt, int W) {
     MsStepLayout L;
     L.wide = (2 * F > 255) ? 1 : 0;
-#if SLK_MS_NODE_WALK
     L.G = 2 * F;
-#else
-    L.G = nt < 2 * F ? nt : 2 * F;
-#endif
     if(L.G < 1) L.G = 1;
     L.grp = 0;
     L.cnt = L.grp + 4u * L.G;
     L.fa = L.cnt + (L.wide ? 4u * L.G : 0u);
-#if SLK_MS_NODE_WALK
     L.hmask = L.fa;
-#else
-    L.hmask = L.fa + ((4u * F + 3u) & ~3u);
-#endif
     L.per_thread = L.hmask + 4u * W;
     L.cta_tables = ((uint32_t)(4 * N + 2 * nt + nt + 4 + 4 * W + 2 * nt + 8 + 8) + 7u) & ~7u;
     return L;
 }
 
-// Host-built record of one launch of a sweep (all records of a sweep are uploaded with one copy before its first
-// kernel): word 0 = number of typed people the predecessor cannot affect (the phase boundary), then the slot masks of
-// the three hypotheses (3 x W words, without the locus's stale slots), then the visiting order, two 16-bit entries per
-// word (index | single-allele flag << 15).  With a record the per-warp prologue is one batch of independent loads.
+// Host-built record of one launch of a sweep (it travels in the kernel parameters): word 0 = number of visited typed
+// people the running chain kernels cannot affect (the phase boundary), word 1 = people visited in all (everybody, or
+// everybody a snapshot does not already hold), word 2 = people the snapshot set visits; then the slot masks of the three
+// hypotheses (3 x W words, without the locus's stale slots), then the visiting order, two 16-bit entries per word
+// (index | single-allele flag << 15), then the snapshot set's order.  With a record the per-warp prologue is one batch of
+// independent loads.
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline int slk_ms_pair_rec_words(int nt, int W) { return 1 + 3 * W + (nt + 1) / 2; }
+static inline int slk_ms_pair_rec_words(int nt, int W) { return 3 + 3 * W + 2 * ((nt + 1) / 2); }
+
+// words per locus of a forest snapshot (ms_walk): the nodes (two words each if wide) and the inconsistency flag
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int slk_ms_snap_words(int F) { return ((2 * F > 255) ? 4 * F : 2 * F) + 1; }
 
 template<bool WIDE>
 __global__ void __launch_bounds__(32)
@@ -849,11 +607,18 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     uint16_t* s_ord = (uint16_t*)(s_prev + W);                                      // [nt]
     int* s_n0 = (int*)(ms_smem + ((4u * N + 3u * nt + 3u) & ~3u) + 4u * W + ((2u * nt + 3u) & ~3u));
     const bool rec = L.rec_n > 0;
+    const int nblk = (M + 31) >> 5;
+    const int set = blockIdx.x / nblk;
+    // Snapshot set (an extra set of CTAs behind the hypothesis sets, host record only): walks the typed people that
+    // no meiosis of the next few launches can affect and saves the forest; those launches start their walks from it.
+    const bool build = set >= L.nsets;
+    const int n_visit = rec ? (int) L.rec[build ? 2 : 1] : nt;
     if(rec) {
         // the order and the phase boundary come from the host
+        const uint32_t* ordw = L.rec + 3 + 3 * W + (build ? (nt + 1) / 2 : 0);
         for(int k = t; k < nt; k += 32) s_typed[k] = L.ms.typed[k];
-        for(int k = t; k < (nt + 1) / 2; k += 32) ((uint32_t*) s_ord)[k] = L.rec[1 + 3 * W + k];
-        if(t == 0) *s_n0 = (int) L.rec[0];
+        for(int k = t; k < (nt + 1) / 2; k += 32) ((uint32_t*) s_ord)[k] = ordw[k];
+        if(t == 0) *s_n0 = build ? n_visit : (int) L.rec[0];
     }
     else {
     for(int k = t; k < nt; k += 32) {
@@ -890,13 +655,12 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     }
     __syncwarp();
 
-    const int nblk = (M + 31) >> 5;
-    const int set = blockIdx.x / nblk;
     const int l = (blockIdx.x - set * nblk) * 32 + (int) t;
     if(l >= M) return;
-    const int nflip = L.set_n[set];
-    const int p0 = nflip > 0 ? L.set_person[set][0] : -1, a0 = L.set_parent[set][0];
-    const int p1 = nflip > 1 ? L.set_person[set][1] : -1, a1 = L.set_parent[set][1];
+    const int hset = build ? 0 : set;
+    const int nflip = build ? 0 : L.set_n[hset];
+    const int p0 = nflip > 0 ? L.set_person[hset][0] : -1, a0 = L.set_parent[hset][0];
+    const int p1 = nflip > 1 ? L.set_person[hset][1] : -1, a1 = L.set_parent[hset][1];
 
     MsLane ln;
     ln.base = (uint32_t) __cvta_generic_to_shared(ms_smem + lay.cta_tables) + (t << 2);
@@ -904,7 +668,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     const uint8_t* row = L.dgp + (size_t) l * N;
     // the hypothesis's slot mask, without the locus's stale slots: those are the predecessor kernel's to write
     if(rec) {
-        for(int w = 0; w < W; ++w) ms_st32(ln.a32(o_hm, w), L.rec[1 + set * W + w]);
+        for(int w = 0; w < W; ++w) ms_st32(ln.a32(o_hm, w), build ? 0u : L.rec[3 + set * W + w]);
     }
     else {
     for(int w = 0; w < W; ++w) {
@@ -1004,7 +768,7 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
         }
     } src = { ln, o_hm, row, s_mo, s_fa, s_typed, s_ord, *s_n0, L.te, L.ms.obsT + l, L.stale,
               (p0 >= 0 && set < 2) ? L.bits + (size_t) set * M + l : (uint8_t*) 0,
-              M, l, F, nt, W, p0, a0, p1, a1, false,
+              M, l, F, n_visit, W, p0, a0, p1, a1, false,
               (L.timeline && blockIdx.x == 0 && t == 0) ? L.timeline + 8 * L.tl_slot : (unsigned long long*) 0, deep,
               0u, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u} };
     const double lnM = L.ms.lnmajor[l], lnm = L.ms.lnminor[l];
@@ -1014,7 +778,13 @@ slk_ms_step_kernel(const SlkMsLaunch L) {
     src.hw_next = ms_ld32(ln.a32(o_hm, (src.qk[0] & 0x7fffu) >> 4));
     if(tr) tr[4] = clock64();
     MS_TL(1);
-    const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, nt, s_auto, src, lnM, lnm, tr);
+    const size_t snap_size = (size_t) slk_ms_snap_words(F) * (size_t) M;
+    const uint32_t* snap_in = (!build && L.snap_use >= 0) ? L.snap + (size_t) L.snap_use * snap_size + l : (const uint32_t*) 0;
+    uint32_t* snap_out = build ? L.snap + (size_t) L.snap_build * snap_size + l : (uint32_t*) 0;
+    const double ret = ms_walk<WIDE>(ln, o_grp, o_cnt, o_fa, F, n_visit, s_auto, src, lnM, lnm, tr, snap_in, snap_out, (size_t) M);
+    // the snapshot set is done: it never waits for the predecessor (the people it visits are out of every running
+    // kernel's reach) and its exit counts as its release of the dependent launch
+    if(build) return;
     if(!src.synced) src.sync();                            // every lane left the walk (impossible graph) in phase 0
     L.lnl[(size_t) set * M + l] = ret;
 
@@ -1311,7 +1081,10 @@ slk_ms_chain_kernel(const SlkMsLaunch L) {
             }
         }
         if(tr) tr[7 + 8 * step] = clock64();
-        cluster.sync();                                    // shared tables are reused by the next step
+        // The CTA's own tables are reused by the next step: a CTA barrier.  The tables other CTAs write into
+        // (s_cmat, s_r0: before the next step's first cluster barrier; s_cmap: before its second) need none: a CTA can
+        // only get that far after every CTA has arrived at the barrier that follows this step's last read of them.
+        __syncthreads();
         if(tr) tr[8 + 8 * step] = clock64();
     }
     for(int i = cta_lo + t; i < cta_hi; i += T) L.lncur[i] = s_lncur[i - cta_lo];

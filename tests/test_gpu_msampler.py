@@ -269,17 +269,18 @@ def test_bench_pedigree_sweeps_match_oracle():
     ch.close(); plan.close(); hst.close()
 
 
-@pytest.mark.parametrize("env", ["SLK_MS_NO_REC", "SLK_NO_PDL", "SLK_MS_NO_PREFIX"])
+@pytest.mark.parametrize("env", ["SLK_MS_NO_REC", "SLK_NO_PDL", "SLK_MS_NO_PREFIX", "SLK_MS_RUN_AHEAD", "SLK_MS_SNAPSHOT=0", "SLK_MS_SNAPSHOT=2"])
 def test_msampler_fallback_paths(env):
     """the library's alternative launch paths -- launch record derived inside the kernel instead of on the host, plain
-    launches instead of programmatic dependent ones, nothing running ahead of the predecessor -- give the same graphs
+    launches instead of programmatic dependent ones, nothing running ahead of the predecessor, one likelihood launch
+    in flight instead of two, no forest snapshots / a snapshot every second launch -- give the same graphs
     (the switches are read once per process, hence the subprocess)"""
     import os
     import subprocess
     import sys
     from common import ROOT
     e = dict(os.environ)
-    e[env] = "1"
+    e[env.split("=")[0]] = env.split("=")[1] if "=" in env else "1"
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_msampler.py"), "-q", "-x",
                           "-k", "test_sweeps_match_oracle or test_steps_match_oracle"], env=e, capture_output=True, text=True,
                          timeout=900, cwd=ROOT)
