@@ -57,6 +57,34 @@ WORKLOAD = ("synthetic 200-member consanguineous pedigree, 10k SNPs, default sam
 STEP_DESC = "%d iterations (each an L-sweep w.p. 0.5, else an M-sweep over all meioses) + 1 LOD scoring pass" % SCORING_PERIOD
 
 
+class quiet_stdout(object):
+    """the host classes print what the reference prints (starting likelihood, P(T), ...) on file descriptor 1; the bench
+    line must be the only thing on stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved); os.close(self.null)
+
+
+def init_nccl(local_rank):
+    """process group + first collective with file descriptor 1 muted: NCCL prints its version banner there when the
+    communicator is created, and the bench line must be the only thing on stdout"""
+    import torch
+    import torch.distributed as dist
+    with quiet_stdout():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.zeros(1, device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    return dist
+
+
 def load_order():
     with open(os.path.join(ROOT, "swiftlink_b200", "data", "synth200_peel_order.json")) as f:
         return json.load(f)
@@ -242,8 +270,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = init_nccl(local_rank)
 
     t_setup = time.time()
     paths = workload_files(N_MARKERS, "r%d" % rank)
@@ -301,9 +328,11 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             # N > 1: the replicates' tables are merged (LODscores::merge_results as MAX / SUM-of-exp / SUM all-reduces
             # over NCCL) at the end of EVERY step, inside the timed region
+            chain.sync()                                   # (so that merge_ms_per_step is the merge, not the step's tail)
             t1 = time.perf_counter()
             cnt = chain.lodscore_read_ptr(pinned_lod.data_ptr())
             merged[0] = sdist.merge_lod(pinned_lod.to("cuda", non_blocking=True), cnt)
+            torch.cuda.synchronize()
             merge_s[0] += time.perf_counter() - t1
         return start_it + SCORING_PERIOD
 
@@ -688,21 +717,6 @@ def run_small_reference(args, rank):
     print(json.dumps(line))
 
 
-class quiet_stdout(object):
-    """the host classes print what the reference prints (starting likelihood, P(T), ...) on file descriptor 1; the bench
-    line must be the only thing on stdout"""
-
-    def __enter__(self):
-        sys.stdout.flush()
-        self.saved = os.dup(1)
-        self.null = os.open(os.devnull, os.O_WRONLY)
-        os.dup2(self.null, 1)
-
-    def __exit__(self, *a):
-        os.dup2(self.saved, 1)
-        os.close(self.saved); os.close(self.null)
-
-
 def run_small_ours(args, rank, world, local_rank):
     """one of the reference's example pedigrees through the host API the `swift` command line drives
     (swiftlink::run_replicates, csrc/host/gpu.cc): every replicate chain on the device, all of them in flight at once"""
@@ -740,8 +754,7 @@ def run_small_ours(args, rank, world, local_rank):
         secs += max(t - t_setup, 1e-9)
     clock_info = clocks.stop()
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = init_nccl(local_rank)
         t = torch.tensor([secs], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t.item())
@@ -850,8 +863,7 @@ def run_c4(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = init_nccl(local_rank)
     paths = workload_files(N_MARKERS, "c4r%d" % rank)
     hst = H.Host(*paths, lodscores=N_LOD)
     assert hst.set_peel_by_names(load_order()["order"]), "committed elimination order rejected"
