@@ -214,11 +214,11 @@ static bool emit_program(const slk_problem& pb, const HostPlan& hp, bool trait, 
     // one-warp team also needs no block-level barrier.  Measured on B200, 200-member pedigree, ms per L-sweep:
     // 12 x 32 threads 3.05, 8 x 64 3.22, 6 x 64 3.58, 5 x 128 3.90, 3 x 128 4.38, 3 x 192 4.54, 3 x 256 5.23.
     if(hybrid) team = 32;
-    // The trait program writes and reads every matrix once per unit, all of it in the global slab: what matters most is
-    // that the slab of all resident teams stays in L2 (126 MB).  Six teams of three warps per SM keep it there (888
-    // teams x 115 KB on the 200-member pedigree) where twelve one-warp teams spill 15 GB per pass to HBM.  Measured on
-    // B200, ms per scoring pass: 6 x 96 threads 12.30, 6 x 64 12.45, 5 x 128 12.83, 8 x 64 13.06, 5 x 96 13.61,
-    // 4 x 128 14.28, 3 x 192 14.50, 3 x 256 15.54, 12 x 32 15.94, 4 x 64 16.00.
+    // The trait program writes and reads every matrix once per unit, all of it in the global slab.  Six teams of three
+    // warps per SM halve the slab of the resident teams (888 x 115 KB on the 200-member pedigree; ncu: 10.9 GB of DRAM
+    // traffic per pass against 15.3 GB) and are faster than twelve one-warp teams.  Measured on B200, ms per scoring pass:
+    // 6 x 96 threads 12.30, 6 x 64 12.45, 5 x 128 12.83, 8 x 64 13.06, 5 x 96 13.61, 4 x 128 14.28, 3 x 192 14.50,
+    // 3 x 256 15.54, 12 x 32 15.94, 4 x 64 16.00.
     if(hybrid && trait) team = 96;
     team = env_int(trait ? "SLK_LOD_TEAM" : "SLK_LS_TEAM", team);
     if(slk_max_cta(team) == 0) team = 128;
