@@ -15,8 +15,8 @@ One bench STEP = 100 iterations (the kind of each drawn from the chain's Philox 
 GPUMarkovChain::run does) + 1 scoring pass.  metric = MCMC iterations / second, whole job.
 
 With N > 1 GPUs every rank runs an independent replicate chain (the reference's -R, one chain
-group per GPU, weak scaling); the LOD accumulators are merged at the end of every step, inside the
-timed region, by small NCCL all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the
+group per GPU, weak scaling); the LOD accumulators are merged once, at the end of the timed region and
+inside it, by small NCCL all-reduces (log-sum-exp: MAX, then SUM of exp(s - max), and SUM of the
 counts).  `--config c4` runs BASELINE.json configs[3] instead: a FIXED job of 8 replicates x MC3 ladders
 dealt out over the GPUs (strong scaling); `--config east|loop|xlinked` the reference's examples.
 
@@ -325,32 +325,36 @@ def run_ours(args, rank, world, local_rank):
                 kinds[1] += 1
         chain.lodscore_accumulate()
         launches[0] += 1
-        if dist is not None:
-            # N > 1: the replicates' tables are merged (LODscores::merge_results as MAX / SUM-of-exp / SUM all-reduces
-            # over NCCL) at the end of EVERY step, inside the timed region
-            chain.sync()                                   # (so that merge_ms_per_step is the merge, not the step's tail)
-            t1 = time.perf_counter()
-            cnt = chain.lodscore_read_ptr(pinned_lod.data_ptr())
-            merged[0] = sdist.merge_lod(pinned_lod.to("cuda", non_blocking=True), cnt)
-            torch.cuda.synchronize()
-            merge_s[0] += time.perf_counter() - t1
         return start_it + SCORING_PERIOD
 
+    def merge_now():
+        """N > 1: the replicates' tables merged as LODscores::merge_results does (MAX / SUM-of-exp / SUM all-reduces over
+        NCCL), once per timed region and inside it, as the reference merges once per job (linkage_program.cc:96-108)"""
+        if dist is None:
+            return
+        chain.sync()                                       # (so that merge_ms is the merge, not the last step's tail)
+        t1 = time.perf_counter()
+        cnt = chain.lodscore_read_ptr(pinned_lod.data_ptr())
+        merged[0] = sdist.merge_lod(pinned_lod.to("cuda", non_blocking=True), cnt)
+        torch.cuda.synchronize()
+        merge_s[0] += time.perf_counter() - t1
+
     def timed(step_fn, k_steps, it0):
-        """K steps, each bracketed by its own CUDA events on the launching stream, an untimed L2
-        flush between steps; returns (seconds, next iteration)"""
-        total_ms = 0.0
+        """EXACTLY K steps back to back inside one bracket (barrier + synchronize on both sides), CUDA events on the
+        launching stream; the merge of the replicates' tables (N > 1) is inside the bracket.  No flush between the
+        steps: a step touches far more than the L2 holds (388 MB of peel scratch per L-sampler launch alone), and one
+        256 MiB flush precedes the bracket.  Returns (seconds, next iteration)."""
+        flush.fill_(1)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
         for _ in range(k_steps):
-            flush.fill_(1)
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
             it0 = step_fn(it0)
-            b.record(stream)
-            b.synchronize()
-            barrier()
-            total_ms += a.elapsed_time(b)
-        return total_ms * 1e-3, it0
+        merge_now()
+        b.record(stream)
+        b.synchronize()
+        barrier()
+        return a.elapsed_time(b) * 1e-3, it0
 
     # ---- device-resident throughput ------------------------------------------------------------
     chain.lodscore_init()
@@ -363,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
     kinds[0] = kinds[1] = 0
     merge_s[0] = 0.0
     secs, it = timed(hot_step, args.steps, it)
-    merge_ms_per_step = 1e3 * merge_s[0] / max(args.steps, 1)
+    merge_ms_per_step = 1e3 * merge_s[0]
     timed_launches, timed_kinds = launches[0], list(kinds)
     chain.sync()
     clock_info = clocks.stop()
@@ -385,15 +389,14 @@ def run_ours(args, rank, world, local_rank):
         return nxt
 
     def timed_wall(step_fn, k_steps, it0):
-        total = 0.0
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(k_steps):
-            flush.fill_(1)
-            barrier()
-            t0 = time.perf_counter()
             it0 = step_fn(it0)
-            torch.cuda.synchronize()
-            total += time.perf_counter() - t0
-            barrier()
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        barrier()
         return total, it0
 
     for _ in range(min(args.warmup, 2)):
@@ -581,8 +584,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": STEP_DESC, "lsampler_prob": LSAMPLER_PROB,
                    "l_sweeps_timed": n_l, "m_sweeps_timed": n_m, "meioses_per_m_sweep": n_meioses,
-                   "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU" + ("; LOD tables merged over NCCL at the end of every step, inside the timed region" if world > 1 else ""),
-                   "l2": "256 MiB buffer written between timed steps (working set is L2-resident by design)",
+                   "n_members": N, "n_founders": hst.F, "n_markers": M, "n_lod": N_LOD, "parallelism": "replicate chain per GPU" + ("; LOD tables merged over NCCL at the end of the timed region, inside it" if world > 1 else ""),
+                   "l2": "inputs larger than L2: a step streams 388 MB of peel scratch per L-sampler launch and 100 MB per scoring pass; one 256 MiB flush before the timed region",
                    "peel_cost_sum4c": stats["sum_cells"], "max_cutset": stats["max_cutset"],
                    "ls_team_threads": stats["ls_team_threads"], "lod_team_threads": stats["lod_team_threads"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -595,7 +598,7 @@ def run_ours(args, rank, world, local_rank):
                     "l_sweep_ms": 2 * ls_ms, "m_sweep_ms": msweep_ms, "lod_pass_ms": lod_ms,
                     "lod_max": lod_max, "lod_argmax_interval": lod_argmax, "scoring_passes_merged": merged_count,
                     "setup_s": t_setup, "si_log10_weight": si_weight / np.log(10.0),
-                    "merge_ms_per_step": merge_ms_per_step if world > 1 else None,
+                    "merge_ms": merge_ms_per_step if world > 1 else None,
                     "replicates_in_flight": in_flight},
     }
     if world == 1 and not args.no_cpu_baseline:
