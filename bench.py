@@ -598,7 +598,7 @@ def run_ours(args, rank, world, local_rank):
                     "l_sweep_ms": 2 * ls_ms, "m_sweep_ms": msweep_ms, "lod_pass_ms": lod_ms,
                     "lod_max": lod_max, "lod_argmax_interval": lod_argmax, "scoring_passes_merged": merged_count,
                     "setup_s": t_setup, "si_log10_weight": si_weight / np.log(10.0),
-                    "merge_ms": merge_ms_per_step if world > 1 else None,
+                    "merge_ms_incl_wait_for_slowest_rank": merge_ms_per_step if world > 1 else None,
                     "replicates_in_flight": in_flight},
     }
     if world == 1 and not args.no_cpu_baseline:
