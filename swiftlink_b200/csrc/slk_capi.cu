@@ -500,6 +500,11 @@ int slk_lsampler_window(slk_chain* c, uint64_t iteration, int window_length, int
     c->ms_cur_valid = false;
     const int tpc = d.ls.cta_threads / d.ls.team_threads;
     const int grid = grid_for(L.nunits, tpc, p->ls_blocks_per_sm, p->sm_count);
+    static const bool no_ticket = getenv("SLK_LS_NO_TICKET") != 0;          // tuning aid
+    if(d.ls.team_threads == 32 && !no_ticket) {
+        L.ticket = c->err + 2;                                                // err[2]: the launch's unit counter
+        CU(cudaMemsetAsync(L.ticket, 0, sizeof(int), c->stream));
+    }
     launch_ls_by_team(d.ls.team_threads, L, grid, d.ls.cta_threads, p->ls_cta_smem, c->stream);
     CU(cudaGetLastError());
     return SLK_OK;

@@ -45,6 +45,7 @@ struct SlkLaunch {
     double* lod;                 // [(M-1)*nlod] log-sum accumulators
     double* gscratch;            // global arena slab: teams x (arena_doubles - smem_doubles)
     int* err;                    // [0] first error code, [1] unit
+    int* ticket;                 // sampler: next unit of the launch (zeroed by the host before the launch), or NULL
     uint64_t seed;
     uint64_t iteration;
     uint32_t chain;
@@ -205,7 +206,16 @@ __global__ void __launch_bounds__(MAXCTA, 1) slk_lsampler_kernel(const SlkLaunch
     const uint64_t iteration = L.iteration + (uint64_t)(si_batch ? graph : 0);
     const int si_start = si_batch ? L.si_starts[graph] : L.si_start;
     double* const si_weight = L.dump_result ? L.dump_result + (si_batch ? graph : 0) : (double*) 0;
-    for(int unit = si_batch ? 0 : gteam; unit < L.nunits; unit += (si_batch ? 1 : total_teams)) {
+    // One-warp teams take the next locus of the launch from a ticket counter (a team that drew cheap loci -- few legal
+    // genotypes -- comes back sooner); larger teams and the sequential walks stride statically.
+    const bool ticketed = T == 32 && L.ticket != 0 && !si_batch && si_start < 0;
+    auto next_unit = [&](int prev) -> int {
+        if(!ticketed) return prev + (si_batch ? 1 : total_teams);
+        int u = 0;
+        if(lane == 0) u = atomicAdd(L.ticket, 1);
+        return __shfl_sync(0xffffffffu, u, 0);
+    };
+    for(int unit = ticketed ? next_unit(0) : (si_batch ? 0 : gteam); unit < L.nunits; unit = next_unit(unit)) {
         int locus = L.offset + unit * L.window;
         bool ign_left = L.ignore_left != 0, ign_right = L.ignore_right != 0;
         if(si_start >= 0) {
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(MAXCTA, 1) slk_lsampler_kernel(const SlkLaunch
         const int plocus = L.period ? locus % L.period : locus;          // row of the plan tables
         const bool has_left = (plocus != 0), has_right = (plocus != (L.period ? L.period : M) - 1);
 
-        const bool tracing = L.trace != 0 && gteam == 0 && unit == gteam && tid == 0;
+        const bool tracing = L.trace != 0 && gteam == 0 && unit == gteam && tid == 0 && !ticketed;
         int tstamp = 0;
         if(tracing) L.trace[tstamp++] = clock64();
         // ---- stage: genotype codes, neighbouring descent-graph rows, thetas, founder priors
