@@ -943,7 +943,9 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
     const int np = (n + 1) / 2;
     std::vector<MsSnapPlan> snaps((size_t) np);
     std::vector<std::vector<uint32_t> > masks;
-    if(snap_k > 0 && run_ahead == 2 && !no_overlap) {
+    static const bool snap_forced = getenv("SLK_MS_SNAPSHOT") != 0;
+    // (a short walk is not worth saving, unless the tuning aid asks for it: the tests do, on the small pedigrees)
+    if(snap_k > 0 && run_ahead == 2 && !no_overlap && (snap_forced || c->plan->dev.ms.n_typed >= 32)) {
         const slk::HostPlan& hp = c->plan->host;
         const int W = hp.ms_W, nt = c->plan->dev.ms.n_typed, F = c->plan->dev.F;
         masks.reserve((size_t) np / snap_k + 1);
