@@ -960,7 +960,7 @@ int slk_msampler_sweep(slk_chain* c, uint64_t iteration) {
                 }
             int held = 0;
             for(int k = 0; k < nt; ++k) if(((m[k >> 4] >> (2 * (k & 15))) & 3u) == 0) ++held;
-            if(held < 8) continue;                                   // not worth a snapshot
+            if(held < (snap_forced ? 1 : 8)) continue;               // not worth a snapshot
             masks.push_back(m);
             const int buf = (s / snap_k) & 1;
             snaps[s].build = buf; snaps[s].build_mask = &masks.back();
