@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def main():
     tag, reps = sys.argv[1], sys.argv[2:]
     out = {"_source": "per launch, from the ncu --set full --clock-control none captures of the 200-member x 10k-SNP workload "
-                      "summarised in profiles/%s_summary.md (raw pages: profiles/%s_*_raw.csv)" % (tag, tag),
+                      "summarised in profiles/%s_final_summary.md (raw pages: profiles/%s_*_raw.csv)" % (tag, tag),
            "_issue_active_pct": {}, "_fp64_pipe_pct": {}, "_warp_inst_per_launch": {}, "_launch_us_under_ncu": {},
            "_issue_source": "smsp__issue_active.avg.pct_of_peak_sustained_active, sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active, "
                             "smsp__inst_executed.sum of the same captures"}
