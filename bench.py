@@ -960,7 +960,7 @@ def main():
                          "east / loop / xlinked: the reference's example pedigrees (configs[0], [1], [4]); c4: configs[3], a fixed "
                          "job of 8 replicates x MC3 ladders over --gpus GPUs (strong scaling, NCCL merges inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-step-seconds", type=float, default=5.0,
+    ap.add_argument("--ref-step-seconds", type=float, default=10.0,
                     help="--impl reference: size of the bounded sample one step times (seconds of CPU work, approximately)")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="also time this many replicate chains in flight on one GPU (derived.replicates_in_flight; 1 = skip)")
