@@ -23,9 +23,10 @@
 //                                phase B  the labels of the typed people are compacted and the label
 //                                         array is overlaid by the component tables;
 //                                phase C  the reference's walk over the typed people, as a disjoint-set
-//                                         forest with parity bits instead of its relabelling loops.
+//                                         forest over the founder alleles with parity bits instead of its
+//                                         relabelling loops (ms_walk).
 //                              Every factor of the likelihood is the major or the minor allele frequency
-//                              of the locus, so a component carries two small exponents, not two doubles,
+//                              of the locus, so a component carries two small counts, not two doubles,
 //                              and the kernel returns ln L = A ln(major) + B ln(minor) + sum over unfixed
 //                              components of ln(1 + (minor/major)^d): exact integer bookkeeping, one
 //                              rounding step at the end (<= 1e-13 relative on L; north_star allows 1e-9).
@@ -34,8 +35,11 @@
 //                              outcomes of step j -- so two steps cost one likelihood latency.
 //   slk_ms_step_kernel         the same likelihood incrementally (only the labels a hypothesis can change are
 //                              re-derived), used for every step of a sweep; launched with programmatic stream
-//                              serialisation, it walks the typed people the previous pair's chain kernel cannot
-//                              affect while that kernel is still sampling, then waits for it and walks the rest.
+//                              serialisation.  Two of these launches are in flight: a launch starts once the chain
+//                              kernel before the previous one has completed, walks the typed people the last two
+//                              pairs cannot affect, waits for its predecessor and walks the rest.  Every fourth
+//                              launch also saves the forest over the people no meiosis of the next launches can
+//                              affect (a snapshot); those launches start their walks from it.
 //   slk_ms_chain_kernel        one 8-CTA cluster, one or two steps.  (2) is a product of 2x2 non-negative
 //                              matrices diag(raw_i) * T(theta_{i-1}): every thread multiplies the matrices
 //                              of its chunk of loci, a scan over threads / warps / CTAs (distributed
@@ -99,7 +103,7 @@ struct SlkMsLaunch {
     uint32_t chain;
     int32_t* dump_edges;         // optional [M][2N] (set 0)
     long long* trace;            // optional: clock64() stamps (tuning aid), see slk_debug_msampler_trace
-    unsigned long long* timeline;// optional: %globaltimer stamps of CTA 0, 8 per launch (tuning aid, SLK_MS_TIMELINE)
+    unsigned long long* timeline;// optional: %globaltimer stamps of CTA 0, 8 per launch (slk_debug_msampler_timeline)
     int tl_slot, tl_cta_off;     // tl_cta_off > 0: also (start, end) of every CTA of this launch at timeline[tl_cta_off + 2 * cta]
     double* out;                 // dg likelihood: [0] = sum ln(lik), [1] = recombination term
     const double* log_theta;
@@ -141,9 +145,8 @@ __device__ __forceinline__ void ms_st32(uint32_t a, uint32_t v) { asm volatile("
 // Host and device agree on the carve-up through this function.  Per thread, in bytes:
 //   keep     te (labels of typed people, 2*nt entries of E bytes) | obs (their genotypes, 2 bits each)
 //   overlay  phase A: labels (2(N-F) entries of E bytes, founders are implicit) | graph row (N bytes)
-//            phase C: grp (G words, 2 words if wide) | fa (2F x u16)
-// E = 1 if 2F <= 256 else 2 ("wide"); G = min(nt, 2F) components at most (each one is created by a
-// typed person and claims at least one founder allele).
+//            phase C: grp (G node words, a second word each if wide)
+// E = 1 if 2F <= 256 else 2 ("wide"); G = 2F: one disjoint-set node per founder allele (ms_walk).
 struct MsLayout {
     int wide;
     int G;
@@ -541,7 +544,7 @@ slk_ms_likelihood_kernel(const SlkMsLaunch L) {
 // where stale[l] collects the slots invalidated by indicators the chain kernel has flipped at this locus since
 // te was last brought up to date; the set-0 thread of the locus writes those entries back at the end of its
 // work and the chain kernel clears the mask before it records new flips.  No per-thread label array, no
-// graph-row or genotype staging: 24 KB of shared memory per warp instead of 31.
+// graph-row or genotype staging: 16 KB of shared memory per warp instead of 31.
 struct MsStepLayout {
     int wide, G;
     uint32_t grp, cnt, fa, hmask;    // per-thread byte offsets (multiply by 32 lanes)
