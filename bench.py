@@ -171,7 +171,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     t0 = time.time()
-    value, info = reference_measure(args.steps, args.warmup, N_MARKERS, target_step_s=args.ref_step_seconds)
+    # the whole run (set-up about 40 s + warm-up and timed steps) has to end within a few minutes whatever --steps is
+    step_s = min(args.ref_step_seconds, 120.0 / max(args.steps + args.warmup, 1))
+    value, info = reference_measure(args.steps, args.warmup, N_MARKERS, target_step_s=step_s)
     if value is None:
         print(json.dumps({"impl": "reference", "unavailable": info["error"]}))
         return
